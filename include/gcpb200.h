@@ -1,0 +1,118 @@
+/* gcpb200.h -- C ABI of the B200-native GCP-tree CEM rollout library (libgcpb200.so).
+ *
+ * This is the drop-in boundary: each entry point replaces one piece of the reference's Python hot path
+ * (paths relative to the reference repository orybkin/video-gcp):
+ *
+ *   gcpb200_rollout        BaseGCPModel.forward in val_mode, i.e. run_encoder + get_end_ind +
+ *                          TreeModel.predict_sequence + run_auxilliary_models
+ *                          (gcp/prediction/models/base_gcp.py:140-161,184-262,
+ *                           gcp/prediction/models/tree/tree.py:42-67)
+ *   gcpb200_prune_gather   BalancedEvalBinding.get_all_samples / __call__ + pad_sequence
+ *                          (gcp/evaluation/evaluation_matching.py:174-206; base_gcp.py:361-374,242)
+ *   gcpb200_cost_l2        L2ImageCost._compute + CostFcn.__call__ (gcp/planning/cem/cost_fcn.py:9-22,65-72)
+ *   gcpb200_cost_learned   ImageWrappedLearnedCostFcn / LearnedCostEstimate list branch
+ *                          (gcp/planning/cem/cost_fcn.py:79-116) with TestTimeCostModel.forward
+ *                          (gcp/prediction/models/auxilliary_models/cost_mdl.py:138-145)
+ *   gcpb200_topk           CEMPlanner._get_best_rollouts argsort + slice (gcp/planning/cem/cem_planner.py:124-135)
+ *   gcpb200_refit          FlatCEMSampler.fit (gcp/planning/cem/sampler.py:44-46)
+ *   gcpb200_sample_noise   FlatCEMSampler.sample (gcp/planning/cem/sampler.py:40-42), on device
+ *
+ * Conventions: plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name says
+ * host; the caller owns all I/O buffers, the context owns packed weights and workspace; every call is
+ * stream-ordered on `stream` (a cudaStream_t passed as void*) and never synchronises the device; return
+ * value 0 = success, non-zero = error with the message available from gcpb200_last_error(); no C++
+ * exception crosses this boundary.  One context per (device, host thread).
+ */
+#ifndef GCPB200_H
+#define GCPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcpb200_ctx gcpb200_ctx;
+
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    int max_candidates;  /* largest B of one rollout call (workspace is sized for it, rounded up to 128) */
+    int attach_cost_mdl; /* 1: expect cost_mdl.cost_pred.* weights (learned cost available) */
+    int use_ref_kernels; /* 1: verification mode, SIMT kernels instead of tcgen05 (tests only) */
+    int decoder_slot_chunk; /* decoder processes this many tree slots per pass (0 = default 64) */
+} gcpb200_config;
+
+/* one fp32 host tensor of the reference state dict */
+typedef struct {
+    const char* name;   /* reference state-dict key */
+    const float* data;  /* HOST pointer, contiguous fp32 */
+    int ndim;
+    int64_t shape[4];
+} gcpb200_tensor;
+
+typedef struct {
+    /* ---- inputs ---- */
+    const float* I_0;        /* [B,3,32,32] (or [1,3,32,32] if images_shared) fp32 in [-1,1] */
+    const float* I_g;
+    int images_shared;       /* 1: every candidate has the same start/goal image (a CEM call) */
+    const float* z;          /* [B,255,256] noise, depth-first node order */
+    const int64_t* end_ind;  /* [B] injected rollout length, or NULL: sample from the length predictor */
+    uint64_t seed;           /* RNG seed for length sampling */
+    int B;
+    /* ---- outputs (any may be NULL) ---- */
+    float* e_0;              /* [B,128] */
+    float* e_g;              /* [B,128] */
+    float* seq_len_logits;   /* [B,200] */
+    int64_t* end_ind_out;    /* [B] */
+    float* e_df;             /* [B,255,128] node latents, depth-first (tree.df.e_g_prime) */
+    float* mu_df;            /* [B,255,256] prior mean */
+    float* log_sigma_df;     /* [B,255,256] prior log sigma */
+    float* images_df;        /* [B,255,3,32,32] decoded node images (tree.df.images) */
+    float* existence;        /* [B,255] existence-predictor logits */
+    float* model_enc_seq;    /* [B,200,128] pruned latents, zero padded */
+    float* actions;          /* [B,200,2] inverse model on consecutive pruned latents (use [:, :Lmax-1]) */
+    float* regressed_state;  /* [B,200,2] state regressor (use [:, :Lmax]) */
+} gcpb200_rollout_io;
+
+const char* gcpb200_last_error(void);
+const char* gcpb200_version(void);
+
+int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg);
+void gcpb200_destroy(gcpb200_ctx* ctx);
+
+/* Packs the reference weights for the kernels: centre taps of the 3x3 "MLP" convs, eval-BatchNorm folded,
+ * [W_ih|W_hh] concatenated and gate-interleaved, up-sample+pad+conv composites, bf16, K-major. */
+int gcpb200_load_weights(gcpb200_ctx* ctx, const gcpb200_tensor* tensors, int n_tensors);
+
+int gcpb200_rollout(gcpb200_ctx* ctx, const gcpb200_rollout_io* io, void* stream);
+
+/* dst[c,t,:] = src[c, node_of_frame(c,t), :] for t <= end_ind[c], zeros after.  row_len % 4 == 0. */
+int gcpb200_prune_gather(gcpb200_ctx* ctx, const float* src_df, const int64_t* end_ind, int B, int row_len,
+                         float* dst /* [B,200,row_len] */, void* stream);
+
+/* goal: [3,32,32] in [-1,1].  dense != 0: sum over frames, else last frame only. */
+int gcpb200_cost_l2(gcpb200_ctx* ctx, const float* images_df, const int64_t* end_ind, const float* goal, int B,
+                    int dense, float final_step_weight, float* cost /* [B] */, void* stream);
+
+/* cost[c] = sum over consecutive pairs of cat(latents of c, goal_seq) of the learned pairwise cost. */
+int gcpb200_cost_learned(gcpb200_ctx* ctx, const float* e_df, const int64_t* end_ind, int B,
+                         const float* goal_seq /* [Lg,128] */, int Lg, float* cost /* [B] */, void* stream);
+
+/* indices (and values) of the k lowest costs in ascending order; ties broken by index. */
+int gcpb200_topk(gcpb200_ctx* ctx, const float* cost, int N, int k, int32_t* idx /* [k] */, float* val /* [k] or NULL */,
+                 void* stream);
+
+int gcpb200_refit(gcpb200_ctx* ctx, const float* z /* [N,255,256] */, const int32_t* elite_idx, int k,
+                  float* mean /* [255*256] */, float* std /* [255*256] */, void* stream);
+
+/* z[c] = clip(mean + std * n(seed, first_candidate_id + c)); mean/std NULL -> 0 / std_scalar. */
+int gcpb200_sample_noise(gcpb200_ctx* ctx, const float* mean, const float* std, float std_scalar, uint64_t seed,
+                         uint64_t first_candidate_id, int B, float clip, float* z /* [B,255,256] */, void* stream);
+
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t gcpb200_launch_count(gcpb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCPB200_H */

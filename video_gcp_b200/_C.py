@@ -1,0 +1,76 @@
+"""ctypes binding of libgcpb200.so (the C ABI declared in include/gcpb200.h).
+
+The library is built in-tree (`python -c "import __graft_entry__ as g; g.build()"` or `make -C
+video_gcp_b200/csrc`).  There is NO fallback: if the shared library is missing, `load()` raises.
+"""
+import ctypes as C
+import os
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgcpb200.so")
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_candidates", C.c_int), ("attach_cost_mdl", C.c_int),
+                ("use_ref_kernels", C.c_int), ("decoder_slot_chunk", C.c_int)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4)]
+
+
+class RolloutIO(C.Structure):
+    _fields_ = [("I_0", C.c_void_p), ("I_g", C.c_void_p), ("images_shared", C.c_int), ("z", C.c_void_p),
+                ("end_ind", C.c_void_p), ("seed", C.c_uint64), ("B", C.c_int),
+                ("e_0", C.c_void_p), ("e_g", C.c_void_p), ("seq_len_logits", C.c_void_p),
+                ("end_ind_out", C.c_void_p), ("e_df", C.c_void_p), ("mu_df", C.c_void_p),
+                ("log_sigma_df", C.c_void_p), ("images_df", C.c_void_p), ("existence", C.c_void_p),
+                ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "gcpb200_last_error": (C.c_char_p, []),
+    "gcpb200_version": (C.c_char_p, []),
+    "gcpb200_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config)]),
+    "gcpb200_destroy": (None, [C.c_void_p]),
+    "gcpb200_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_int]),
+    "gcpb200_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutIO), C.c_void_p]),
+    "gcpb200_prune_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gcpb200_cost_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                  C.c_void_p, C.c_void_p]),
+    "gcpb200_cost_learned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p]),
+    "gcpb200_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gcpb200_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gcpb200_sample_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_uint64,
+                                       C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "gcpb200_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+
+class GcpB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and set the prototypes of every exported symbol."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise GcpB200Error(
+            "libgcpb200.so not found at %s -- build it first (`make -C video_gcp_b200/csrc` or "
+            "`__graft_entry__.build()`); this package has no CPU or PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)            # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GcpB200Error(load().gcpb200_last_error().decode())

@@ -1,0 +1,989 @@
+// libgcpb200: context, weight packing and the rollout schedule behind the C ABI in include/gcpb200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gcpb200.h"
+#include "dec_tail.cuh"
+#include "gemm_host.cuh"
+#include "kernels_misc.cuh"
+
+using namespace gcp;
+
+// ---------------------------------------------------------------------------------------------
+// error reporting
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+extern "C" void gcp_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* gcpb200_last_error(void) { return g_err; }
+extern "C" const char* gcpb200_version(void) { return "gcpb200 0.1.0 (sm_100a)"; }
+
+#define CHECK(x)             \
+    do {                     \
+        if ((x) != 0) return -1; \
+    } while (0)
+
+// model dimensions of the 25-room GCP-tree (experiments/control/25room/gcp_tree/mod_hyper.py:33-54)
+static const int DEPTH = 8, N_NODES = 255, N_SLOTS = 257;
+static const int NZ_ENC = 128, NZ_VAE = 256, NZ_MID = 128, HID = 512, N_LSTM = 3, STATE = 3072;
+static const int MAX_LEN = 200, INIT_MID = 32;
+
+// ---------------------------------------------------------------------------------------------
+// device containers
+// ---------------------------------------------------------------------------------------------
+struct DevMat {           // packed weight matrix [N][K] bf16 (K-major) + fp32 bias in packed column order
+    bf16* w = nullptr;
+    float* bias = nullptr;
+    int N = 0, K = 0;
+    CUtensorMap map128, map256;
+};
+struct DevBuf {           // bf16 activation array [rows][ld] with a TMA map over its full extent
+    bf16* p = nullptr;
+    size_t rows = 0;
+    int ld = 0;
+    CUtensorMap map;
+};
+struct Mlp {              // BaseProcessingNet: in(+bias,LReLU) -> 3x[lin, GroupNorm(8), LReLU] -> head(+bias)
+    DevMat in, mid[3], head;
+    float* gam[3] = {nullptr, nullptr, nullptr};
+    float* bet[3] = {nullptr, nullptr, nullptr};
+    int gn_group = 16;    // channels per group
+    int mid_k = 128;      // K of the mid/head layers (mid width padded to 64)
+    int mid_valid = 128;  // columns written by in/mid layers
+    int n_out = 0;
+};
+struct LevelW {
+    Mlp prior;
+    Mlp init;             // level 0 only; head rows [0,3072) -> left state, [3072,6144) -> right state
+    DevMat init_head_r;   // second half of the init head
+    DevMat proj, embed_main, embed_ctx, lstm[3], out;
+};
+
+struct gcpb200_ctx {
+    gcpb200_config cfg;
+    int Bp_max = 0, sms = 0, slot_chunk = 64;
+    bool use_ref = false, weights_loaded = false;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    // weights
+    LevelW lvl[8];
+    Mlp length_pred, existence, inv_mdl, state_reg, cost_mdl;
+    bool has_cost = false;
+    EncoderWeights enc;
+    DevMat dec1, dec2x, dec2s, dec3;
+    bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr;
+    float *b4 = nullptr, *b5 = nullptr;
+    // workspace
+    float* lat_f32 = nullptr;
+    DevBuf lat, hid, xa, xb, zeta, sh, ta, tb, s2b, x1, x2, x3, pairs;
+    float *sc = nullptr, *ctxb = nullptr, *logits = nullptr, *s0 = nullptr, *s2 = nullptr, *rowbias2 = nullptr;
+    bf16* skip_up = nullptr;
+    float *exist_slot = nullptr, *e_df = nullptr, *seq = nullptr, *rowcost = nullptr, *goal_tail = nullptr;
+    long long* end_ind = nullptr;
+    long long* scratch_ei = nullptr;
+    int* frame_node = nullptr;
+};
+
+template <class T>
+static int dalloc(gcpb200_ctx* c, T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) {
+        gcp_set_error("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        return -1;
+    }
+    if (zero) cudaMemset(q, 0, n * sizeof(T));
+    c->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+static int make_buf(gcpb200_ctx* c, DevBuf* b, size_t rows, int ld) {
+    b->rows = rows;
+    b->ld = ld;
+    CHECK(dalloc(c, &b->p, rows * ld));
+    return make_tmap_bf16(&b->map, b->p, rows, ld, ld, 128);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight access + packing (host)
+// ---------------------------------------------------------------------------------------------
+struct WStore {
+    std::map<std::string, const gcpb200_tensor*> m;
+    const gcpb200_tensor* get(const std::string& k, int ndim) const {
+        auto it = m.find(k);
+        if (it == m.end()) {
+            gcp_set_error("missing weight tensor '%s'", k.c_str());
+            return nullptr;
+        }
+        if (it->second->ndim != ndim) {
+            gcp_set_error("weight tensor '%s' has ndim %d, expected %d", k.c_str(), it->second->ndim, ndim);
+            return nullptr;
+        }
+        return it->second;
+    }
+};
+
+static int upload_mat(gcpb200_ctx* c, DevMat* d, int N, int K, const std::function<float(int, int)>& f,
+                      const std::function<float(int)>& bias) {
+    std::vector<bf16> h((size_t)N * K);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) h[(size_t)n * K + k] = __float2bfloat16(f(n, k));
+    d->N = N;
+    d->K = K;
+    CHECK(dalloc(c, &d->w, (size_t)N * K, false));
+    GCP_CUDA_CHECK(cudaMemcpy(d->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<float> hb(N, 0.f);
+    if (bias)
+        for (int n = 0; n < N; ++n) hb[n] = bias(n);
+    CHECK(dalloc(c, &d->bias, N, false));
+    GCP_CUDA_CHECK(cudaMemcpy(d->bias, hb.data(), N * 4, cudaMemcpyHostToDevice));
+    CHECK(make_tmap_bf16(&d->map128, d->w, N, K, K, 128));
+    if (N % 256 == 0) CHECK(make_tmap_bf16(&d->map256, d->w, N, K, K, 256));
+    return 0;
+}
+static int upload_f32(gcpb200_ctx* c, float** d, const std::vector<float>& h) {
+    CHECK(dalloc(c, d, h.size(), false));
+    GCP_CUDA_CHECK(cudaMemcpy(*d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int upload_f32(gcpb200_ctx* c, const float** d, const std::vector<float>& h) {
+    float* p;
+    CHECK(upload_f32(c, &p, h));
+    *d = p;
+    return 0;
+}
+
+// linear weight element (o,i) of a Predictor layer: centre tap for the conv builder
+struct Lin {
+    const float* w = nullptr;
+    const float* b = nullptr;
+    int O = 0, I = 0, stride = 1, off = 0;
+    float at(int o, int i) const { return (o < O && i < I) ? w[((size_t)o * I + i) * stride + off] : 0.f; }
+    float bias(int o) const { return (b != nullptr && o < O) ? b[o] : 0.f; }
+};
+static int get_lin(const WStore& ws, const std::string& prefix, bool conv, bool has_bias, Lin* l) {
+    const gcpb200_tensor* t = ws.get(prefix + (conv ? ".conv.weight" : ".linear.weight"), conv ? 4 : 2);
+    if (!t) return -1;
+    l->w = t->data;
+    l->O = (int)t->shape[0];
+    l->I = (int)t->shape[1];
+    l->stride = conv ? 9 : 1;   // [O][I][3][3]: centre tap (1,1) is the only one that touches a 1x1 map
+    l->off = conv ? 4 : 0;
+    l->b = nullptr;
+    if (has_bias) {
+        const gcpb200_tensor* b = ws.get(prefix + (conv ? ".conv.bias" : ".linear.bias"), 1);
+        if (!b) return -1;
+        l->b = b->data;
+    }
+    return 0;
+}
+
+// head_perm: packed row -> original row (or -1 for a zero row); null = identity
+static int pack_mlp(gcpb200_ctx* c, const WStore& ws, const std::string& prefix, bool conv, int d_in, int mid,
+                    int d_out, int head_N, const std::function<int(int)>& head_perm, Mlp* m, DevMat* head2 = nullptr,
+                    int head2_row0 = 0) {
+    Lin in, md[3], hd;
+    CHECK(get_lin(ws, prefix + ".input", conv, true, &in));
+    if (in.I != d_in || in.O != mid) {
+        gcp_set_error("%s.input: got [%d,%d], expected [%d,%d]", prefix.c_str(), in.O, in.I, mid, d_in);
+        return -1;
+    }
+    m->mid_k = mid < 64 ? 64 : mid;
+    m->mid_valid = m->mid_k;
+    m->gn_group = mid / 8;
+    m->n_out = d_out;
+    CHECK(upload_mat(c, &m->in, 128, d_in, [&](int n, int k) { return in.at(n, k); }, [&](int n) { return in.bias(n); }));
+    for (int i = 0; i < 3; ++i) {
+        const std::string p = prefix + ".pyramid-" + std::to_string(i);
+        CHECK(get_lin(ws, p, conv, false, &md[i]));
+        CHECK(upload_mat(c, &m->mid[i], 128, m->mid_k, [&](int n, int k) { return md[i].at(n, k); }, nullptr));
+        const gcpb200_tensor* g = ws.get(p + ".norm.weight", 1);
+        const gcpb200_tensor* b = ws.get(p + ".norm.bias", 1);
+        if (!g || !b) return -1;
+        std::vector<float> hg(128, 0.f), hb(128, 0.f);
+        for (int k = 0; k < mid; ++k) {
+            hg[k] = g->data[k];
+            hb[k] = b->data[k];
+        }
+        CHECK(upload_f32(c, &m->gam[i], hg));
+        CHECK(upload_f32(c, &m->bet[i], hb));
+    }
+    CHECK(get_lin(ws, prefix + ".head", conv, true, &hd));
+    if (hd.O != d_out) {
+        gcp_set_error("%s.head: got %d outputs, expected %d", prefix.c_str(), hd.O, d_out);
+        return -1;
+    }
+    auto orig = [&](int n) { return head_perm ? head_perm(n) : n; };
+    CHECK(upload_mat(c, &m->head, head_N, m->mid_k,
+                     [&](int n, int k) { int o = orig(n); return o < 0 ? 0.f : hd.at(o, k); },
+                     [&](int n) { int o = orig(n); return o < 0 ? 0.f : hd.bias(o); }));
+    if (head2 != nullptr)
+        CHECK(upload_mat(c, head2, head_N, m->mid_k, [&](int n, int k) { return hd.at(head2_row0 + n, k); },
+                         [&](int n) { return hd.bias(head2_row0 + n); }));
+    return 0;
+}
+
+// 1-D bilinear x2 matrix U[2n][n], align_corners=False (torch.nn.Upsample)
+static std::vector<double> up_matrix(int n) {
+    std::vector<double> U((size_t)2 * n * n, 0.0);
+    for (int o = 0; o < 2 * n; ++o) {
+        int i0, i1;
+        float w0, w1;
+        up2_src(o, n, i0, i1, w0, w1);
+        U[(size_t)o * n + i0] += w0;
+        U[(size_t)o * n + i1] += w1;
+    }
+    return U;
+}
+// Composite of bilinear x2 -> ZeroPad2d(1,2,1,2) -> conv k4 for one (co, ci) filter: dense [2n*2n][n*n]
+// matrix C[(oy,ox)][(iy,ix)] = sum_{ky,kx} w[ky][kx] U[oy+ky-1][iy] U[ox+kx-1][ix] (U = 0 outside [0,2n)).
+static void composite_filter(const float* w /*[4][4]*/, int n, const std::vector<double>& U, std::vector<double>& C) {
+    const int m = 2 * n;
+    std::vector<double> M((size_t)m * n * 4);   // M[oy][iy][kx] = sum_ky w[ky][kx] U[oy+ky-1][iy]
+    for (int oy = 0; oy < m; ++oy)
+        for (int iy = 0; iy < n; ++iy)
+            for (int kx = 0; kx < 4; ++kx) {
+                double s = 0;
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int u = oy + ky - 1;
+                    if (u >= 0 && u < m) s += (double)w[ky * 4 + kx] * U[(size_t)u * n + iy];
+                }
+                M[((size_t)oy * n + iy) * 4 + kx] = s;
+            }
+    C.assign((size_t)m * m * n * n, 0.0);
+    for (int oy = 0; oy < m; ++oy)
+        for (int ox = 0; ox < m; ++ox)
+            for (int iy = 0; iy < n; ++iy)
+                for (int ix = 0; ix < n; ++ix) {
+                    double s = 0;
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const int u = ox + kx - 1;
+                        if (u >= 0 && u < m) s += M[((size_t)oy * n + iy) * 4 + kx] * U[(size_t)u * n + ix];
+                    }
+                    C[(((size_t)oy * m + ox) * n + iy) * n + ix] = s;
+                }
+}
+
+struct BNFold {
+    std::vector<float> scale, shift;
+};
+static int fold_bn(const WStore& ws, const std::string& p, int C, BNFold* f) {
+    const gcpb200_tensor *w = ws.get(p + ".weight", 1), *b = ws.get(p + ".bias", 1), *rm = ws.get(p + ".running_mean", 1),
+                         *rv = ws.get(p + ".running_var", 1);
+    if (!w || !b || !rm || !rv) return -1;
+    f->scale.resize(C);
+    f->shift.resize(C);
+    for (int i = 0; i < C; ++i) {
+        const float s = w->data[i] / sqrtf(rv->data[i] + 1e-5f);
+        f->scale[i] = s;
+        f->shift[i] = b->data[i] - rm->data[i] * s;
+    }
+    return 0;
+}
+
+static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
+    const std::string p = "decoder.net.net.";
+    // ---- layer 1: ConvTranspose2d(128->64,k4) on a 1x1 map + BN + ReLU == Linear 128 -> 64*16
+    const gcpb200_tensor* w1 = ws.get(p + "net.conv.weight", 4);
+    if (!w1) return -1;
+    BNFold bn1, bn2, bn3;
+    CHECK(fold_bn(ws, p + "net.norm", 64, &bn1));
+    CHECK(upload_mat(c, &c->dec1, 1024, 128,
+                     [&](int n, int k) { return w1->data[((size_t)k * 64 + n / 16) * 16 + n % 16] * bn1.scale[n / 16]; },
+                     [&](int n) { return bn1.shift[n / 16]; }));
+    // ---- layer 2: cat(x1 64ch, skip 64ch) 4x4 -> up -> pad -> conv(128->32) -> BN -> ReLU, as dense maps
+    const gcpb200_tensor* w2 = ws.get(p + "pyramid-1.conv.weight", 4);
+    if (!w2) return -1;
+    CHECK(fold_bn(ws, p + "pyramid-1.norm", 32, &bn2));
+    {
+        const std::vector<double> U = up_matrix(4);
+        std::vector<float> Wx((size_t)2048 * 1024), Wsk((size_t)2048 * 1024);
+        std::vector<double> C;
+        for (int co = 0; co < 32; ++co)
+            for (int ci = 0; ci < 128; ++ci) {
+                composite_filter(w2->data + ((size_t)co * 128 + ci) * 16, 4, U, C);
+                std::vector<float>& dst = ci < 64 ? Wx : Wsk;
+                const int cil = ci & 63;
+                for (int o = 0; o < 64; ++o)
+                    for (int i = 0; i < 16; ++i)
+                        dst[(size_t)(co * 64 + o) * 1024 + cil * 16 + i] = (float)(C[(size_t)o * 16 + i] * bn2.scale[co]);
+            }
+        CHECK(upload_mat(c, &c->dec2x, 2048, 1024, [&](int n, int k) { return Wx[(size_t)n * 1024 + k]; }, nullptr));
+        CHECK(upload_mat(c, &c->dec2s, 2048, 1024, [&](int n, int k) { return Wsk[(size_t)n * 1024 + k]; },
+                         [&](int n) { return bn2.shift[n / 64]; }));
+    }
+    // ---- layer 3: 32ch 8x8 -> up -> pad -> conv(32->16) -> BN -> ReLU, dense; output in plane layout
+    const gcpb200_tensor* w3 = ws.get(p + "pyramid-0.conv.weight", 4);
+    if (!w3) return -1;
+    CHECK(fold_bn(ws, p + "pyramid-0.norm", 16, &bn3));
+    {
+        const std::vector<double> U = up_matrix(8);
+        std::vector<float> W3((size_t)4096 * 2048);
+        std::vector<double> C;
+        for (int co = 0; co < 16; ++co)
+            for (int ci = 0; ci < 32; ++ci) {
+                composite_filter(w3->data + ((size_t)co * 32 + ci) * 16, 8, U, C);
+                for (int o = 0; o < 256; ++o) {
+                    const size_t n3 = ((size_t)(co >> 3) * 256 + o) * 8 + (co & 7);
+                    for (int i = 0; i < 64; ++i) W3[n3 * 2048 + ci * 64 + i] = (float)(C[(size_t)o * 64 + i] * bn3.scale[co]);
+                }
+            }
+        CHECK(upload_mat(c, &c->dec3, 4096, 2048, [&](int n, int k) { return W3[(size_t)n * 2048 + k]; },
+                         [&](int n) { return bn3.shift[((n >> 3) / 256) * 8 + (n & 7)]; }));
+    }
+    // ---- layers 4, 5: packed for the implicit-GEMM kernel + plain copies for the verification kernel
+    const gcpb200_tensor* w4 = ws.get(p + "additional_conv_layer.conv.weight", 4);
+    const gcpb200_tensor* b4 = ws.get(p + "additional_conv_layer.conv.bias", 1);
+    const gcpb200_tensor* w5 = ws.get("decoder.net.gen_head.conv.weight", 4);
+    const gcpb200_tensor* b5 = ws.get("decoder.net.gen_head.conv.bias", 1);
+    if (!w4 || !b4 || !w5 || !b5) return -1;
+    {
+        std::vector<bf16> h4(DT_W4_BYTES / 2), h5(DT_W5_BYTES / 2), p4(16 * 32 * 16), p5(32 * 16 * 16);
+        for (int tap = 0; tap < 16; ++tap)
+            for (int ci = 0; ci < 32; ++ci)
+                for (int co = 0; co < 16; ++co) {
+                    const float v = w4->data[((size_t)co * 32 + ci) * 16 + tap];
+                    const int ks = ci >> 4, kc = (ci >> 3) & 1;
+                    h4[(size_t)(tap * 2 + ks) * 256 + kc * 128 + co * 8 + (ci & 7)] = __float2bfloat16(v);
+                    p4[((size_t)co * 32 + ci) * 16 + tap] = __float2bfloat16(v);
+                }
+        for (int tap = 0; tap < 16; ++tap)
+            for (int ci = 0; ci < 16; ++ci)
+                for (int co = 0; co < 32; ++co) {
+                    const float v = co < 30 ? w5->data[((size_t)co * 16 + ci) * 16 + tap] : 0.f;
+                    h5[(size_t)tap * 512 + (ci >> 3) * 256 + co * 8 + (ci & 7)] = __float2bfloat16(v);
+                    p5[((size_t)co * 16 + ci) * 16 + tap] = __float2bfloat16(v);
+                }
+        CHECK(dalloc(c, &c->w4, h4.size(), false));
+        CHECK(dalloc(c, &c->w5, h5.size(), false));
+        CHECK(dalloc(c, &c->w4p, p4.size(), false));
+        CHECK(dalloc(c, &c->w5p, p5.size(), false));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w4, h4.data(), h4.size() * 2, cudaMemcpyHostToDevice));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w5, h5.data(), h5.size() * 2, cudaMemcpyHostToDevice));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w4p, p4.data(), p4.size() * 2, cudaMemcpyHostToDevice));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w5p, p5.data(), p5.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<float> hb4(b4->data, b4->data + 16), hb5(32, 0.f);
+        for (int i = 0; i < 30; ++i) hb5[i] = b5->data[i];
+        CHECK(upload_f32(c, &c->b4, hb4));
+        CHECK(upload_f32(c, &c->b5, hb5));
+    }
+    return 0;
+}
+
+static int pack_encoder(gcpb200_ctx* c, const WStore& ws) {
+    const std::string p = "encoder.net.net.";
+    auto up = [&](const std::string& k, int ndim, const float** d) -> int {
+        const gcpb200_tensor* t = ws.get(k, ndim);
+        if (!t) return -1;
+        size_t n = 1;
+        for (int i = 0; i < ndim; ++i) n *= t->shape[i];
+        return upload_f32(c, d, std::vector<float>(t->data, t->data + n));
+    };
+    CHECK(up(p + "input.conv.weight", 4, &c->enc.w0));
+    CHECK(up(p + "input.conv.bias", 1, &c->enc.b0));
+    CHECK(up(p + "pyramid-0.conv.weight", 4, &c->enc.w1));
+    CHECK(up(p + "pyramid-1.conv.weight", 4, &c->enc.w2));
+    CHECK(up(p + "head.weight", 4, &c->enc.w3));
+    CHECK(up(p + "head.bias", 1, &c->enc.b3));
+    BNFold f1, f2;
+    CHECK(fold_bn(ws, p + "pyramid-0.norm", 32, &f1));
+    CHECK(fold_bn(ws, p + "pyramid-1.norm", 64, &f2));
+    CHECK(upload_f32(c, &c->enc.sc1, f1.scale));
+    CHECK(upload_f32(c, &c->enc.sh1, f1.shift));
+    CHECK(upload_f32(c, &c->enc.sc2, f2.scale));
+    CHECK(upload_f32(c, &c->enc.sh2, f2.shift));
+    return 0;
+}
+
+static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
+    LevelW& L = c->lvl[l];
+    const std::string tm = "tree_module.tree_modules." + std::to_string(l) + ".";
+    // prior head: packed row p = tile*256 + chunk*32 + part*16 + u  <->  part*256 + tile*128 + chunk*16 + u
+    auto reparam_perm = [](int p) {
+        const int tile = p >> 8, chunk = (p >> 5) & 7, part = (p >> 4) & 1, u = p & 15;
+        return part * 256 + tile * 128 + chunk * 16 + u;
+    };
+    CHECK(pack_mlp(c, ws, tm + "prior", true, 2 * NZ_ENC, NZ_MID, 2 * NZ_VAE, 512, reparam_perm, &L.prior));
+    if (l == 0)
+        CHECK(pack_mlp(c, ws, tm + "lstm_initializer.net", true, 2 * NZ_ENC + NZ_VAE, INIT_MID, 2 * STATE, STATE, nullptr,
+                       &L.init, &L.init_head_r, STATE));
+    const std::string sp = tm + "subgoal_pred.";
+    // six parent-state projections, stacked [P0,P2,P4 | P1,P3,P5] so that h-parts come first
+    {
+        const gcpb200_tensor* P[6];
+        const gcpb200_tensor* Pb[6];
+        for (int k = 0; k < 6; ++k) {
+            P[k] = ws.get(sp + "projections." + std::to_string(k) + ".weight", 2);
+            Pb[k] = ws.get(sp + "projections." + std::to_string(k) + ".bias", 1);
+            if (!P[k] || !Pb[k]) return -1;
+        }
+        auto src = [](int g) { return g < 3 ? 2 * g : 2 * (g - 3) + 1; };
+        CHECK(upload_mat(c, &L.proj, 6 * HID, 2 * HID,
+                         [&](int n, int k) { return P[src(n / HID)]->data[(size_t)(n % HID) * 2 * HID + k]; },
+                         [&](int n) { return Pb[src(n / HID)]->data[n % HID]; }));
+    }
+    const gcpb200_tensor* we = ws.get(sp + "embed.weight", 2);
+    const gcpb200_tensor* be = ws.get(sp + "embed.bias", 1);
+    if (!we || !be) return -1;
+    const int EIN = 4 * NZ_ENC + NZ_VAE;   // 768 = [e_l, e_r, z, e_0, e_g]
+    CHECK(upload_mat(c, &L.embed_main, HID, 2 * NZ_ENC + NZ_VAE, [&](int n, int k) { return we->data[(size_t)n * EIN + k]; }, nullptr));
+    CHECK(upload_mat(c, &L.embed_ctx, HID, 2 * NZ_ENC,
+                     [&](int n, int k) { return we->data[(size_t)n * EIN + 2 * NZ_ENC + NZ_VAE + k]; },
+                     [&](int n) { return be->data[n]; }));
+    for (int i = 0; i < N_LSTM; ++i) {
+        const std::string lp = sp + "lstm." + std::to_string(i) + ".";
+        const gcpb200_tensor *wih = ws.get(lp + "weight_ih", 2), *whh = ws.get(lp + "weight_hh", 2),
+                             *bih = ws.get(lp + "bias_ih", 1), *bhh = ws.get(lp + "bias_hh", 1);
+        if (!wih || !whh || !bih || !bhh) return -1;
+        // packed row p = tile*256 + chunk*32 + gate*8 + u  <->  gate*512 + tile*64 + chunk*8 + u
+        auto orig = [](int p) {
+            const int tile = p >> 8, chunk = (p >> 5) & 7, gate = (p >> 3) & 3, u = p & 7;
+            return gate * HID + tile * 64 + chunk * 8 + u;
+        };
+        CHECK(upload_mat(c, &L.lstm[i], 4 * HID, 2 * HID,
+                         [&](int n, int k) {
+                             const int o = orig(n);
+                             return k < HID ? wih->data[(size_t)o * HID + k] : whh->data[(size_t)o * HID + k - HID];
+                         },
+                         [&](int n) { const int o = orig(n); return bih->data[o] + bhh->data[o]; }));
+    }
+    const gcpb200_tensor* wo = ws.get(sp + "output.weight", 2);
+    const gcpb200_tensor* bo = ws.get(sp + "output.bias", 1);
+    if (!wo || !bo) return -1;
+    CHECK(upload_mat(c, &L.out, NZ_ENC, HID, [&](int n, int k) { return wo->data[(size_t)n * HID + k]; },
+                     [&](int n) { return bo->data[n]; }));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM call builder
+// ---------------------------------------------------------------------------------------------
+struct Seg {
+    const DevBuf* buf;
+    int col0, k_len, mode, row_base;
+    int group_cols;
+    int group_col[6];
+};
+static Seg seg(const DevBuf& b, int col0, int k_len, int mode = ROW_LEVEL, int row_base = 0) {
+    Seg s;
+    memset(&s, 0, sizeof(s));
+    s.buf = &b; s.col0 = col0; s.k_len = k_len; s.mode = mode; s.row_base = row_base;
+    return s;
+}
+static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const std::vector<Seg>& segs, const DevMat& W,
+                int BN, int epi, const EpiParams& ep, int w_row0 = 0, int n_cols = -1) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_seg = (int)segs.size();
+    int K = 0;
+    for (int i = 0; i < a.n_seg; ++i) {
+        const Seg& s = segs[i];
+        a.a_map[i] = s.buf->map;
+        a.seg[i].ptr = s.buf->p;
+        a.seg[i].ld = s.buf->ld;
+        a.seg[i].col0 = s.col0;
+        a.seg[i].k_len = s.k_len;
+        a.seg[i].row_mode = s.mode;
+        a.seg[i].row_base = s.row_base;
+        a.seg[i].group_cols = s.group_cols;
+        for (int q = 0; q < 6; ++q) a.seg[i].group_col[q] = s.group_col[q];
+        K += s.k_len;
+    }
+    if (K != W.K) {
+        gcp_set_error("gemm: K mismatch (segments %d, weights %d)", K, W.K);
+        return -1;
+    }
+    (void)w_row0;
+    a.w_map = (BN == 256) ? W.map256 : W.map128;
+    a.w = W.w;
+    a.w_ld = W.K;
+    a.rows = rows;
+    a.N = n_cols < 0 ? W.N : n_cols;
+    a.K = K;
+    a.g = g;
+    a.epi = ep;
+    a.epi.bias = W.bias;
+    ++c->launches;
+    return launch_gemm(a, BN, epi, c->use_ref, st, c->sms);
+}
+
+static EpiParams epi_linear(int act, bf16* ob, int ob_ld, float* of, int of_ld, int n_valid, int ob_mode = ROW_LEVEL,
+                            int of_mode = ROW_LEVEL) {
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.act = act;
+    e.out_bf16 = ob; e.out_bf16_ld = ob_ld; e.out_bf16_mode = ob_mode;
+    e.out_f32 = of; e.out_f32_ld = of_ld; e.out_f32_mode = of_mode;
+    e.n_valid = n_valid;
+    return e;
+}
+
+// runs in -> mid x3; the last activation ends in c->tb (K = m.mid_k columns valid)
+static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
+    CHECK(gemm(c, st, rows, g, in, m.in, 128, EPI_LINEAR, epi_linear(ACT_LRELU, c->ta.p, c->ta.ld, nullptr, 0, m.mid_valid)));
+    DevBuf* src = &c->ta;
+    DevBuf* dst = &c->tb;
+    LevelGeom flat = g;
+    for (int i = 0; i < 3; ++i) {
+        EpiParams e = epi_linear(ACT_LRELU, dst->p, dst->ld, nullptr, 0, m.mid_valid);
+        e.gn_gamma = m.gam[i];
+        e.gn_beta = m.bet[i];
+        e.gn_group = m.gn_group;
+        CHECK(gemm(c, st, rows, flat, {seg(*src, 0, m.mid_k)}, m.mid[i], 128, EPI_GN, e));
+        std::swap(src, dst);
+    }
+    // after 3 swaps the result is in `src` == tb
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
+    if (!out || !cfg || cfg->max_candidates <= 0) {
+        gcp_set_error("gcpb200_create: bad arguments");
+        return -1;
+    }
+    GCP_CUDA_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    GCP_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        gcp_set_error("gcpb200 needs a Blackwell sm_100 device, found %s (cc %d.%d)", prop.name, prop.major, prop.minor);
+        return -1;
+    }
+    gcpb200_ctx* c = new gcpb200_ctx();
+    c->cfg = *cfg;
+    c->sms = prop.multiProcessorCount;
+    c->use_ref = cfg->use_ref_kernels != 0;
+    c->Bp_max = (cfg->max_candidates + 127) / 128 * 128;
+    c->slot_chunk = cfg->decoder_slot_chunk > 0 ? cfg->decoder_slot_chunk : 64;
+    const size_t Bp = c->Bp_max, NL = 128 * Bp, NS = (size_t)N_SLOTS * Bp, ND = 256 * Bp;
+    int rc = 0;
+    rc |= dalloc(c, &c->lat_f32, NS * NZ_ENC);
+    rc |= make_buf(c, &c->lat, NS, NZ_ENC);
+    rc |= make_buf(c, &c->hid, NS, STATE);
+    rc |= make_buf(c, &c->xa, NL, HID);
+    rc |= make_buf(c, &c->xb, NL, HID);
+    rc |= make_buf(c, &c->zeta, NL, NZ_VAE);
+    rc |= make_buf(c, &c->sh, NL, 3 * HID);
+    rc |= dalloc(c, &c->sc, NL * 3 * HID);
+    rc |= make_buf(c, &c->ta, ND, 128);
+    rc |= make_buf(c, &c->tb, ND, 128);
+    rc |= make_buf(c, &c->s2b, Bp, 1024);
+    rc |= make_buf(c, &c->x1, (size_t)c->slot_chunk * Bp, 1024);
+    rc |= make_buf(c, &c->x2, (size_t)c->slot_chunk * Bp, 2048);
+    rc |= make_buf(c, &c->x3, (size_t)c->slot_chunk * Bp, 4096);
+    rc |= make_buf(c, &c->pairs, (size_t)MAX_LEN * Bp + 256, 256);
+    rc |= dalloc(c, &c->ctxb, Bp * HID);
+    rc |= dalloc(c, &c->logits, Bp * 256);
+    rc |= dalloc(c, &c->s0, Bp * 4096);
+    rc |= dalloc(c, &c->s2, Bp * 1024);
+    rc |= dalloc(c, &c->rowbias2, Bp * 2048);
+    rc |= dalloc(c, &c->skip_up, Bp * 2 * DT_PSTRIDE * 8);
+    rc |= dalloc(c, &c->exist_slot, ND);
+    rc |= dalloc(c, &c->e_df, Bp * N_NODES * NZ_ENC);
+    rc |= dalloc(c, &c->seq, Bp * MAX_LEN * NZ_ENC);
+    rc |= dalloc(c, &c->rowcost, ((size_t)MAX_LEN * Bp + 256) * 2);
+    rc |= dalloc(c, &c->goal_tail, 256);
+    rc |= dalloc(c, &c->end_ind, Bp);
+    rc |= dalloc(c, &c->scratch_ei, 8);
+    rc |= dalloc(c, &c->frame_node, Bp * MAX_LEN);
+    if (rc) {
+        gcpb200_destroy(c);
+        return -1;
+    }
+    cudaError_t e = cudaFuncSetAttribute(dec_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
+    if (e != cudaSuccess) {
+        gcp_set_error("cudaFuncSetAttribute(dec_tail) failed: %s", cudaGetErrorString(e));
+        gcpb200_destroy(c);
+        return -1;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
+    if (!c) return;
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+}
+
+extern "C" int64_t gcpb200_launch_count(gcpb200_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensors, int n) {
+    if (!c || !tensors) {
+        gcp_set_error("gcpb200_load_weights: bad arguments");
+        return -1;
+    }
+    GCP_CUDA_CHECK(cudaSetDevice(c->cfg.device));
+    WStore ws;
+    for (int i = 0; i < n; ++i) ws.m[tensors[i].name] = &tensors[i];
+    CHECK(pack_encoder(c, ws));
+    CHECK(pack_decoder(c, ws));
+    for (int l = 0; l < DEPTH; ++l) CHECK(pack_level(c, ws, l));
+    CHECK(pack_mlp(c, ws, "length_pred.p", true, 2 * NZ_ENC, NZ_MID, MAX_LEN, 256, nullptr, &c->length_pred));
+    CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128, nullptr,
+                   &c->existence));
+    CHECK(pack_mlp(c, ws, "inv_mdl.action_pred", false, 2 * NZ_ENC, 128, 2, 128, nullptr, &c->inv_mdl));
+    CHECK(pack_mlp(c, ws, "state_regressor", false, NZ_ENC, NZ_MID, 2, 128, nullptr, &c->state_reg));
+    c->has_cost = false;
+    if (c->cfg.attach_cost_mdl) {
+        CHECK(pack_mlp(c, ws, "cost_mdl.cost_pred", false, 2 * NZ_ENC, 128, 1, 128, nullptr, &c->cost_mdl));
+        c->has_cost = true;
+    }
+    c->weights_loaded = true;
+    return 0;
+}
+
+static int check_ready(gcpb200_ctx* c, int B) {
+    if (!c) {
+        gcp_set_error("null context");
+        return -1;
+    }
+    if (!c->weights_loaded) {
+        gcp_set_error("weights not loaded (call gcpb200_load_weights first)");
+        return -1;
+    }
+    if (B <= 0 || B > c->Bp_max) {
+        gcp_set_error("B = %d outside (0, max_candidates = %d]", B, c->Bp_max);
+        return -1;
+    }
+    return 0;
+}
+
+#define LAUNCH_CHECK()                         \
+    do {                                       \
+        ++c->launches;                         \
+        GCP_CUDA_CHECK(cudaGetLastError());    \
+    } while (0)
+
+static int compute_frame_map(gcpb200_ctx* c, const long long* end_ind, int B, cudaStream_t st) {
+    GCP_CUDA_CHECK(cudaMemsetAsync(c->frame_node, 0, (size_t)B * MAX_LEN * sizeof(int), st));
+    prune_map_kernel<<<(B * N_NODES + 255) / 256, 256, 0, st>>>(end_ind, B, DEPTH, MAX_LEN, c->frame_node);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, void* stream) {
+    if (!io) {
+        gcp_set_error("null io");
+        return -1;
+    }
+    CHECK(check_ready(c, io->B));
+    if (!io->I_0 || !io->I_g || !io->z) {
+        gcp_set_error("gcpb200_rollout: I_0, I_g and z are required");
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = io->B, Bp = (B + 127) / 128 * 128;
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int goal_row0 = 256 * Bp;
+
+    // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
+    const int n_img = io->images_shared ? 1 : B;
+    encoder_kernel<<<n_img, 256, 0, st>>>(io->I_0, c->enc, c->lat_f32, c->lat.p, 0, c->s0, c->s2, c->s2b.p);
+    LAUNCH_CHECK();
+    encoder_kernel<<<n_img, 256, 0, st>>>(io->I_g, c->enc, c->lat_f32, c->lat.p, goal_row0, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK();
+    if (io->images_shared) {
+        broadcast_rows_kernel<<<(Bp * NZ_ENC + 255) / 256, 256, 0, st>>>(c->lat_f32, c->lat.p, 0, Bp, NZ_ENC);
+        LAUNCH_CHECK();
+        broadcast_rows_kernel<<<(Bp * NZ_ENC + 255) / 256, 256, 0, st>>>(c->lat_f32, c->lat.p, goal_row0, Bp, NZ_ENC);
+        LAUNCH_CHECK();
+    }
+    if (io->e_0) GCP_CUDA_CHECK(cudaMemcpyAsync(io->e_0, c->lat_f32, (size_t)B * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));
+    if (io->e_g)
+        GCP_CUDA_CHECK(cudaMemcpyAsync(io->e_g, c->lat_f32 + (size_t)goal_row0 * NZ_ENC, (size_t)B * NZ_ENC * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+
+    // ---- 2. rollout length (LengthPredictorModule + OneHotCategorical sample, or injected)
+    const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
+    if (io->seq_len_logits || !io->end_ind) {
+        CHECK(mlp_body(c, st, c->length_pred, Bp, flat, ctx_in));
+        CHECK(gemm(c, st, Bp, flat, {seg(c->tb, 0, c->length_pred.mid_k)}, c->length_pred.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->logits, 256, MAX_LEN)));
+        if (io->seq_len_logits)
+            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->seq_len_logits, MAX_LEN * 4, c->logits, 256 * 4, MAX_LEN * 4, B,
+                                             cudaMemcpyDeviceToDevice, st));
+    }
+    if (io->end_ind) {
+        GCP_CUDA_CHECK(cudaMemcpyAsync(c->end_ind, io->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        sample_length_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->logits, 256, MAX_LEN, B, io->seed, c->end_ind);
+        LAUNCH_CHECK();
+    }
+    if (io->end_ind_out) GCP_CUDA_CHECK(cudaMemcpyAsync(io->end_ind_out, c->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+
+    // ---- 3. tree recursion, level by level (SubgoalTreeLayer.produce_tree)
+    for (int l = 0; l < DEPTH; ++l) {
+        const LevelW& L = c->lvl[l];
+        const LevelGeom g = {Bp, l, DEPTH};
+        const int rows = Bp << l;
+        // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
+        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 128, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
+        // prior p(z | e_l, e_r) and reparametrisation
+        const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
+        CHECK(mlp_body(c, st, L.prior, rows, g, par));
+        {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.z = io->z; e.n_cand = B; e.nz = NZ_VAE;
+            e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
+            e.mu_out = io->mu_df; e.ls_out = io->log_sigma_df;
+            if ((e.mu_out == nullptr) != (e.ls_out == nullptr)) {
+                gcp_set_error("mu_df and log_sigma_df must be given together");
+                return -1;
+            }
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.prior.mid_k)}, L.prior.head, 256, EPI_REPARAM, e));
+        }
+        const std::vector<Seg> par_z = {par[0], par[1], seg(c->zeta, 0, NZ_VAE)};
+        if (l == 0) {
+            // MLPLSTMCellInitializer: hidden states of the two root parents (slots 0 and 256)
+            CHECK(mlp_body(c, st, L.init, rows, g, par_z));
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 128, EPI_LINEAR,
+                       epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE)));
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 128, EPI_LINEAR,
+                       epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE)));
+        }
+        // split-linear projections of the parents' LSTM state
+        {
+            Seg a = seg(c->hid, 0, HID, ROW_LEFT), b = seg(c->hid, 0, HID, ROW_RIGHT);
+            const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
+            a.group_cols = b.group_cols = HID;
+            for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
+            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 3 * HID, c->sc, 3 * HID, 6 * HID);
+            e.split_col = 3 * HID;
+            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 128, EPI_LINEAR, e));
+        }
+        // embed
+        {
+            EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
+            e.rowbias = c->ctxb;
+            e.rowbias_ld = HID;
+            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 128, EPI_LINEAR, e));
+        }
+        // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
+        DevBuf* xin = &c->xa;
+        DevBuf* xout = &c->xb;
+        for (int i = 0; i < N_LSTM; ++i) {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.c_prev = c->sc; e.c_prev_ld = 3 * HID; e.c_prev_col0 = i * HID;
+            e.out_bf16 = xout->p; e.out_bf16_ld = HID;
+            e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
+            e.write_hid = (l < DEPTH - 1);
+            CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e));
+            std::swap(xin, xout);
+        }
+        // output linear -> node latent e' (raw, no activation) at the node's slot
+        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF)));
+    }
+
+    // ---- 4. depth-first latents, existence predictor
+    float* e_df = io->e_df ? io->e_df : c->e_df;
+    {
+        const size_t n = (size_t)B * N_NODES * NZ_ENC;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, Bp, B, N_NODES, NZ_ENC, NZ_ENC, e_df);
+        LAUNCH_CHECK();
+    }
+    if (io->existence) {
+        const int rows = N_NODES * Bp;
+        CHECK(mlp_body(c, st, c->existence, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, Bp)}));
+        CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->existence.mid_k)}, c->existence.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->exist_slot + Bp, 1, 1)));
+        const size_t n = (size_t)B * N_NODES;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->exist_slot, Bp, B, N_NODES, 1, 1, io->existence);
+        LAUNCH_CHECK();
+    }
+
+    // ---- 5. decoder over all 255 node latents
+    if (io->images_df) {
+        const int n_skip = io->images_shared ? 1 : B;
+        skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
+        LAUNCH_CHECK();
+        // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
+        CHECK(gemm(c, st, io->images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
+        for (int s0 = 1; s0 <= N_NODES; s0 += c->slot_chunk) {
+            const int ns = (s0 + c->slot_chunk <= N_NODES + 1) ? c->slot_chunk : N_NODES + 1 - s0;
+            const int rows = ns * Bp;
+            CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 128, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
+            {
+                EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
+                e.rowbias = c->rowbias2;
+                e.rowbias_ld = io->images_shared ? 0 : 2048;
+                CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 128, EPI_LINEAR, e));
+            }
+            CHECK(gemm(c, st, rows, flat, {seg(c->x2, 0, 2048)}, c->dec3, 128, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
+            DecTailArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = io->images_shared ? 0 : 2 * DT_PSTRIDE * 8;
+            a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
+            a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
+            if (c->use_ref) {
+                dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
+            } else {
+                // work unit = (candidate, run of slots); keep >= ~4 units per SM when B is small
+                int spu = ns;
+                while (spu > 4 && (long long)B * ((ns + spu - 1) / spu) < 4LL * c->sms) spu = (spu + 1) / 2;
+                a.slots_per_unit = spu;
+                const int units = B * ((ns + spu - 1) / spu);
+                dec_tail_tc_kernel<<<units < c->sms ? units : c->sms, DT_THREADS, DT_SMEM_BYTES, st>>>(a);
+            }
+            LAUNCH_CHECK();
+        }
+    }
+
+    // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
+    if (io->model_enc_seq || io->actions || io->regressed_state) {
+        CHECK(compute_frame_map(c, c->end_ind, B, st));
+        float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
+        const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
+        gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
+                                                                           NZ_ENC / 4, seq);
+        LAUNCH_CHECK();
+        if (io->actions || io->regressed_state) {
+            const int rows = (B * MAX_LEN + 127) / 128 * 128;
+            const size_t np = (size_t)rows * 256;
+            make_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(seq, c->end_ind, nullptr, B, MAX_LEN, rows, c->pairs.p);
+            LAUNCH_CHECK();
+            if (io->actions) {
+                CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+                CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
+                           epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
+                GCP_CUDA_CHECK(cudaMemcpyAsync(io->actions, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            if (io->regressed_state) {
+                CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->pairs, 0, 128)}));
+                CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->state_reg.mid_k)}, c->state_reg.head, 128, EPI_LINEAR,
+                           epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
+                GCP_CUDA_CHECK(cudaMemcpyAsync(io->regressed_state, c->rowcost, (size_t)B * MAX_LEN * 2 * 4,
+                                               cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int gcpb200_prune_gather(gcpb200_ctx* c, const float* src_df, const int64_t* end_ind, int B, int row_len,
+                                    float* dst, void* stream) {
+    CHECK(check_ready(c, B));
+    if (row_len % 4) {
+        gcp_set_error("row_len must be a multiple of 4");
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long* ei = reinterpret_cast<const long long*>(end_ind);
+    CHECK(compute_frame_map(c, ei, B, st));
+    const size_t n = (size_t)B * MAX_LEN * (row_len / 4);
+    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src_df, c->frame_node, ei, B, N_NODES, MAX_LEN, row_len / 4, dst);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_cost_l2(gcpb200_ctx* c, const float* images_df, const int64_t* end_ind, const float* goal, int B,
+                               int dense, float final_step_weight, float* cost, void* stream) {
+    CHECK(check_ready(c, B));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long* ei = reinterpret_cast<const long long*>(end_ind);
+    CHECK(compute_frame_map(c, ei, B, st));
+    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, c->frame_node, ei, goal, N_NODES, MAX_LEN, dense, final_step_weight, cost);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_cost_learned(gcpb200_ctx* c, const float* e_df, const int64_t* end_ind, int B, const float* goal_seq,
+                                    int Lg, float* cost, void* stream) {
+    CHECK(check_ready(c, B));
+    if (!c->has_cost) {
+        gcp_set_error("learned cost needs attach_cost_mdl=1 and cost_mdl.cost_pred.* weights");
+        return -1;
+    }
+    if (Lg < 1 || Lg > MAX_LEN) {
+        gcp_set_error("goal sequence length %d outside [1,%d]", Lg, MAX_LEN);
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long* ei = reinterpret_cast<const long long*>(end_ind);
+    const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
+    CHECK(compute_frame_map(c, ei, B, st));
+    const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
+    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, ei, B, N_NODES, MAX_LEN, NZ_ENC / 4, c->seq);
+    LAUNCH_CHECK();
+    // pairs inside each candidate's sequence, the pair bridging into the goal sequence, then the goal's own pairs
+    const int rows = (B * MAX_LEN + 127) / 128 * 128;
+    make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(c->seq, ei, goal_seq, B, MAX_LEN, rows, c->pairs.p);
+    LAUNCH_CHECK();
+    CHECK(mlp_body(c, st, c->cost_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+    CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
+               epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 1, 1)));
+    int n_tail = 0;
+    if (Lg > 1) {
+        // goal-internal pairs: reuse the pair builder on the goal sequence as a 1-candidate batch
+        long long* e1 = c->scratch_ei;   // [Lg-1] as "end_ind" of a single pseudo-candidate
+        const long long hv = Lg - 1;
+        GCP_CUDA_CHECK(cudaMemcpyAsync(e1, &hv, 8, cudaMemcpyHostToDevice, st));
+        GCP_CUDA_CHECK(cudaMemsetAsync(c->seq, 0, (size_t)MAX_LEN * NZ_ENC * 4, st));
+        GCP_CUDA_CHECK(cudaMemcpyAsync(c->seq, goal_seq, (size_t)Lg * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));
+        make_pairs_kernel<<<(256 * 256 + 255) / 256, 256, 0, st>>>(c->seq, e1, nullptr, 1, MAX_LEN, 256, c->pairs.p);
+        LAUNCH_CHECK();
+        CHECK(mlp_body(c, st, c->cost_mdl, 256, flat, {seg(c->pairs, 0, 256)}));
+        CHECK(gemm(c, st, 256, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->goal_tail, 1, 1)));
+        n_tail = Lg - 1;
+    }
+    cost_sum_kernel<<<B, 32, 0, st>>>(c->rowcost, ei, MAX_LEN, c->goal_tail, n_tail, cost);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_topk(gcpb200_ctx* c, const float* cost, int N, int k, int32_t* idx, float* val, void* stream) {
+    if (!c || N <= 0 || k <= 0 || k > N) {
+        gcp_set_error("gcpb200_topk: bad arguments (N %d, k %d)", N, k);
+        return -1;
+    }
+    topk_rank_kernel<<<(N + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cost, N, k, idx, val);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_refit(gcpb200_ctx* c, const float* z, const int32_t* elite_idx, int k, float* mean, float* stdv,
+                             void* stream) {
+    if (!c || k <= 0) {
+        gcp_set_error("gcpb200_refit: bad arguments");
+        return -1;
+    }
+    const int per = N_NODES * NZ_VAE;
+    refit_kernel<<<(per + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, elite_idx, k, per, mean, stdv);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_sample_noise(gcpb200_ctx* c, const float* mean, const float* stdv, float std_scalar, uint64_t seed,
+                                    uint64_t first_candidate_id, int B, float clip, float* z, void* stream) {
+    if (!c || B <= 0) {
+        gcp_set_error("gcpb200_sample_noise: bad arguments");
+        return -1;
+    }
+    const int per = N_NODES * NZ_VAE;
+    const size_t n = (size_t)B * (per / 4);
+    sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        mean, stdv, std_scalar, seed, first_candidate_id, B, per, clip, z);
+    LAUNCH_CHECK();
+    return 0;
+}

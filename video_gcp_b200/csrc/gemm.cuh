@@ -1,0 +1,446 @@
+// Row-tiled GEMM with fused epilogues for the TreeLSTM recursion and every row-MLP of the rollout.
+//
+//   D[rows, N] = concat_K(A_seg0, A_seg1, ...)[rows, K] * Wp[N, K]^T      (bf16 in, fp32 accumulate)
+//
+// Two implementations share the same argument block and the same epilogue code:
+//   * gemm_tc_kernel  -- the product path: persistent, warp-specialised tcgen05 kernel
+//                        (warp 0 = TMA producer, warp 1 = UMMA issuer + TMEM owner, warps 2-9 =
+//                        epilogue, thread = accumulator row), 128B-swizzled K-major operands staged by
+//                        TMA through a 4/6-deep mbarrier ring, double-buffered accumulators in TMEM.
+//   * gemm_ref_kernel -- a deliberately simple SIMT kernel used only by tests / the verification
+//                        mode to isolate tensor-core/TMA bugs from epilogue / packing bugs.
+//
+// A-operand rows are addressed through "row modes" because the tree recursion stores node state in a
+// slot-major array [257 slots][Bp candidates][features]: slot 0 = start frame, slot 256 = goal frame,
+// slot s = in-order (depth-first) node s-1.  Level l, node j sits at slot (2j+1)*2^(7-l); its parents
+// are the slots +-2^(7-l) away (gcp/prediction/utils/tree_utils.py:21-44,202-208 restated as indexing).
+#pragma once
+#include "common.cuh"
+
+namespace gcp {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_SEGS = 4;
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each takes half the columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+
+enum RowMode { ROW_LEVEL = 0, ROW_SELF = 1, ROW_LEFT = 2, ROW_RIGHT = 3 };
+enum EpiKind { EPI_LINEAR = 0, EPI_GN = 1, EPI_REPARAM = 2, EPI_LSTM = 3 };
+enum ActKind { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+
+struct LevelGeom {
+    int Bp;     // candidates padded to a multiple of 128
+    int level;  // tree level 0..depth-1 (0 for plain GEMMs)
+    int depth;  // 8
+};
+
+struct ASeg {
+    const bf16* ptr;   // base of the source array (for the SIMT reference path)
+    int ld;            // leading dimension in elements
+    int col0;          // first column of this K-segment in the source array
+    int k_len;         // multiple of 64
+    int row_mode;      // RowMode
+    int row_base;      // ROW_LEVEL only: first array row of level-row 0 (views into bigger arrays)
+    int group_cols;    // if > 0: output columns are split in groups of this many, each group reads a
+    int group_col[6];  //          different column window of the source: col0 + group_col[n / group_cols]
+};
+
+struct EpiParams {
+    const float* bias;      // [N] in packed column order (may be null)
+    const float* rowbias;   // per-candidate additive term [Bp][rowbias_ld] (may be null)
+    int rowbias_ld;
+    const float* gn_gamma;  // EPI_GN
+    const float* gn_beta;
+    int gn_group;           // channels per group (16 or 4)
+    int act;                // ActKind
+    bf16* out_bf16;
+    int out_bf16_ld, out_bf16_mode;
+    float* out_f32;
+    int out_f32_ld, out_f32_mode;
+    int split_col;          // >0: columns < split go to out_bf16, the rest to out_f32 (col - split)
+    int n_valid;            // columns >= n_valid are dropped
+    // EPI_REPARAM: zeta = exp(log_sigma) * eps + mu (blox/torch/dist.py:285-287)
+    const float* z;         // [B][n_nodes][nz] candidate-major, depth-first nodes (reference layout)
+    int n_cand;             // valid candidates B (<= Bp)
+    int nz;                 // 256
+    float* mu_out;          // optional [B][n_nodes][nz]
+    float* ls_out;
+    // EPI_LSTM: torch.nn.LSTMCell update, gate order i,f,g,o
+    const float* c_prev;    // projected cell state [rows][c_prev_ld], column window c_prev_col0
+    int c_prev_ld, c_prev_col0;
+    bf16* hid;              // slot-major hidden state [slots*Bp][hid_ld]; h at hid_col0+u, c at +H
+    int hid_ld, hid_col0, hidden;  // hidden = 512
+    int write_hid;
+};
+
+struct GemmArgs {
+    CUtensorMap a_map[GEMM_MAX_SEGS];
+    CUtensorMap w_map;
+    ASeg seg[GEMM_MAX_SEGS];
+    int n_seg;
+    const bf16* w;   // packed weights [N][K] (K contiguous)
+    int w_ld;
+    int rows, N, K;  // rows % 128 == 0, N % BN == 0, K % 64 == 0
+    LevelGeom g;
+    EpiParams epi;
+};
+
+// ---------------------------------------------------------------------------------------------
+// row addressing
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int slot_of(const LevelGeom& g, int j, int mode) {
+    const int half = 1 << (g.depth - 1 - g.level);
+    int slot = (2 * j + 1) * half;
+    if (mode == ROW_LEFT) slot -= half;
+    if (mode == ROW_RIGHT) slot += half;
+    return slot;
+}
+// first array row of a 128-row tile (tiles never straddle nodes because Bp % 128 == 0)
+__device__ __forceinline__ int tile_row0(const LevelGeom& g, int mode, int tile_m) {
+    if (mode == ROW_LEVEL) return tile_m * GEMM_BM;   // caller adds row_base
+    const int tpn = g.Bp >> 7;
+    const int j = tile_m / tpn;
+    const int c0 = (tile_m - j * tpn) << 7;
+    return slot_of(g, j, mode) * g.Bp + c0;
+}
+__device__ __forceinline__ int map_row(const LevelGeom& g, int mode, int row) {
+    if (mode == ROW_LEVEL) return row;
+    const int j = row / g.Bp;
+    const int c = row - j * g.Bp;
+    return slot_of(g, j, mode) * g.Bp + c;
+}
+__device__ __forceinline__ int seg_col0(const ASeg& s, int n0) {
+    return s.col0 + (s.group_cols > 0 ? s.group_col[n0 / s.group_cols] : 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues: one thread = one output row, 32 consecutive (packed) columns at a time
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            d4[i] = u;
+        }
+    } else {
+        for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int nvalid) {
+    if (nvalid >= 32) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void group_norm_chunk(const EpiParams& p, int col0, float (&acc)[32]) {
+#pragma unroll
+    for (int g0 = 0; g0 < 32; g0 += G) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < G; ++i) s += acc[g0 + i];
+        const float mean = s * (1.0f / (float)G);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const float d = acc[g0 + i] - mean;
+            q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(q * (1.0f / (float)G) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            acc[g0 + i] = (acc[g0 + i] - mean) * rstd * __ldg(p.gn_gamma + col0 + g0 + i) + __ldg(p.gn_beta + col0 + g0 + i);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int col0,
+                                               float (&acc)[32]) {
+    const int cand = row % g.Bp;
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += __ldg(p.bias + col0 + i);
+    }
+    if (EPI == EPI_LINEAR || EPI == EPI_GN) {
+        if (col0 >= p.n_valid) return;
+        const int nvalid = min(32, p.n_valid - col0);
+        if (p.rowbias != nullptr) {
+            const float* rb = p.rowbias + (size_t)cand * p.rowbias_ld + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] += __ldg(rb + i);
+        }
+        if (EPI == EPI_GN) {
+            // torch GroupNorm: biased variance over the channels of one group, eps 1e-5
+            if (p.gn_group == 16) group_norm_chunk<16>(p, col0, acc);
+            else group_norm_chunk<4>(p, col0, acc);
+        }
+        if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = lrelu_(acc[i]);
+        } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        }
+        if (p.split_col > 0) {
+            if (col0 < p.split_col) {
+                const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
+                store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
+            } else {
+                const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
+                store_f32x32(p.out_f32 + r * p.out_f32_ld + (col0 - p.split_col), acc, nvalid);
+            }
+        } else {
+            if (p.out_bf16 != nullptr) {
+                const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
+                store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
+            }
+            if (p.out_f32 != nullptr) {
+                const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
+                store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
+            }
+        }
+    } else if (EPI == EPI_REPARAM) {
+        // packed columns: [mu(16) | log_sigma(16)] for latent dims d0 .. d0+15
+        const int d0 = col0 >> 1;
+        const int j = row / g.Bp;
+        const int node = slot_of(g, j, ROW_SELF) - 1;  // depth-first node index
+        const int n_nodes = (1 << g.depth) - 1;
+        float zeta[16];
+        if (cand < p.n_cand) {
+            const size_t zoff = ((size_t)cand * n_nodes + node) * p.nz + d0;
+            const float4* z4 = reinterpret_cast<const float4*>(p.z + zoff);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 e = __ldg(z4 + i);
+                zeta[4 * i + 0] = __expf(acc[16 + 4 * i + 0]) * e.x + acc[4 * i + 0];
+                zeta[4 * i + 1] = __expf(acc[16 + 4 * i + 1]) * e.y + acc[4 * i + 1];
+                zeta[4 * i + 2] = __expf(acc[16 + 4 * i + 2]) * e.z + acc[4 * i + 2];
+                zeta[4 * i + 3] = __expf(acc[16 + 4 * i + 3]) * e.w + acc[4 * i + 3];
+            }
+            if (p.mu_out != nullptr) {
+                for (int i = 0; i < 16; ++i) {
+                    p.mu_out[zoff + i] = acc[i];
+                    p.ls_out[zoff + i] = acc[16 + i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zeta[i] = acc[i];  // padded candidates: eps = 0
+        }
+        uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.out_bf16_ld + d0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(zeta[8 * i + 0], zeta[8 * i + 1]);
+            u.y = pack_bf16x2(zeta[8 * i + 2], zeta[8 * i + 3]);
+            u.z = pack_bf16x2(zeta[8 * i + 4], zeta[8 * i + 5]);
+            u.w = pack_bf16x2(zeta[8 * i + 6], zeta[8 * i + 7]);
+            o[i] = u;
+        }
+    } else if (EPI == EPI_LSTM) {
+        // packed columns: [i(8) | f(8) | g(8) | o(8)] for hidden units u0 .. u0+7
+        const int u0 = col0 >> 2;
+        const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + (size_t)row * p.c_prev_ld + p.c_prev_col0 + u0);
+        const float4 ca = __ldg(c4), cb = __ldg(c4 + 1);
+        const float cprev[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float h[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float ig = sigmoidf_(acc[u]);
+            const float fg = sigmoidf_(acc[8 + u]);
+            const float gg = tanhf_(acc[16 + u]);
+            const float og = sigmoidf_(acc[24 + u]);
+            c[u] = fg * cprev[u] + ig * gg;
+            h[u] = og * tanhf_(c[u]);
+        }
+        uint4 hv, cv;
+        hv.x = pack_bf16x2(h[0], h[1]); hv.y = pack_bf16x2(h[2], h[3]);
+        hv.z = pack_bf16x2(h[4], h[5]); hv.w = pack_bf16x2(h[6], h[7]);
+        cv.x = pack_bf16x2(c[0], c[1]); cv.y = pack_bf16x2(c[2], c[3]);
+        cv.z = pack_bf16x2(c[4], c[5]); cv.w = pack_bf16x2(c[6], c[7]);
+        *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.out_bf16_ld + u0) = hv;
+        if (p.write_hid) {
+            const size_t r = (size_t)map_row(g, ROW_SELF, row);
+            bf16* hrow = p.hid + r * p.hid_ld + p.hid_col0 + u0;
+            *reinterpret_cast<uint4*>(hrow) = hv;
+            *reinterpret_cast<uint4*>(hrow + p.hidden) = cv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_n = args.N / BN;
+    const int tiles_m = args.rows / GEMM_BM;
+    const int n_tiles = tiles_m * tiles_n;
+    const int num_kb = args.K / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < args.n_seg; ++s) tma_prefetch_desc(&args.a_map[s]);
+        tma_prefetch_desc(&args.w_map);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 32 * GEMM_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+                int kb = 0;
+                for (int s = 0; s < args.n_seg; ++s) {
+                    const ASeg& sg = args.seg[s];
+                    const int row0 = tile_row0(args.g, sg.row_mode, tile_m) + sg.row_base;
+                    const int c0 = seg_col0(sg, tile_n * BN);
+                    for (int kk = 0; kk < sg.k_len; kk += GEMM_BK, ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &args.a_map[s], &full_bar[stage], c0 + kk, row0);
+                        tma_load_2d(sa + Cfg::A_BYTES, &args.w_map, &full_bar[stage], kb * GEMM_BK, tile_n * BN);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== UMMA issuer (single thread) =====
+            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp drains
+        constexpr int CH_PER_WARP = BN / 32 / (GEMM_EPI_WARPS / 4);
+        const int row_in_tile = q * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const int row = tile_m * GEMM_BM + row_in_tile;
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int ch = half * CH_PER_WARP; ch < (half + 1) * CH_PER_WARP; ++ch) {
+                float acc[32];
+                __syncwarp();
+                tmem_ld32(t0 + ch * 32, acc);
+                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT verification kernel (same args, same epilogue)
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(128) gemm_ref_kernel(const __grid_constant__ GemmArgs args, int BN) {
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int row = tile_m * GEMM_BM + threadIdx.x;
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        const int n0 = tile_n * BN + ch * 32;
+        int kb = 0;
+        for (int s = 0; s < args.n_seg; ++s) {
+            const ASeg& sg = args.seg[s];
+            const bf16* arow = sg.ptr + ((size_t)map_row(args.g, sg.row_mode, row) + sg.row_base) * sg.ld + seg_col0(sg, tile_n * BN);
+            for (int k = 0; k < sg.k_len; ++k) {
+                const float a = __bfloat162float(arow[k]);
+                const bf16* wp = args.w + (size_t)n0 * args.w_ld + kb + k;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = fmaf(a, __bfloat162float(wp[(size_t)i * args.w_ld]), acc[i]);
+            }
+            kb += sg.k_len;
+        }
+        epilogue_chunk<EPI>(args.epi, args.g, row, n0, acc);
+    }
+}
+
+}  // namespace gcp

@@ -1,0 +1,106 @@
+// Host-side helpers for the GEMM kernels: TMA tensor-map construction (driver entry point fetched at
+// run time, so the library has no link-time dependency on libcuda) and launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "gemm.cuh"
+
+namespace gcp {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows][ld] array viewed as a 2-D tensor (cols x rows); box = 64 columns x box_rows rows,
+// 128B swizzle (64 bf16 = 128 B per box row), out-of-bounds reads return zeros.
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (enc == nullptr) {
+        gcp_set_error("cuTensorMapEncodeTiled entry point not available");
+        return -1;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gcp_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows %llu cols %llu ld %llu box_rows %u)", (int)r,
+                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return -1;
+    }
+    return 0;
+}
+
+template <int BN, int EPI>
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        GCP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    if (a.rows % GEMM_BM || a.N % BN || a.K % GEMM_BK) {
+        gcp_set_error("gemm: bad shape rows %d N %d K %d (BN %d)", a.rows, a.N, a.K, BN);
+        return -1;
+    }
+    const int n_tiles = (a.rows / GEMM_BM) * (a.N / BN);
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a);
+    GCP_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <int EPI>
+int launch_gemm_ref(const GemmArgs& a, int BN, cudaStream_t st) {
+    dim3 grid(a.rows / GEMM_BM, a.N / BN);
+    gemm_ref_kernel<EPI><<<grid, 128, 0, st>>>(a, BN);
+    GCP_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// dispatch on (BN, EPI, use_ref)
+inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStream_t st, int num_sms) {
+    if (use_ref) {
+        switch (epi) {
+            case EPI_LINEAR: return launch_gemm_ref<EPI_LINEAR>(a, BN, st);
+            case EPI_GN: return launch_gemm_ref<EPI_GN>(a, BN, st);
+            case EPI_REPARAM: return launch_gemm_ref<EPI_REPARAM>(a, BN, st);
+            case EPI_LSTM: return launch_gemm_ref<EPI_LSTM>(a, BN, st);
+        }
+    } else if (BN == 128) {
+        switch (epi) {
+            case EPI_LINEAR: return launch_gemm_tc<128, EPI_LINEAR>(a, st, num_sms);
+            case EPI_GN: return launch_gemm_tc<128, EPI_GN>(a, st, num_sms);
+        }
+    } else if (BN == 256) {
+        switch (epi) {
+            case EPI_LINEAR: return launch_gemm_tc<256, EPI_LINEAR>(a, st, num_sms);
+            case EPI_REPARAM: return launch_gemm_tc<256, EPI_REPARAM>(a, st, num_sms);
+            case EPI_LSTM: return launch_gemm_tc<256, EPI_LSTM>(a, st, num_sms);
+        }
+    }
+    gcp_set_error("gemm: unsupported BN %d / epilogue %d", BN, epi);
+    return -1;
+}
+
+}  // namespace gcp

@@ -1,0 +1,354 @@
+// Small kernels around the GEMM / decoder cores: image encoder, balanced pruning, gathers, trajectory
+// costs, elite selection, refit, on-device noise.  These are HBM- or latency-bound; they use coalesced,
+// vectorised global access and warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace gcp {
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv encoder (blox/torch/encoder_decoder.py:31-53): k4 s2 p1 x3 (+BN eval, LeakyReLU .2) then k4
+// valid head.  One block per image; activations stay in shared memory.  BatchNorm is folded to a
+// per-channel scale/shift on the host.  1.4 MMAC per image, < 0.1 % of the rollout: SIMT is enough.
+// ---------------------------------------------------------------------------------------------
+struct EncoderWeights {
+    const float* w0;   // [16][3][4][4]
+    const float* b0;   // [16]
+    const float* w1;   // [32][16][4][4]
+    const float* sc1;  // [32] BN scale
+    const float* sh1;  // [32] BN shift
+    const float* w2;   // [64][32][4][4]
+    const float* sc2;
+    const float* sh2;
+    const float* w3;   // [128][64][4][4]
+    const float* b3;   // [128]
+};
+
+template <int CI, int CO, int HIN>
+__device__ __forceinline__ void enc_conv_s2(const float* in, float* out, const float* w, const float* sc,
+                                            const float* sh, const float* bias, int tid, int nthreads) {
+    constexpr int HO = HIN / 2;
+    for (int o = tid; o < CO * HO * HO; o += nthreads) {
+        const int co = o / (HO * HO), oy = (o / HO) % HO, ox = o % HO;
+        float s = 0.f;
+        for (int ci = 0; ci < CI; ++ci) {
+            const float* wp = w + ((size_t)co * CI + ci) * 16;
+            const float* ip = in + ci * HIN * HIN;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const int iy = 2 * oy - 1 + ky;
+                if (iy < 0 || iy >= HIN) continue;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    const int ix = 2 * ox - 1 + kx;
+                    if (ix < 0 || ix >= HIN) continue;
+                    s = fmaf(ip[iy * HIN + ix], __ldg(wp + ky * 4 + kx), s);
+                }
+            }
+        }
+        if (bias != nullptr) s += __ldg(bias + co);
+        if (sc != nullptr) s = s * __ldg(sc + co) + __ldg(sh + co);
+        out[o] = lrelu_(s);
+    }
+}
+
+// grid = n_images; image i is written to latent row slot*Bp + i.  If skip outputs are non-null the
+// post-activation layer-0 / layer-2 maps are stored (GetIntermediatesSequential, stride 2).
+__global__ void __launch_bounds__(256) encoder_kernel(const float* __restrict__ img, EncoderWeights W,
+                                                      float* lat_f32, bf16* lat_bf16, int lat_row0,
+                                                      float* skip0, float* skip2, bf16* skip2_bf16) {
+    __shared__ float a0[3 * 32 * 32];
+    __shared__ float a1[16 * 16 * 16];
+    __shared__ float a2[32 * 8 * 8];
+    __shared__ float a3[64 * 4 * 4];
+    const int tid = threadIdx.x, i = blockIdx.x;
+    for (int k = tid; k < 3072; k += 256) a0[k] = img[(size_t)i * 3072 + k];
+    __syncthreads();
+    enc_conv_s2<3, 16, 32>(a0, a1, W.w0, nullptr, nullptr, W.b0, tid, 256);
+    __syncthreads();
+    enc_conv_s2<16, 32, 16>(a1, a2, W.w1, W.sc1, W.sh1, nullptr, tid, 256);
+    __syncthreads();
+    enc_conv_s2<32, 64, 8>(a2, a3, W.w2, W.sc2, W.sh2, nullptr, tid, 256);
+    __syncthreads();
+    if (skip0 != nullptr) {
+        for (int k = tid; k < 4096; k += 256) skip0[(size_t)i * 4096 + k] = a1[k];
+        for (int k = tid; k < 1024; k += 256) {
+            skip2[(size_t)i * 1024 + k] = a3[k];
+            skip2_bf16[(size_t)i * 1024 + k] = __float2bfloat16_rn(a3[k]);
+        }
+    }
+    if (tid < 128) {
+        float s = __ldg(W.b3 + tid);
+        const float* wp = W.w3 + (size_t)tid * 1024;
+        for (int k = 0; k < 1024; ++k) s = fmaf(a3[k], __ldg(wp + k), s);
+        const size_t r = (size_t)lat_row0 + i;
+        lat_f32[r * 128 + tid] = s;
+        lat_bf16[r * 128 + tid] = __float2bfloat16_rn(s);
+    }
+}
+
+// broadcast row 0 of a slot to all candidates (CEM: every candidate shares the start / goal image)
+__global__ void broadcast_rows_kernel(float* f32, bf16* b16, int row0, int n_rows, int cols) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (n_rows - 1) * cols) return;
+    const int r = 1 + idx / cols, c = idx % cols;
+    if (f32 != nullptr) f32[((size_t)row0 + r) * cols + c] = f32[(size_t)row0 * cols + c];
+    if (b16 != nullptr) b16[((size_t)row0 + r) * cols + c] = b16[(size_t)row0 * cols + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rollout length: OneHotCategorical(logits).sample() -> argmax -> clamp(min=2)
+// (gcp/prediction/models/base_gcp.py:215-229).  Gumbel-max with a counter-based hash RNG.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__global__ void sample_length_kernel(const float* __restrict__ logits, int ld, int n_len, int n_cand,
+                                     unsigned long long seed, long long* end_ind) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < n_len; ++k) {
+        const uint32_t h = mix32(mix32((uint32_t)seed ^ (uint32_t)(seed >> 32)) + 0x9E3779B9u * (uint32_t)(c * n_len + k + 1));
+        const float u = ((h >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float v = logits[(size_t)c * ld + k] - __logf(-__logf(u));
+        if (v > best) { best = v; arg = k; }
+    }
+    end_ind[c] = arg < 2 ? 2 : arg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Balanced pruning (gcp/evaluation/evaluation_matching.py:192-206; gcp/prediction/models/tree/
+// frame_binding.py:42-65): integer interval recursion from (-1, end_ind+1); midpoint with truncating
+// division; a node is kept iff its timestep differs from both interval ends.  Kept nodes have the
+// distinct timesteps 0..end_ind, so frame t of candidate c is node frame_node[c][t].
+// ---------------------------------------------------------------------------------------------
+__global__ void prune_map_kernel(const long long* __restrict__ end_ind, int n_cand, int depth, int lcap,
+                                 int* __restrict__ frame_node) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_nodes = (1 << depth) - 1;
+    if (idx >= n_cand * n_nodes) return;
+    const int c = idx / n_nodes, node = idx - c * n_nodes;
+    // node (in-order index) -> level / position: slot = node+1 = (2j+1) * 2^(depth-1-level)
+    const int slot = node + 1;
+    const int tz = __ffs(slot) - 1;
+    const int level = depth - 1 - tz;
+    const int j = slot >> (tz + 1);
+    int l = -1, r = (int)end_ind[c] + 1, t = 0;
+    for (int lv = 0; lv <= level; ++lv) {
+        t = (l + r) / 2;  // C integer division truncates toward zero, as torch 1.3 did on int64
+        if (lv < level) {
+            if ((j >> (level - 1 - lv)) & 1) l = t; else r = t;
+        }
+    }
+    if (t != l && t != r && t >= 0 && t < lcap) frame_node[c * lcap + t] = node;
+}
+
+// dst[c][t][:] = src[c][frame_node[c][t]][:] for t <= end_ind[c], zeros after (pad_sequence)
+__global__ void gather_frames_kernel(const float* __restrict__ src, const int* __restrict__ frame_node,
+                                     const long long* __restrict__ end_ind, int n_cand, int n_nodes, int lcap,
+                                     int d4 /* row length in float4 */, float* __restrict__ dst) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n_cand * lcap * d4;
+    if (idx >= total) return;
+    const int k = idx % d4;
+    const int t = (idx / d4) % lcap;
+    const int c = idx / ((size_t)d4 * lcap);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t <= (int)end_ind[c]) {
+        const int node = frame_node[c * lcap + t];
+        v = __ldg(reinterpret_cast<const float4*>(src) + ((size_t)c * n_nodes + node) * d4 + k);
+    }
+    reinterpret_cast<float4*>(dst)[idx] = v;
+}
+
+// pair rows for the inverse model / learned cost: row (c,t) = [seq[c][t] | seq[c][t+1]] as bf16,
+// seq = zero-padded pruned latent sequence [n_cand][lcap][128].  `goal0` (optional, [128]) replaces the
+// element just past a candidate's end (the first frame of the goal sequence, learned cost).
+__global__ void make_pairs_kernel(const float* __restrict__ seq, const long long* __restrict__ end_ind,
+                                  const float* __restrict__ goal0, int n_cand, int lcap, int rows_padded,
+                                  bf16* __restrict__ pairs) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows_padded * 256) return;
+    const int k = idx & 255;
+    const size_t row = idx >> 8;
+    float v = 0.f;
+    if (row < (size_t)n_cand * lcap) {
+        const int c = row / lcap, t = row - (size_t)c * lcap;
+        const int tt = t + (k >> 7);
+        if (tt < lcap) v = seq[((size_t)c * lcap + tt) * 128 + (k & 127)];
+        if (goal0 != nullptr && tt == (int)end_ind[c] + 1) v = goal0[k & 127];
+    }
+    pairs[idx] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// L2 image cost (gcp/planning/cem/cost_fcn.py:9-22,65-72): per kept frame sqrt(sum((img-goal)^2)),
+// last frame weighted, dense sum or last only.  One block per candidate, one warp per frame,
+// float4 coalesced reads; algorithmic bytes = (end_ind+1) * 12 KB per candidate.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cost_l2_kernel(const float* __restrict__ images, const int* __restrict__ frame_node,
+                                                      const long long* __restrict__ end_ind, const float* __restrict__ goal,
+                                                      int n_nodes, int lcap, int dense, float final_w,
+                                                      float* __restrict__ cost) {
+    __shared__ float part[8];
+    const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int last = max((int)end_ind[c], 1);   // cem_simulator.py:31: end_ind = max(end_ind, 1)
+    const float4* g4 = reinterpret_cast<const float4*>(goal);
+    float acc = 0.f;
+    for (int t = warp; t <= last; t += 8) {
+        if (!dense && t != last) continue;
+        const int node = frame_node[c * lcap + t];
+        const float4* p = reinterpret_cast<const float4*>(images) + ((size_t)c * n_nodes + node) * 768;
+        float s = 0.f;
+#pragma unroll 4
+        for (int k = lane; k < 768; k += 32) {
+            const float4 a = __ldg(p + k), b = __ldg(g4 + k);
+            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+            s += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
+        s = warp_sum(s);
+        acc += sqrtf(s) * (t == last ? final_w : 1.f);
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += part[w];
+        cost[c] = s;
+    }
+}
+
+// learned cost reduction: cost[c] = sum_{t <= end_ind[c]} rowcost[c*lcap + t] + tail
+__global__ void cost_sum_kernel(const float* __restrict__ rowcost, const long long* __restrict__ end_ind, int lcap,
+                                const float* __restrict__ tail, int n_tail, float* __restrict__ cost) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    float s = 0.f;
+    for (int t = lane; t <= (int)end_ind[c] && t < lcap; t += 32) s += rowcost[(size_t)c * lcap + t];
+    for (int t = lane; t < n_tail; t += 32) s += tail[t];
+    s = warp_sum(s);
+    if (lane == 0) cost[c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Elite selection (gcp/planning/cem/cem_planner.py:124-135): the k lowest costs in ascending order.
+// Rank by counting (stable: ties broken by index), O(N^2) compares spread over the whole chip; for
+// N = 65536 that is 4.3 G compares, well under a millisecond, and exact / deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict__ cost, int n, int k,
+                                                        int* __restrict__ idx_out, float* __restrict__ val_out) {
+    __shared__ float tile[1024];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const float ci = i < n ? cost[i] : INFINITY;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = base + t < n ? cost[base + t] : INFINITY;
+        __syncthreads();
+        const int lim = min(1024, n - base);
+        for (int t = 0; t < lim; ++t) {
+            const float cj = tile[t];
+            rank += (cj < ci) || (cj == ci && base + t < i);
+        }
+        __syncthreads();
+    }
+    if (i < n && rank < k) {
+        idx_out[rank] = i;
+        if (val_out != nullptr) val_out[rank] = ci;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refit (gcp/planning/cem/sampler.py:44-46): mean / std (ddof 0) over the elite samples per (node, dim).
+// Thread per output element, elites streamed with coalesced reads; fp64 accumulation like numpy.
+// ---------------------------------------------------------------------------------------------
+__global__ void refit_kernel(const float* __restrict__ z, const int* __restrict__ elite, int k, int per_cand,
+                             float* __restrict__ mean, float* __restrict__ stdv) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_cand) return;
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += (double)__ldg(z + (size_t)elite[i] * per_cand + e);
+    const double m = s / k;
+    double q = 0.0;
+    for (int i = 0; i < k; ++i) {
+        const double d = (double)__ldg(z + (size_t)elite[i] * per_cand + e) - m;
+        q += d * d;
+    }
+    mean[e] = (float)m;
+    stdv[e] = (float)sqrt(q / k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Noise: z = clip(mean + std * n, +-clip), n ~ N(0,1) from Philox4x32-10 keyed by (seed, global
+// candidate id) so any rank can regenerate any candidate (FlatCEMSampler.sample, sampler.py:40-42).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__global__ void sample_noise_kernel(const float* __restrict__ mean, const float* __restrict__ stdv, float std_scalar,
+                                    unsigned long long seed, unsigned long long cand0, int n_cand, int per_cand,
+                                    float clip, float* __restrict__ z) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 4 outputs
+    const int per4 = per_cand >> 2;
+    if (idx >= (size_t)n_cand * per4) return;
+    const int c = idx / per4, e4 = idx - (size_t)c * per4;
+    const unsigned long long gid = cand0 + c;
+    uint32_t ctr[4] = {(uint32_t)e4, 0u, (uint32_t)gid, (uint32_t)(gid >> 32)};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float n[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((ctr[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((ctr[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        n[2 * h] = r * cs;
+        n[2 * h + 1] = r * sn;
+    }
+    float4 o;
+    float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = e4 * 4 + q;
+        const float m = mean != nullptr ? __ldg(mean + e) : 0.f;
+        const float s = stdv != nullptr ? __ldg(stdv + e) : std_scalar;
+        op[q] = fminf(fmaxf(m + s * n[q], -clip), clip);
+    }
+    reinterpret_cast<float4*>(z)[idx] = o;
+}
+
+// slot-major [n_slots*Bp][cols] (rows = slot, cand) -> candidate-major depth-first [B][n_nodes][cols]
+__global__ void slot_to_df_kernel(const float* __restrict__ src, int Bp, int n_cand, int n_nodes, int cols,
+                                  int src_ld, float* __restrict__ dst) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * n_nodes * cols) return;
+    const int k = idx % cols;
+    const int node = (idx / cols) % n_nodes;
+    const int c = idx / ((size_t)cols * n_nodes);
+    dst[idx] = src[((size_t)(node + 1) * Bp + c) * src_ld + k];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace gcp

@@ -1,0 +1,168 @@
+"""Thin Python owner of one gcpb200 context: weight upload and typed wrappers over the C ABI.
+
+PyTorch is used for device memory, streams and host<->device copies only; every arithmetic step of the
+rollout runs inside libgcpb200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _C
+
+N_NODES, NZ_ENC, NZ_VAE, MAX_LEN = 255, 128, 256, 200
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One context = one device.  Not thread-safe (same as the reference model object)."""
+
+    def __init__(self, device, max_candidates=1024, attach_cost_mdl=False, use_ref_kernels=False,
+                 decoder_slot_chunk=0):
+        if not torch.cuda.is_available():
+            raise _C.GcpB200Error("video_gcp_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _C.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _C.GcpB200Error("Engine device must be a CUDA device, got %s" % device)
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.max_candidates = int(max_candidates)
+        self.attach_cost_mdl = bool(attach_cost_mdl)
+        cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(use_ref_kernels),
+                        int(decoder_slot_chunk))
+        h = C.c_void_p()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
+        self.h = h
+        self.weights_loaded = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gcpb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def load_weights(self, state_dict):
+        """state_dict: reference key names -> tensors (any device); packed + uploaded by the library."""
+        keep, arr = [], []
+        for k, v in state_dict.items():
+            if not torch.is_floating_point(v):
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            if t.dim() > 4 or t.dim() == 0:
+                continue
+            keep.append(t)
+            shape = (C.c_int64 * 4)(*(list(t.shape) + [0] * (4 - t.dim())))
+            arr.append(_C.Tensor(k.encode(), C.c_void_p(t.data_ptr()), t.dim(), shape))
+        tens = (_C.Tensor * len(arr))(*arr)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_load_weights(self.h, tens, len(arr)))
+        self.weights_loaded = True
+
+    # ------------------------------------------------------------------------------------------
+    def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
+                want_prior=False, want_existence=True, want_aux=True, want_logits=True):
+        """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32 cuda."""
+        dev = self.device
+        B = z.shape[0]
+        f32 = dict(device=dev, dtype=torch.float32)
+        assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (N_NODES, NZ_VAE)
+        I_0 = I_0.to(**f32).contiguous()
+        I_g = I_g.to(**f32).contiguous()
+        out = dict(
+            e_0=torch.empty(B, NZ_ENC, **f32), e_g=torch.empty(B, NZ_ENC, **f32),
+            end_ind=torch.empty(B, device=dev, dtype=torch.int64),
+            e_df=torch.empty(B, N_NODES, NZ_ENC, **f32),
+        )
+        if want_logits:
+            out["seq_len_logits"] = torch.empty(B, MAX_LEN, **f32)
+        if want_prior:
+            out["mu_df"] = torch.empty(B, N_NODES, NZ_VAE, **f32)
+            out["log_sigma_df"] = torch.empty(B, N_NODES, NZ_VAE, **f32)
+        if want_images:
+            out["images_df"] = torch.empty(B, N_NODES, 3, 32, 32, **f32)
+        if want_existence:
+            out["existence"] = torch.empty(B, N_NODES, **f32)
+        if want_aux:
+            out["model_enc_seq"] = torch.empty(B, MAX_LEN, NZ_ENC, **f32)
+            out["actions"] = torch.empty(B, MAX_LEN, 2, **f32)
+            out["regressed_state"] = torch.empty(B, MAX_LEN, 2, **f32)
+        if end_ind is not None:
+            end_ind = end_ind.to(device=dev, dtype=torch.int64).contiguous()
+        io = _C.RolloutIO(
+            _ptr(I_0), _ptr(I_g), int(images_shared), _ptr(z), _ptr(end_ind), int(seed), int(B),
+            _ptr(out["e_0"]), _ptr(out["e_g"]), _ptr(out.get("seq_len_logits")), _ptr(out["end_ind"]),
+            _ptr(out["e_df"]), _ptr(out.get("mu_df")), _ptr(out.get("log_sigma_df")), _ptr(out.get("images_df")),
+            _ptr(out.get("existence")), _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")),
+            _ptr(out.get("regressed_state")))
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
+        return out
+
+    def prune_gather(self, src_df, end_ind):
+        """src_df [B,255,D...] -> [B,200,D] with frames 0..end_ind in order, zeros after."""
+        B = src_df.shape[0]
+        flat = src_df.reshape(B, N_NODES, -1).contiguous()
+        D = flat.shape[2]
+        dst = torch.empty(B, MAX_LEN, D, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_prune_gather(self.h, _ptr(flat), _ptr(end_ind.contiguous()), B, D, _ptr(dst), _stream()))
+        return dst
+
+    def cost_l2(self, images_df, end_ind, goal, dense=True, final_step_weight=1.0):
+        B = images_df.shape[0]
+        cost = torch.empty(B, device=self.device, dtype=torch.float32)
+        goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cost_l2(self.h, _ptr(images_df), _ptr(end_ind.contiguous()), _ptr(goal), B, int(dense),
+                                              float(final_step_weight), _ptr(cost), _stream()))
+        return cost
+
+    def cost_learned(self, e_df, end_ind, goal_seq):
+        B = e_df.shape[0]
+        cost = torch.empty(B, device=self.device, dtype=torch.float32)
+        goal_seq = goal_seq.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cost_learned(self.h, _ptr(e_df), _ptr(end_ind.contiguous()), B, _ptr(goal_seq),
+                                                   goal_seq.shape[0], _ptr(cost), _stream()))
+        return cost
+
+    def topk(self, cost, k):
+        N = cost.shape[0]
+        idx = torch.empty(k, device=self.device, dtype=torch.int32)
+        val = torch.empty(k, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_topk(self.h, _ptr(cost.contiguous()), N, k, _ptr(idx), _ptr(val), _stream()))
+        return idx, val
+
+    def refit(self, z, elite_idx):
+        mean = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        std = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_refit(self.h, _ptr(z), _ptr(elite_idx.contiguous()), elite_idx.shape[0], _ptr(mean),
+                                            _ptr(std), _stream()))
+        return mean, std
+
+    def sample_noise(self, n, mean=None, std=None, std_scalar=1.0, seed=0, first_candidate_id=0, clip=float("inf"),
+                     out=None):
+        z = out if out is not None else torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_sample_noise(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
+                                                   int(first_candidate_id), int(n), float(min(clip, 3.0e38)), _ptr(z),
+                                                   _stream()))
+        return z
+
+    def launch_count(self):
+        return int(self.lib.gcpb200_launch_count(self.h))

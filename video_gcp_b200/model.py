@@ -1,0 +1,292 @@
+"""`TreeModel`: drop-in for the reference's GCP-tree model on the planner path.
+
+Mirrors the surface the planner and simulator use (gcp/prediction/models/base_gcp.py:29-66,140-161;
+gcp/prediction/models/tree/tree.py:14-67; gcp/planning/planner_policy.py:36-51):
+
+    model = TreeModel(params, logger); model.to(device); model.device = device
+    CheckpointHandler.load_weights(...) -> model.load_state_dict(state_dict, strict=False); model.eval()
+    with model.val_mode():
+        out = model(inputs)          # inputs: AttrDict(I_0, I_g, z, start_ind, end_ind); mutated in place
+    model.dense_rec.get_sample_with_len(i, L, out, inputs, 'basic'[, name='e_g_prime'])
+
+`state_dict()` has exactly the reference's keys (including its aliases), so reference checkpoints load.
+All arithmetic runs in libgcpb200.so on a B200; there is no PyTorch / CPU fallback -- calling the model
+without a CUDA device or outside `val_mode()` (training-time inference networks) raises.
+"""
+from contextlib import contextmanager
+
+import torch
+import torch.nn as nn
+
+from . import spec
+from .engine import Engine, MAX_LEN, N_NODES
+from .hparams import build_hparams
+from .types import AttrDict
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _attach(root, dotted, tensor, is_buffer):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], tensor)
+
+
+def _init_tensor(shape, kind):
+    """Random init with the reference's scales (xavier / kaiming-uniform style fan-in scaling, forget-gate
+    bias 1, BatchNorm identity statistics)."""
+    if kind in (spec.W, spec.LSTM_W):
+        fan_in = shape[1] if (len(shape) == 2 or tuple(shape[2:]) == (3, 3)) else int(torch.tensor(shape[1:]).prod())
+        a = (3.0 / max(fan_in, 1)) ** 0.5 if kind == spec.W else 1.0 / shape[1] ** 0.5
+        return torch.empty(shape).uniform_(-a, a)
+    if kind == spec.LSTM_B:
+        b = torch.zeros(shape)
+        n = shape[0]
+        b[n // 4:n // 2] = 1.0
+        return b
+    if kind in (spec.BN_W, spec.GN_W, spec.BN_RV):
+        return torch.ones(shape)
+    if kind == spec.BN_NBT:
+        return torch.zeros(shape, dtype=torch.long)
+    return torch.zeros(shape)
+
+
+class TreeView:
+    """Read access to the rollout's node tensors the way `outputs.tree.df.* / .bf.*` exposes them
+    (gcp/prediction/utils/tree_utils.py:90-102,185-199)."""
+
+    def __init__(self, fields, depth):
+        self._fields = fields
+        self.depth = depth
+        bf = []
+        for lvl in range(depth):
+            bf += [(2 * j + 1) * 2 ** (depth - 1 - lvl) - 1 for j in range(2 ** lvl)]
+        self._bf_index = bf
+
+    @property
+    def size(self):
+        return 2 ** self.depth - 1
+
+    @property
+    def df(self):
+        return _Access(self, False)
+
+    @property
+    def bf(self):
+        return _Access(self, True)
+
+
+class _Access:
+    def __init__(self, tree, bf):
+        self._tree, self._bf = tree, bf
+
+    def __getattr__(self, item):
+        f = self._tree._fields
+        if item not in f:
+            raise AttributeError(item)
+        t = f[item]
+        if self._bf:
+            t = t[:, torch.as_tensor(self._tree._bf_index, device=t.device)]
+        return t
+
+    __getitem__ = __getattr__
+
+
+class TreeDenseRec(nn.Module):
+    """Stand-in for gcp/prediction/models/tree/tree_dense_rec.py: balanced ('basic') pruning only."""
+
+    def __init__(self, model):
+        super().__init__()
+        object.__setattr__(self, "_model", model)
+
+    def _pruned(self, outputs, name):
+        key = "_pruned_" + name
+        if key not in outputs:
+            src = outputs.tree.df.images if name == "images" else outputs.tree.df.e_g_prime
+            outputs[key] = self._model.engine.prune_gather(src, outputs.end_ind)
+        return outputs[key]
+
+    def get_sample_with_len(self, i_ex, length, outputs, inputs, pruning_scheme, name=None):
+        if pruning_scheme != "basic":
+            raise NotImplementedError("only the balanced 'basic' pruning scheme is on the planner path")
+        name = "images" if name is None else name
+        seq = self._pruned(outputs, name)[i_ex, :int(outputs.end_ind[i_ex]) + 1]
+        shape = (3, 32, 32) if name == "images" else (seq.shape[-1], 1, 1)
+        return seq.reshape(seq.shape[0], *shape), None
+
+    def get_all_samples_with_len(self, length, outputs, inputs, pruning_scheme, name=None):
+        if pruning_scheme != "basic":
+            raise NotImplementedError("only the balanced 'basic' pruning scheme is on the planner path")
+        name = "images" if name is None else name
+        buf = self._pruned(outputs, name)
+        shape = (3, 32, 32) if name == "images" else (buf.shape[-1], 1, 1)
+        ends = outputs.end_ind.tolist()
+        return [buf[i, :e + 1].reshape(e + 1, *shape) for i, e in enumerate(ends)], None
+
+
+class TreeModel(nn.Module):
+    def __init__(self, params, logger=None, max_candidates=1024, use_ref_kernels=False):
+        super().__init__()
+        self._logger = logger
+        self._hp = build_hparams(params)
+        hp = self._hp
+        if not (hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
+                and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
+                and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
+                and hp.lstm_init == "mlp" and hp.matching_type == "balanced" and hp.use_skips
+                and hp.decoder_distribution == "discrete_logistic_mixture" and not hp.add_weighted_pixel_copy):
+            raise NotImplementedError("libgcpb200 is specialised to the 25-room GCP-tree configuration "
+                                      "(experiments/control/25room/gcp_tree/mod_hyper.py)")
+        canon = spec.canonical_entries(hp)
+        tensors = {}
+        for key, (shape, kind) in canon.items():
+            is_buf = kind in (spec.BN_RM, spec.BN_RV, spec.BN_NBT)
+            t = _init_tensor(tuple(shape), kind)
+            tensors[key] = (t if is_buf else nn.Parameter(t, requires_grad=False), is_buf)
+            _attach(self, key, tensors[key][0], is_buf)
+        for alias, target in spec.aliases(hp):
+            for key in canon:
+                if key.startswith(target + "."):
+                    _attach(self, alias + key[len(target):], tensors[key][0], tensors[key][1])
+        self._canonical_keys = list(canon.keys())
+        self.device = torch.device("cpu")
+        self._max_candidates = max_candidates
+        self._use_ref_kernels = use_ref_kernels
+        self._engine = None
+        self._dirty = True
+        self._val_mode = False
+        self._use_pred_length = False
+        self.return_prior = False       # also return p_z (mu / log_sigma) per node
+        self.return_images = True
+        self.inject_end_ind = None      # parity harness: replaces the sampled rollout length
+        self.seed = 0
+        self.__dict__["dense_rec_impl"] = TreeDenseRec(self)
+
+    # the reference registers `dense_rec` as a module holding the decoder alias; ours only needs methods
+    def __getattr__(self, name):
+        if name == "dense_rec" and "dense_rec_impl" in self.__dict__:
+            return _DenseRecProxy(self.__dict__["dense_rec_impl"], super().__getattr__("dense_rec"))
+        return super().__getattr__(name)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._engine is None:
+            dev = self.device if isinstance(self.device, torch.device) else torch.device(self.device)
+            if dev.type != "cuda":
+                dev = next(self.parameters()).device
+            self._engine = Engine(dev, self._max_candidates, attach_cost_mdl=self._hp.attach_cost_mdl,
+                                  use_ref_kernels=self._use_ref_kernels)
+            self._dirty = True
+        if self._dirty:
+            sd = {k: v for k, v in nn.Module.state_dict(self).items() if k in set(self._canonical_keys)}
+            self._engine.load_weights(sd)
+            self._dirty = False
+        return self._engine
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._dirty = True
+        return r
+
+    def pack_weights(self):
+        """Force re-packing after in-place parameter edits."""
+        self._dirty = True
+        return self.engine
+
+    @contextmanager
+    def val_mode(self, pred_length=True):
+        self._val_mode, self._use_pred_length = True, pred_length
+        try:
+            yield
+        finally:
+            self._val_mode, self._use_pred_length = False, False
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, inputs, phase="train"):
+        if not self._val_mode:
+            raise NotImplementedError("only the prior rollout (`with model.val_mode():`) is implemented; the "
+                                      "training-time inference path is out of scope for libgcpb200")
+        if "z" not in inputs:
+            raise NotImplementedError("the rollout needs injected noise `inputs.z` (as the CEM simulator provides)")
+        eng = self.engine
+        dev = eng.device
+        z = inputs.z
+        if z.dim() == 5:
+            z = z[..., 0, 0]
+        z = z.to(device=dev, dtype=torch.float32).contiguous()
+        B = z.shape[0]
+        inject = self.inject_end_ind
+        if not (self._use_pred_length and self._hp.length_pred_weight > 0) and "end_ind" in inputs:
+            inject = inputs.end_ind      # base_gcp.py:222: predicted length only when _use_pred_length
+        shared = bool(inputs.get("images_shared", False))
+        outputs = AttrDict()
+        inputs.reference_tensor = inputs.I_0
+        if "start_ind" not in inputs:
+            inputs.start_ind = torch.zeros(B, dtype=torch.long, device=dev)
+        res = eng.rollout(inputs.I_0, inputs.I_g, z, end_ind=inject, seed=self.seed, images_shared=shared,
+                          want_images=self.return_images, want_prior=self.return_prior)
+        self.seed += 1
+        inputs.e_0 = res["e_0"][..., None, None]
+        inputs.e_g = res["e_g"][..., None, None]
+        outputs.seq_len_logits = res["seq_len_logits"]
+        outputs.end_ind = res["end_ind"]
+        fields = dict(e_g_prime=res["e_df"][..., None, None])
+        if "images_df" in res:
+            fields["images"] = res["images_df"]
+        if "mu_df" in res:
+            fields["p_z_mu"] = res["mu_df"][..., None, None]
+            fields["p_z_log_sigma"] = res["log_sigma_df"][..., None, None]
+        outputs.tree = TreeView(fields, self._hp.hierarchy_levels)
+        outputs.dense_rec = AttrDict()
+        outputs.existence_predictor = AttrDict(existence=res["existence"])
+        lmax = int(res["end_ind"].max()) + 1
+        inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
+        outputs.actions = res["actions"][:, :lmax - 1]
+        outputs.regressed_state = res["regressed_state"][:, :lmax]
+        outputs["_pruned_e_g_prime"] = res["model_enc_seq"]
+        if "images_df" in res:
+            outputs.pruned_prediction = _LazyPruned(self, outputs)
+        return outputs
+
+
+class _LazyPruned:
+    """`outputs.pruned_prediction`: list of [L_i,3,32,32]; materialised on first use."""
+
+    def __init__(self, model, outputs):
+        self._m, self._o, self._v = model, outputs, None
+
+    def _get(self):
+        if self._v is None:
+            self._v = self._m.dense_rec.get_all_samples_with_len(None, self._o, None, "basic")[0]
+        return self._v
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
+class _DenseRecProxy:
+    """Gives `model.dense_rec` both the parameter container (state-dict alias) and the sampling API."""
+
+    def __init__(self, impl, container):
+        self._impl, self._container = impl, container
+
+    def __getattr__(self, name):
+        if hasattr(self._impl, name):
+            return getattr(self._impl, name)
+        return getattr(self._container, name)

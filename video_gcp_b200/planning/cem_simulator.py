@@ -1,0 +1,105 @@
+"""Simulator interface of the CEM planner (reference: gcp/planning/cem/cem_simulator.py:7-96).
+
+`rollout()` keeps the reference contract (numpy in, AttrDict of per-candidate numpy lists out).
+`rollout_device()` is the B200-first variant the planner uses: everything stays in HBM and only what the
+caller asks for is copied back.
+"""
+import numpy as np
+import torch
+
+from ..types import AttrDict
+
+
+class DeviceRollouts:
+    """Result of one batched rollout, resident on the device."""
+
+    def __init__(self, model, inputs, outputs, goal_chw):
+        self.model, self.inputs, self.outputs, self.goal_chw = model, inputs, outputs, goal_chw
+        self.end_ind = torch.max(outputs.end_ind, torch.ones_like(outputs.end_ind))   # cem_simulator.py:31
+        self.images_df = outputs.tree.df.images if "images" in outputs.tree._fields else None
+        self.e_df = outputs.tree.df.e_g_prime[..., 0, 0]
+
+    def __len__(self):
+        return int(self.end_ind.shape[0])
+
+    def to_host(self, append_latent, idx=None):
+        """AttrDict(predictions, actions, states, latents) of numpy lists, for candidates `idx` (default all)."""
+        eng = self.model.engine
+        ends = self.end_ind.tolist()
+        sel = list(range(len(ends))) if idx is None else [int(i) for i in idx]
+        sel_t = torch.as_tensor(sel, device=self.e_df.device)
+        end_sel = self.end_ind[sel_t]
+        img = eng.prune_gather(self.images_df[sel_t], end_sel)
+        lat = eng.prune_gather(self.e_df[sel_t], end_sel)
+        if append_latent:
+            img = torch.cat([img, lat], -1)
+        img, lat = img.cpu().numpy(), lat.cpu().numpy()
+        act = self.outputs.actions[sel_t].cpu().numpy()
+        sta = self.outputs.regressed_state[sel_t].cpu().numpy()
+        out = AttrDict(predictions=[], actions=[], states=[], latents=[])
+        for n, i in enumerate(sel):
+            L = ends[i] + 1
+            out.predictions.append(img[n, :L])
+            out.actions.append(act[n, :L])
+            out.states.append(sta[n, :L])
+            out.latents.append(lat[n, :L])
+        return out
+
+
+class GCPSimulator:
+    """Implements the simulator interface for GCP models."""
+
+    def __init__(self, model, append_latent):
+        self._model = model
+        self._append_latent = append_latent
+        self._logs = []
+
+    def _postprocess_inputs(self, input_dict):
+        return input_dict
+
+    def rollout_device(self, state, goal_state, samples, rollout_len):
+        """samples: numpy [B,255,256] or a CUDA tensor (kept on device).  Returns DeviceRollouts."""
+        dev = self._model.engine.device
+        B = samples.shape[0]
+        if isinstance(samples, torch.Tensor):
+            z = samples.to(device=dev, dtype=torch.float32)
+        else:
+            z = torch.as_tensor(np.ascontiguousarray(samples, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+        input_dict = AttrDict(
+            I_0=torch.as_tensor(np.asarray(state), dtype=torch.float32).to(dev),
+            I_g=torch.as_tensor(np.asarray(goal_state), dtype=torch.float32).to(dev),
+            start_ind=torch.zeros(B, dtype=torch.long, device=dev),
+            end_ind=torch.full((B,), rollout_len - 1, dtype=torch.long, device=dev),
+            z=z, images_shared=True)
+        input_dict = self._postprocess_inputs(input_dict)
+        with self._model.val_mode():
+            out = self._model(input_dict)
+        return DeviceRollouts(self._model, input_dict, out, input_dict.I_g[0])
+
+    def rollout(self, state, goal_state, samples, rollout_len, prune=False):
+        """Reference contract: AttrDict of python lists with one numpy array per candidate."""
+        return self.rollout_device(state, goal_state, samples, rollout_len).to_host(self._append_latent)
+
+    def dump_logs(self, dump_file='rollout_dump.pkl'):
+        self._logs = []
+
+
+class GCPImageSimulator(GCPSimulator):
+    def _postprocess_inputs(self, input_dict):
+        input_dict = super()._postprocess_inputs(input_dict)
+        if input_dict.z.dim() == 3:
+            input_dict.z = input_dict.z[..., None, None]
+        input_dict.I_0 = self._env2planner(input_dict.I_0)
+        input_dict.I_g = self._env2planner(input_dict.I_g)
+        return input_dict
+
+    @staticmethod
+    def _env2planner(img):
+        """[0..1] or [0..255] HWC environment images -> [-1..1] CHW planner images (cem_simulator.py:87-96)."""
+        if img.max() > 1.0:
+            img = img / 255.0
+        if len(img.shape) == 5:
+            img = img[0]
+        if len(img.shape) == 4:
+            img = img.permute(0, 3, 1, 2)
+        return (img * 2 - 1.0).contiguous()
