@@ -109,8 +109,21 @@ int gcpb200_refit(gcpb200_ctx* ctx, const float* z /* [N,255,256] */, const int3
 int gcpb200_sample_noise(gcpb200_ctx* ctx, const float* mean, const float* std, float std_scalar, uint64_t seed,
                          uint64_t first_candidate_id, int B, float clip, float* z /* [B,255,256] */, void* stream);
 
+/* same, for an explicit list of global candidate ids (device int32[B]): regenerates e.g. the elites of a
+ * sharded CEM iteration on every rank without moving samples between GPUs. */
+int gcpb200_sample_noise_ids(gcpb200_ctx* ctx, const float* mean, const float* std, float std_scalar, uint64_t seed,
+                             const int32_t* ids, int B, float clip, float* z /* [B,255,256] */, void* stream);
+
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t gcpb200_launch_count(gcpb200_ctx* ctx);
+
+/* Phase timing with CUDA events on the caller's stream (measurement aid for bench.py; off by default).
+ * phases: 0 encoder+length, 1 tree recursion, 2 decoder GEMM layers, 3 decoder tail conv kernel, 4 heads,
+ * 5 = the whole gcpb200_rollout call. */
+#define GCPB200_N_PHASES 6
+int gcpb200_profile_enable(gcpb200_ctx* ctx, int on);
+int gcpb200_profile_read(gcpb200_ctx* ctx, double* ms /* [GCPB200_N_PHASES] */, int64_t* tail_images,
+                         int64_t* tail_launches);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,11 @@ EXPORTS = {
     "gcpb200_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gcpb200_sample_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_uint64,
                                        C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "gcpb200_sample_noise_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
+                                           C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "gcpb200_launch_count": (C.c_int64, [C.c_void_p]),
+    "gcpb200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gcpb200_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 

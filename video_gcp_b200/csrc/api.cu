@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/gcpb200.h"
-#include "dec_tail.cuh"
+#include "dec_tail2.cuh"
 #include "gemm_host.cuh"
 #include "kernels_misc.cuh"
 
@@ -81,7 +81,7 @@ struct gcpb200_ctx {
     bool has_cost = false;
     EncoderWeights enc;
     DevMat dec1, dec2x, dec2s, dec3;
-    bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr;
+    bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *w4m = nullptr, *w5m = nullptr, *s4 = nullptr;
     float *b4 = nullptr, *b5 = nullptr;
     // workspace
     float* lat_f32 = nullptr;
@@ -92,6 +92,40 @@ struct gcpb200_ctx {
     long long* end_ind = nullptr;
     long long* scratch_ei = nullptr;
     int* frame_node = nullptr;
+    // optional phase profiling (CUDA events on the caller's stream)
+    bool profile = false;
+    struct ProfSpan { int phase; cudaEvent_t a, b; };
+    std::vector<ProfSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[GCPB200_N_PHASES] = {0, 0, 0, 0, 0, 0};
+    long long prof_tail_images = 0, prof_tail_launches = 0;
+};
+
+static cudaEvent_t prof_event(gcpb200_ctx* c) {
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) {
+        e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+struct ProfScope {
+    gcpb200_ctx* c;
+    cudaStream_t st;
+    size_t idx = 0;
+    bool on;
+    ProfScope(gcpb200_ctx* c_, cudaStream_t st_, int phase) : c(c_), st(st_), on(c_->profile) {
+        if (!on) return;
+        gcpb200_ctx::ProfSpan sp{phase, prof_event(c), prof_event(c)};
+        cudaEventRecord(sp.a, st);
+        idx = c->spans.size();
+        c->spans.push_back(sp);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(c->spans[idx].b, st);
+    }
 };
 
 template <class T>
@@ -364,6 +398,22 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
                     h5[(size_t)tap * 512 + (ci >> 3) * 256 + co * 8 + (ci & 7)] = __float2bfloat16(v);
                     p5[((size_t)co * 16 + ci) * 16 + tap] = __float2bfloat16(v);
                 }
+        // kx folded into N for the pipelined kernel (dec_tail2.cuh): [ky][kchunk][n=(kx,co)][8]
+        std::vector<bf16> m4(D2_W4_BYTES / 2), m5(D2_W5_BYTES / 2);
+        for (int ky = 0; ky < 4; ++ky)
+            for (int kx = 0; kx < 4; ++kx)
+                for (int ci = 0; ci < 16; ++ci) {
+                    for (int co = 0; co < 16; ++co)
+                        m4[(size_t)ky * 1024 + (ci >> 3) * 512 + (kx * 16 + co) * 8 + (ci & 7)] =
+                            __float2bfloat16(w4->data[((size_t)co * 32 + ci) * 16 + ky * 4 + kx]);
+                    for (int co = 0; co < 32; ++co)
+                        m5[(size_t)ky * 2048 + (ci >> 3) * 1024 + (kx * 32 + co) * 8 + (ci & 7)] =
+                            __float2bfloat16(co < 30 ? w5->data[((size_t)co * 16 + ci) * 16 + ky * 4 + kx] : 0.f);
+                }
+        CHECK(dalloc(c, &c->w4m, m4.size(), false));
+        CHECK(dalloc(c, &c->w5m, m5.size(), false));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w4m, m4.data(), m4.size() * 2, cudaMemcpyHostToDevice));
+        GCP_CUDA_CHECK(cudaMemcpy(c->w5m, m5.data(), m5.size() * 2, cudaMemcpyHostToDevice));
         CHECK(dalloc(c, &c->w4, h4.size(), false));
         CHECK(dalloc(c, &c->w5, h5.size(), false));
         CHECK(dalloc(c, &c->w4p, p4.size(), false));
@@ -590,6 +640,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->s2, Bp * 1024);
     rc |= dalloc(c, &c->rowbias2, Bp * 2048);
     rc |= dalloc(c, &c->skip_up, Bp * 2 * DT_PSTRIDE * 8);
+    rc |= dalloc(c, &c->s4, Bp * 1152 * 16);
     rc |= dalloc(c, &c->exist_slot, ND);
     rc |= dalloc(c, &c->e_df, Bp * N_NODES * NZ_ENC);
     rc |= dalloc(c, &c->seq, Bp * MAX_LEN * NZ_ENC);
@@ -602,7 +653,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         gcpb200_destroy(c);
         return -1;
     }
-    cudaError_t e = cudaFuncSetAttribute(dec_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(dec_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
     if (e != cudaSuccess) {
@@ -621,6 +672,34 @@ extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
 }
 
 extern "C" int64_t gcpb200_launch_count(gcpb200_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int gcpb200_profile_enable(gcpb200_ctx* c, int on) {
+    if (!c) return -1;
+    c->profile = on != 0;
+    return 0;
+}
+// Synchronises on the recorded events, returns accumulated milliseconds per phase since the last call
+// and the number of node images / launches the decoder-tail kernel processed; then resets.
+extern "C" int gcpb200_profile_read(gcpb200_ctx* c, double* ms, int64_t* tail_images, int64_t* tail_launches) {
+    if (!c || !ms) return -1;
+    for (auto& sp : c->spans) {
+        GCP_CUDA_CHECK(cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        GCP_CUDA_CHECK(cudaEventElapsedTime(&t, sp.a, sp.b));
+        c->prof_ms[sp.phase] += t;
+        c->ev_pool.push_back(sp.a);
+        c->ev_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < GCPB200_N_PHASES; ++i) {
+        ms[i] = c->prof_ms[i];
+        c->prof_ms[i] = 0;
+    }
+    if (tail_images) *tail_images = c->prof_tail_images;
+    if (tail_launches) *tail_launches = c->prof_tail_launches;
+    c->prof_tail_images = c->prof_tail_launches = 0;
+    return 0;
+}
 
 extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensors, int n) {
     if (!c || !tensors) {
@@ -691,6 +770,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     const LevelGeom flat = {Bp, 0, DEPTH};
     const int goal_row0 = 256 * Bp;
 
+    ProfScope total_scope(c, st, 5);
+    ProfScope* scope = new ProfScope(c, st, 0);
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
     encoder_kernel<<<n_img, 256, 0, st>>>(io->I_0, c->enc, c->lat_f32, c->lat.p, 0, c->s0, c->s2, c->s2b.p);
@@ -726,6 +807,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     }
     if (io->end_ind_out) GCP_CUDA_CHECK(cudaMemcpyAsync(io->end_ind_out, c->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
 
+    delete scope;
+    scope = new ProfScope(c, st, 1);
     // ---- 3. tree recursion, level by level (SubgoalTreeLayer.produce_tree)
     for (int l = 0; l < DEPTH; ++l) {
         const LevelW& L = c->lvl[l];
@@ -792,6 +875,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
                    epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF)));
     }
 
+    delete scope;
+    scope = new ProfScope(c, st, 4);
     // ---- 4. depth-first latents, existence predictor
     float* e_df = io->e_df ? io->e_df : c->e_df;
     {
@@ -809,15 +894,22 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         LAUNCH_CHECK();
     }
 
+    delete scope;
+    scope = nullptr;
     // ---- 5. decoder over all 255 node latents
     if (io->images_df) {
         const int n_skip = io->images_shared ? 1 : B;
         skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
         LAUNCH_CHECK();
+        if (!c->use_ref) {
+            skip_term_kernel<<<dim3(9, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
+            LAUNCH_CHECK();
+        }
         // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
         CHECK(gemm(c, st, io->images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
         for (int s0 = 1; s0 <= N_NODES; s0 += c->slot_chunk) {
+            ProfScope* dsc = new ProfScope(c, st, 2);
             const int ns = (s0 + c->slot_chunk <= N_NODES + 1) ? c->slot_chunk : N_NODES + 1 - s0;
             const int rows = ns * Bp;
             CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 128, EPI_LINEAR,
@@ -830,25 +922,37 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             }
             CHECK(gemm(c, st, rows, flat, {seg(c->x2, 0, 2048)}, c->dec3, 128, EPI_LINEAR,
                        epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
-            DecTailArgs a;
-            memset(&a, 0, sizeof(a));
-            a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = io->images_shared ? 0 : 2 * DT_PSTRIDE * 8;
-            a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
-            a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
+            delete dsc;
+            ProfScope tsc(c, st, 3);
+            if (c->profile) {
+                c->prof_tail_images += (long long)ns * B;
+                ++c->prof_tail_launches;
+            }
             if (c->use_ref) {
+                DecTailArgs a;
+                memset(&a, 0, sizeof(a));
+                a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = io->images_shared ? 0 : 2 * DT_PSTRIDE * 8;
+                a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
+                a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
                 dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
             } else {
+                DecTail2Args a;
+                memset(&a, 0, sizeof(a));
+                a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = io->images_shared ? 0 : 1152 * 16;
+                a.w4 = c->w4m; a.w5 = c->w5m; a.b5 = c->b5;
+                a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
                 // work unit = (candidate, run of slots); keep >= ~4 units per SM when B is small
                 int spu = ns;
                 while (spu > 4 && (long long)B * ((ns + spu - 1) / spu) < 4LL * c->sms) spu = (spu + 1) / 2;
                 a.slots_per_unit = spu;
                 const int units = B * ((ns + spu - 1) / spu);
-                dec_tail_tc_kernel<<<units < c->sms ? units : c->sms, DT_THREADS, DT_SMEM_BYTES, st>>>(a);
+                dec_tail2_kernel<<<units < c->sms ? units : c->sms, D2_THREADS, D2_SMEM_BYTES, st>>>(a);
             }
             LAUNCH_CHECK();
         }
     }
 
+    ProfScope asc(c, st, 4);
     // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
     if (io->model_enc_seq || io->actions || io->regressed_state) {
         CHECK(compute_frame_map(c, c->end_ind, B, st));
@@ -983,7 +1087,21 @@ extern "C" int gcpb200_sample_noise(gcpb200_ctx* c, const float* mean, const flo
     const int per = N_NODES * NZ_VAE;
     const size_t n = (size_t)B * (per / 4);
     sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        mean, stdv, std_scalar, seed, first_candidate_id, B, per, clip, z);
+        mean, stdv, std_scalar, seed, first_candidate_id, nullptr, B, per, clip, z);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_sample_noise_ids(gcpb200_ctx* c, const float* mean, const float* stdv, float std_scalar,
+                                        uint64_t seed, const int32_t* ids, int B, float clip, float* z, void* stream) {
+    if (!c || B <= 0 || !ids) {
+        gcp_set_error("gcpb200_sample_noise_ids: bad arguments");
+        return -1;
+    }
+    const int per = N_NODES * NZ_VAE;
+    const size_t n = (size_t)B * (per / 4);
+    sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        mean, stdv, std_scalar, seed, 0ULL, ids, B, per, clip, z);
     LAUNCH_CHECK();
     return 0;
 }

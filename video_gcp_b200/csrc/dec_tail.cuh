@@ -1,4 +1,5 @@
 // Decoder tail: the two full-resolution convolutions of the GCP decoder, fused per node image.
+// (shared definitions + the SIMT verification kernel; the tcgen05 product kernel is in dec_tail2.cuh)
 //
 //   x3 [16ch,16x16] --bilinear x2--> cat with up(skip s0 [16ch,16x16]) --ZeroPad(1,2,1,2)--> conv k4 (32->16)
 //   + bias, tanh = feat [16,32,32] --ZeroPad(1,2,1,2)--> conv k4 (16->30) + bias --> sigmoid on the 15 mixture
@@ -98,151 +99,6 @@ __device__ __forceinline__ void dt_build_up(uint8_t* in4, const bf16* x3row, int
         u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
         u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
         *reinterpret_cast<uint4*>(in4 + plane * DT_PLANE_BYTES + ((oy + 1) * DT_WP + ox + 1) * 16) = u;
-    }
-}
-
-__global__ void __launch_bounds__(DT_THREADS, 1) dec_tail_tc_kernel(const __grid_constant__ DecTailArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint8_t* in4 = smem;                                  // 4 planes (32 ch)
-    uint8_t* in5 = in4 + 4 * DT_PLANE_BYTES;              // 2 planes (16 ch)
-    uint8_t* w4 = in5 + 2 * DT_PLANE_BYTES;
-    uint8_t* w5 = w4 + DT_W4_BYTES;
-    float* bias = reinterpret_cast<float*>(w5 + DT_W5_BYTES);   // [16] + [32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias + 48);    // bar4, bar5
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // one-time: zero operand planes (the padding ring stays zero forever), stage weights / biases
-    for (int i = tid; i < 6 * DT_PLANE_BYTES / 16; i += DT_THREADS) reinterpret_cast<uint4*>(in4)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < DT_W4_BYTES / 16; i += DT_THREADS) reinterpret_cast<uint4*>(w4)[i] = __ldg(reinterpret_cast<const uint4*>(a.w4) + i);
-    for (int i = tid; i < DT_W5_BYTES / 16; i += DT_THREADS) reinterpret_cast<uint4*>(w5)[i] = __ldg(reinterpret_cast<const uint4*>(a.w5) + i);
-    if (tid < 16) bias[tid] = a.b4[tid];
-    if (tid < 32) bias[16 + tid] = a.b5[tid];
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_holder;
-    constexpr uint32_t TM5 = DT_TILES * 16;   // conv5 accumulators start after conv4's 144 columns
-
-    const int units_per_cand = (a.n_slots + a.slots_per_unit - 1) / a.slots_per_unit;
-    const int n_units = a.n_cand * units_per_cand;
-    uint32_t phase = 0;
-    int loaded_cand = -1;
-    const int q = warp & 3, tsel = warp >> 2;
-
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int cand = unit / units_per_cand;
-        const int s_begin = (unit - cand * units_per_cand) * a.slots_per_unit;
-        const int s_end = min(s_begin + a.slots_per_unit, a.n_slots);
-        if (cand != loaded_cand) {
-            // planes 2,3 of in4 = up-sampled padded skip of this candidate (persist across its nodes)
-            const uint4* src = reinterpret_cast<const uint4*>(a.skip_up + (size_t)cand * a.skip_stride);
-            uint4* dst = reinterpret_cast<uint4*>(in4 + 2 * DT_PLANE_BYTES);
-            for (int i = tid; i < 2 * DT_PSTRIDE; i += DT_THREADS) dst[i] = __ldg(src + i);
-            loaded_cand = cand;
-        }
-        for (int sl = s_begin; sl < s_end; ++sl) {
-            const size_t row = (size_t)sl * a.Bp + cand;
-            dt_build_up(in4, a.x3 + row * 4096, tid, DT_THREADS);
-            fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core
-            tc_fence_before();
-            __syncthreads();
-            // ---------------- conv 32->16: 9 tiles x 16 taps x 2 K-steps of UMMA 128x16x16
-            if (tid == 0) {
-                tc_fence_after();
-                constexpr uint32_t idesc = umma_idesc_bf16(128, DT_C4_OUT);
-                const uint32_t a_base = smem_u32(in4), b_base = smem_u32(w4);
-                for (int t = 0; t < DT_TILES; ++t) {
-#pragma unroll 4
-                    for (int tap = 0; tap < 16; ++tap) {
-                        const int off = (tap >> 2) * DT_WP + (tap & 3);
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t da = umma_desc_nosw(a_base + 2 * ks * DT_PLANE_BYTES + (t * 128 + off) * 16,
-                                                               DT_PLANE_BYTES, 128);
-                            const uint64_t db = umma_desc_nosw(b_base + (tap * 2 + ks) * 512, DT_C4_OUT * 16, 128);
-                            umma_bf16(tmem + t * 16, da, db, idesc, (tap | ks) != 0);
-                        }
-                    }
-                }
-                umma_commit(&bars[0]);
-            }
-            mbar_wait(&bars[0], phase);
-            tc_fence_after();
-            // ---------------- epilogue 1: + bias, tanh, bf16 -> second conv's operand planes
-            for (int t = tsel; t < DT_TILES; t += 2) {
-                float acc[16];
-                __syncwarp();
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + t * 16, acc);
-                const int p = t * 128 + q * 32 + lane;
-                const int x = p % DT_WP;
-                if (p < DT_NPIX && x < 32) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) acc[c] = tanhf_(acc[c] + bias[c]);
-                    uint4 u0, u1;
-                    u0.x = pack_bf16x2(acc[0], acc[1]);   u0.y = pack_bf16x2(acc[2], acc[3]);
-                    u0.z = pack_bf16x2(acc[4], acc[5]);   u0.w = pack_bf16x2(acc[6], acc[7]);
-                    u1.x = pack_bf16x2(acc[8], acc[9]);   u1.y = pack_bf16x2(acc[10], acc[11]);
-                    u1.z = pack_bf16x2(acc[12], acc[13]); u1.w = pack_bf16x2(acc[14], acc[15]);
-                    *reinterpret_cast<uint4*>(in5 + (p + DT_WP + 1) * 16) = u0;
-                    *reinterpret_cast<uint4*>(in5 + DT_PLANE_BYTES + (p + DT_WP + 1) * 16) = u1;
-                }
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            // ---------------- conv 16->30(32): 9 tiles x 16 taps of UMMA 128x32x16
-            if (tid == 0) {
-                tc_fence_after();
-                constexpr uint32_t idesc = umma_idesc_bf16(128, DT_C5_OUT);
-                const uint32_t a_base = smem_u32(in5), b_base = smem_u32(w5);
-                for (int t = 0; t < DT_TILES; ++t) {
-#pragma unroll 4
-                    for (int tap = 0; tap < 16; ++tap) {
-                        const int off = (tap >> 2) * DT_WP + (tap & 3);
-                        const uint64_t da = umma_desc_nosw(a_base + (t * 128 + off) * 16, DT_PLANE_BYTES, 128);
-                        const uint64_t db = umma_desc_nosw(b_base + tap * 1024, DT_C5_OUT * 16, 128);
-                        umma_bf16(tmem + TM5 + t * 32, da, db, idesc, tap != 0);
-                    }
-                }
-                umma_commit(&bars[1]);
-            }
-            mbar_wait(&bars[1], phase);
-            tc_fence_after();
-            // ---------------- epilogue 2: DLM mean image
-            const int node = a.slot0 + sl - 1;
-            float* img = a.images + ((size_t)cand * a.n_nodes + node) * 3072;
-            for (int t = tsel; t < DT_TILES; t += 2) {
-                float acc[32];
-                __syncwarp();
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM5 + t * 32, acc);
-                const int p = t * 128 + q * 32 + lane;
-                const int y = p / DT_WP, x = p - y * DT_WP;
-                if (p < DT_NPIX && x < 32) {
-                    float rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int c = 0; c < 15; ++c) rgb[c % 3] += sigmoidf_(acc[c] + bias[16 + c]);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) img[k * 1024 + y * 32 + x] = rgb[k] * 0.4f - 1.0f;
-                }
-            }
-            tc_fence_before();
-            __syncthreads();
-            phase ^= 1;
-        }
-    }
-    if (warp == 0) {
-        __syncwarp();
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
     }
 }
 

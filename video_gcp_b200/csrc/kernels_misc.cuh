@@ -303,13 +303,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     }
 }
 __global__ void sample_noise_kernel(const float* __restrict__ mean, const float* __restrict__ stdv, float std_scalar,
-                                    unsigned long long seed, unsigned long long cand0, int n_cand, int per_cand,
-                                    float clip, float* __restrict__ z) {
+                                    unsigned long long seed, unsigned long long cand0, const int* __restrict__ ids,
+                                    int n_cand, int per_cand, float clip, float* __restrict__ z) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 4 outputs
     const int per4 = per_cand >> 2;
     if (idx >= (size_t)n_cand * per4) return;
     const int c = idx / per4, e4 = idx - (size_t)c * per4;
-    const unsigned long long gid = cand0 + c;
+    const unsigned long long gid = ids != nullptr ? (unsigned long long)ids[c] : cand0 + c;
     uint32_t ctr[4] = {(uint32_t)e4, 0u, (uint32_t)gid, (uint32_t)(gid >> 32)};
     philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
     float n[4];

@@ -41,6 +41,18 @@ class Engine:
             _C.check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
         self.h = h
         self.weights_loaded = False
+        self._bufs = {}          # persistent output buffers (no allocator traffic on the hot path)
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        """Output buffer reused across calls: contents are valid until the next call that writes `name`."""
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            for k in [k for k in self._bufs if k[0] == name]:
+                del self._bufs[k]
+            t = torch.empty(*shape, device=self.device, dtype=dtype)
+            self._bufs[key] = t
+        return t
 
     def close(self):
         if getattr(self, "h", None):
@@ -73,32 +85,35 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
-                want_prior=False, want_existence=True, want_aux=True, want_logits=True):
-        """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32 cuda."""
+                want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False):
+        """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32 cuda.
+        Outputs live in persistent buffers owned by the engine (overwritten by the next rollout) unless
+        fresh=True."""
         dev = self.device
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
         assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (N_NODES, NZ_VAE)
         I_0 = I_0.to(**f32).contiguous()
         I_g = I_g.to(**f32).contiguous()
-        out = dict(
-            e_0=torch.empty(B, NZ_ENC, **f32), e_g=torch.empty(B, NZ_ENC, **f32),
-            end_ind=torch.empty(B, device=dev, dtype=torch.int64),
-            e_df=torch.empty(B, N_NODES, NZ_ENC, **f32),
-        )
+        if fresh:
+            mk = lambda name, shape, dtype=torch.float32: torch.empty(*shape, device=dev, dtype=dtype)
+        else:
+            mk = self._buf
+        out = dict(e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
+                   e_df=mk("e_df", (B, N_NODES, NZ_ENC)))
         if want_logits:
-            out["seq_len_logits"] = torch.empty(B, MAX_LEN, **f32)
+            out["seq_len_logits"] = mk("seq_len_logits", (B, MAX_LEN))
         if want_prior:
-            out["mu_df"] = torch.empty(B, N_NODES, NZ_VAE, **f32)
-            out["log_sigma_df"] = torch.empty(B, N_NODES, NZ_VAE, **f32)
+            out["mu_df"] = mk("mu_df", (B, N_NODES, NZ_VAE))
+            out["log_sigma_df"] = mk("log_sigma_df", (B, N_NODES, NZ_VAE))
         if want_images:
-            out["images_df"] = torch.empty(B, N_NODES, 3, 32, 32, **f32)
+            out["images_df"] = mk("images_df", (B, N_NODES, 3, 32, 32))
         if want_existence:
-            out["existence"] = torch.empty(B, N_NODES, **f32)
+            out["existence"] = mk("existence", (B, N_NODES))
         if want_aux:
-            out["model_enc_seq"] = torch.empty(B, MAX_LEN, NZ_ENC, **f32)
-            out["actions"] = torch.empty(B, MAX_LEN, 2, **f32)
-            out["regressed_state"] = torch.empty(B, MAX_LEN, 2, **f32)
+            out["model_enc_seq"] = mk("model_enc_seq", (B, MAX_LEN, NZ_ENC))
+            out["actions"] = mk("actions", (B, MAX_LEN, 2))
+            out["regressed_state"] = mk("regressed_state", (B, MAX_LEN, 2))
         if end_ind is not None:
             end_ind = end_ind.to(device=dev, dtype=torch.int64).contiguous()
         io = _C.RolloutIO(
@@ -123,7 +138,7 @@ class Engine:
 
     def cost_l2(self, images_df, end_ind, goal, dense=True, final_step_weight=1.0):
         B = images_df.shape[0]
-        cost = torch.empty(B, device=self.device, dtype=torch.float32)
+        cost = self._buf("cost_l2", (B,))
         goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.index):
             _C.check(self.lib.gcpb200_cost_l2(self.h, _ptr(images_df), _ptr(end_ind.contiguous()), _ptr(goal), B, int(dense),
@@ -164,5 +179,30 @@ class Engine:
                                                    _stream()))
         return z
 
+    def sample_noise_ids(self, ids, mean=None, std=None, std_scalar=1.0, seed=0, clip=float("inf")):
+        """Noise of the global candidate ids in `ids` (int32 cuda tensor)."""
+        n = ids.shape[0]
+        z = torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_sample_noise_ids(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
+                                                       _ptr(ids.contiguous()), int(n), float(min(clip, 3.0e38)), _ptr(z),
+                                                       _stream()))
+        return z
+
     def launch_count(self):
         return int(self.lib.gcpb200_launch_count(self.h))
+
+    PHASES = ("encoder_length", "tree_recursion", "decoder_gemm", "decoder_tail", "heads", "rollout_total")
+
+    def profile_enable(self, on=True):
+        _C.check(self.lib.gcpb200_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """dict phase -> ms accumulated since the last read, plus decoder-tail image / launch counts."""
+        ms = (C.c_double * 6)()
+        imgs, launches = C.c_int64(), C.c_int64()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_profile_read(self.h, ms, C.byref(imgs), C.byref(launches)))
+        out = {k: ms[i] for i, k in enumerate(self.PHASES)}
+        out["tail_images"], out["tail_launches"] = imgs.value, launches.value
+        return out

@@ -79,7 +79,7 @@ class CEMPlanner:
         k = max(int(N * self._hp.elite_frac), 1)
         idx, val = self._simulator._model.engine.topk(cost, k)
         if world > 1:
-            z_elite = self._sampler.regenerate(idx.tolist())
+            z_elite = self._sampler.regenerate(idx)
             self._sampler.fit_device(z_elite, torch.arange(k, device=idx.device, dtype=torch.int32))
         else:
             z_elite = z[idx.long()]

@@ -65,13 +65,16 @@ class GCPSimulator:
             z = samples.to(device=dev, dtype=torch.float32)
         else:
             z = torch.as_tensor(np.ascontiguousarray(samples, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+        # start / goal are converted on the host (12 KB each) and uploaded once: every candidate shares them
         input_dict = AttrDict(
-            I_0=torch.as_tensor(np.asarray(state), dtype=torch.float32).to(dev),
-            I_g=torch.as_tensor(np.asarray(goal_state), dtype=torch.float32).to(dev),
+            I_0=torch.as_tensor(np.asarray(state), dtype=torch.float32),
+            I_g=torch.as_tensor(np.asarray(goal_state), dtype=torch.float32),
             start_ind=torch.zeros(B, dtype=torch.long, device=dev),
             end_ind=torch.full((B,), rollout_len - 1, dtype=torch.long, device=dev),
             z=z, images_shared=True)
         input_dict = self._postprocess_inputs(input_dict)
+        input_dict.I_0 = input_dict.I_0.to(dev, non_blocking=True)
+        input_dict.I_g = input_dict.I_g.to(dev, non_blocking=True)
         with self._model.val_mode():
             out = self._model(input_dict)
         return DeviceRollouts(self._model, input_dict, out, input_dict.I_g[0])

@@ -61,19 +61,9 @@ class FlatCEMSampler(CEMSampler):
                                         first_id, self._clip_val, out=out)
 
     def regenerate(self, ids):
-        """Noise of the given global candidate ids (this iteration's distribution)."""
-        ids = [int(i) for i in ids]
-        z = torch.empty(len(ids), self._n_steps, self._action_dim, device=self.engine.device, dtype=torch.float32)
-        # contiguous runs are generated with one launch each
-        s = 0
-        while s < len(ids):
-            e = s + 1
-            while e < len(ids) and ids[e] == ids[e - 1] + 1:
-                e += 1
-            self.engine.sample_noise(e - s, self._mean_d, self._std_d, float(self._initial_std), self._iter_seed(),
-                                     ids[s], self._clip_val, out=z[s:e])
-            s = e
-        return z
+        """Noise of the given global candidate ids (int32 cuda tensor), this iteration's distribution."""
+        return self.engine.sample_noise_ids(ids.int(), self._mean_d, self._std_d, float(self._initial_std),
+                                            self._iter_seed(), self._clip_val)
 
     def fit_device(self, z, elite_idx):
         """Refit from rows `elite_idx` (int32 cuda) of device samples z."""
