@@ -301,7 +301,41 @@ int main() {
         report("T5 projections s_c (f32)", d, ma, 1e-4);
     }
 
-    // ---------------- T6: throughput of the LSTM-gate GEMM at level-7 size -------------------------
+    // ---------------- T4b: cluster multicast of the weight tile (clusters of 2, 4, 8 CTAs along M) ---------
+    for (int cl : {2, 4, 8}) {
+        const int Bp = 1024, level = 0, depth = 8, H = 512;
+        const int rows = Bp << level, N = 2048, K = 1024;
+        bf16* X = dev_bf16((size_t)rows * H, 1.f);
+        bf16* SH = dev_bf16((size_t)rows * H, 1.f);
+        float* SC = dev_f32((size_t)rows * H, 1.f);
+        bf16* Wd = dev_bf16((size_t)N * K, 0.03f);
+        float* bias = dev_f32(N, 0.2f);
+        bf16* xn_tc = dev_zero<bf16>((size_t)rows * H);
+        bf16* xn_ref = dev_zero<bf16>((size_t)rows * H);
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_seg = 2;
+        a.seg[0] = {X, H, 0, H, ROW_LEVEL, 0, 0, {0}};
+        a.seg[1] = {SH, H, 0, H, ROW_LEVEL, 0, 0, {0}};
+        if (make_tmap_bf16(&a.a_map[0], X, rows, H, H, 128)) return 2;
+        if (make_tmap_bf16(&a.a_map[1], SH, rows, H, H, 128)) return 2;
+        a.w = Wd; a.w_ld = K; a.rows = rows; a.N = N; a.K = K;
+        a.g = {Bp, level, depth};
+        a.epi.bias = bias; a.epi.c_prev = SC; a.epi.c_prev_ld = H; a.epi.out_bf16_ld = H; a.epi.hidden = H;
+        a.epi.out_bf16 = xn_tc;
+        if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 256 / cl)) return 2;
+        if (launch_gemm(a, 256, EPI_LSTM, false, 0, sms, cl)) return 2;
+        a.epi.out_bf16 = xn_ref;
+        if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 256)) return 2;
+        if (launch_gemm(a, 256, EPI_LSTM, true, 0, sms)) return 2;
+        CK(cudaDeviceSynchronize());
+        double ma, d = max_diff_bf16(xn_tc, xn_ref, (size_t)rows * H, &ma);
+        char nm[64];
+        snprintf(nm, 64, "T4b lstm h' with cluster %d multicast", cl);
+        report(nm, d, ma, 1.6e-2);
+    }
+
+    // ---------------- T6: throughput of the LSTM-gate GEMM at level-7 size, per cluster size ------------
     {
         const int rows = 131072, N = 2048, K = 1024, H = 512;
         bf16* X = dev_bf16((size_t)rows * H, 1.f);
@@ -317,24 +351,55 @@ int main() {
         a.seg[1] = {SH, H, 0, H, ROW_LEVEL, 0, 0, {0}};
         if (make_tmap_bf16(&a.a_map[0], X, rows, H, H, 128)) return 2;
         if (make_tmap_bf16(&a.a_map[1], SH, rows, H, H, 128)) return 2;
-        if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 256)) return 2;
         a.w = Wd; a.w_ld = K; a.rows = rows; a.N = N; a.K = K;
         a.g = {1024, 7, 8};
         a.epi.bias = bias; a.epi.c_prev = SC; a.epi.c_prev_ld = H; a.epi.out_bf16_ld = H; a.epi.hidden = H;
         a.epi.out_bf16 = xn;
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 3; ++i) launch_gemm(a, 256, EPI_LSTM, false, 0, sms);
-        CK(cudaEventRecord(e0));
-        const int iters = 10;
-        for (int i = 0; i < iters; ++i) launch_gemm(a, 256, EPI_LSTM, false, 0, sms);
-        CK(cudaEventRecord(e1));
-        CK(cudaDeviceSynchronize());
-        float ms;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double fl = 2.0 * rows * N * K;
-        printf("T6 lstm-gate GEMM %dx%dx%d: %.3f ms/launch, %.1f TFLOP/s\n", rows, N, K, ms / iters,
-               fl / (ms / iters * 1e-3) / 1e12);
+        for (int cl : {1, 2, 4, 8}) {
+            if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 256 / cl)) return 2;
+            for (int i = 0; i < 3; ++i) launch_gemm(a, 256, EPI_LSTM, false, 0, sms, cl);
+            CK(cudaEventRecord(e0));
+            const int iters = 10;
+            for (int i = 0; i < iters; ++i) launch_gemm(a, 256, EPI_LSTM, false, 0, sms, cl);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double fl = 2.0 * rows * N * K;
+            printf("T6 lstm-gate GEMM %dx%dx%d cluster %d: %.3f ms/launch, %.1f TFLOP/s\n", rows, N, K, cl, ms / iters,
+                   fl / (ms / iters * 1e-3) / 1e12);
+        }
+        // plain linear epilogue (decoder layer 3 shape: K 2048, N 4096, BN 128)
+        {
+            const int r2 = 65536, N2 = 4096, K2 = 2048;
+            bf16* A2 = dev_bf16((size_t)r2 * K2, 1.f);
+            bf16* W2 = dev_bf16((size_t)N2 * K2, 0.02f);
+            float* b2 = dev_f32(N2, 0.1f);
+            bf16* o2 = dev_zero<bf16>((size_t)r2 * N2);
+            GemmArgs g;
+            memset(&g, 0, sizeof(g));
+            g.n_seg = 1;
+            g.seg[0] = {A2, K2, 0, K2, ROW_LEVEL, 0, 0, {0}};
+            if (make_tmap_bf16(&g.a_map[0], A2, r2, K2, K2, 128)) return 2;
+            g.w = W2; g.w_ld = K2; g.rows = r2; g.N = N2; g.K = K2;
+            g.g = {1024, 0, 8};
+            g.epi.bias = b2; g.epi.act = ACT_RELU; g.epi.n_valid = N2; g.epi.out_bf16 = o2; g.epi.out_bf16_ld = N2;
+            for (int bn : {128, 256})
+                for (int cl : {1, 2, 4, 8}) {
+                    if (make_tmap_bf16(&g.w_map, W2, N2, K2, K2, bn / cl)) return 2;
+                    for (int i = 0; i < 2; ++i) launch_gemm(g, bn, EPI_LINEAR, false, 0, sms, cl);
+                    CK(cudaEventRecord(e0));
+                    for (int i = 0; i < 5; ++i) launch_gemm(g, bn, EPI_LINEAR, false, 0, sms, cl);
+                    CK(cudaEventRecord(e1));
+                    CK(cudaDeviceSynchronize());
+                    float ms;
+                    CK(cudaEventElapsedTime(&ms, e0, e1));
+                    printf("T6 linear GEMM %dx%dx%d BN %d cluster %d: %.3f ms/launch, %.1f TFLOP/s\n", r2, N2, K2, bn, cl, ms / 5,
+                           2.0 * r2 * N2 * K2 / (ms / 5 * 1e-3) / 1e12);
+                }
+        }
     }
     printf(n_fail ? "GEMM_TEST FAILED (%d)\n" : "GEMM_TEST PASSED\n", n_fail);
     return n_fail ? 1 : 0;

@@ -1,6 +1,7 @@
 // libgcpb200: context, weight packing and the rollout schedule behind the C ABI in include/gcpb200.h.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -45,7 +46,7 @@ struct DevMat {           // packed weight matrix [N][K] bf16 (K-major) + fp32 b
     bf16* w = nullptr;
     float* bias = nullptr;
     int N = 0, K = 0;
-    CUtensorMap map128, map256;
+    CUtensorMap map_box[5];   // TMA boxes of 16, 32, 64, 128, 256 weight rows (BN / cluster size)
 };
 struct DevBuf {           // bf16 activation array [rows][ld] with a TMA map over its full extent
     bf16* p = nullptr;
@@ -71,7 +72,7 @@ struct LevelW {
 
 struct gcpb200_ctx {
     gcpb200_config cfg;
-    int Bp_max = 0, sms = 0, slot_chunk = 64;
+    int Bp_max = 0, sms = 0, slot_chunk = 64, max_cluster = 2;
     bool use_ref = false, weights_loaded = false;
     int64_t launches = 0;
     std::vector<void*> allocs;
@@ -181,8 +182,8 @@ static int upload_mat(gcpb200_ctx* c, DevMat* d, int N, int K, const std::functi
         for (int n = 0; n < N; ++n) hb[n] = bias(n);
     CHECK(dalloc(c, &d->bias, N, false));
     GCP_CUDA_CHECK(cudaMemcpy(d->bias, hb.data(), N * 4, cudaMemcpyHostToDevice));
-    CHECK(make_tmap_bf16(&d->map128, d->w, N, K, K, 128));
-    if (N % 256 == 0) CHECK(make_tmap_bf16(&d->map256, d->w, N, K, K, 256));
+    for (int i = 0; i < 5; ++i)
+        if (N % (16 << i) == 0) CHECK(make_tmap_bf16(&d->map_box[i], d->w, N, K, K, 16 << i));
     return 0;
 }
 static int upload_f32(gcpb200_ctx* c, float** d, const std::vector<float>& h) {
@@ -554,7 +555,11 @@ static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const st
         return -1;
     }
     (void)w_row0;
-    a.w_map = (BN == 256) ? W.map256 : W.map128;
+    const int cluster = c->use_ref ? 1 : gemm_cluster_size(rows, c->max_cluster);
+    const int box = BN / cluster;
+    int bi = 0;
+    while ((16 << bi) < box) ++bi;
+    a.w_map = W.map_box[bi];
     a.w = W.w;
     a.w_ld = W.K;
     a.rows = rows;
@@ -564,7 +569,7 @@ static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const st
     a.epi = ep;
     a.epi.bias = W.bias;
     ++c->launches;
-    return launch_gemm(a, BN, epi, c->use_ref, st, c->sms);
+    return launch_gemm(a, BN, epi, c->use_ref, st, c->sms, cluster);
 }
 
 static EpiParams epi_linear(int act, bf16* ob, int ob_ld, float* of, int of_ld, int n_valid, int ob_mode = ROW_LEVEL,
@@ -617,6 +622,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     c->use_ref = cfg->use_ref_kernels != 0;
     c->Bp_max = (cfg->max_candidates + 127) / 128 * 128;
     c->slot_chunk = cfg->decoder_slot_chunk > 0 ? cfg->decoder_slot_chunk : 64;
+    if (const char* e = getenv("GCPB200_GEMM_CLUSTER")) c->max_cluster = atoi(e) > 0 ? atoi(e) : 1;
     const size_t Bp = c->Bp_max, NL = 128 * Bp, NS = (size_t)N_SLOTS * Bp, ND = 256 * Bp;
     int rc = 0;
     rc |= dalloc(c, &c->lat_f32, NS * NZ_ENC);
@@ -815,7 +821,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         const LevelGeom g = {Bp, l, DEPTH};
         const int rows = Bp << l;
         // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
-        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 128, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
+        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
         // prior p(z | e_l, e_r) and reparametrisation
         const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
         CHECK(mlp_body(c, st, L.prior, rows, g, par));
@@ -835,9 +841,9 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         if (l == 0) {
             // MLPLSTMCellInitializer: hidden states of the two root parents (slots 0 and 256)
             CHECK(mlp_body(c, st, L.init, rows, g, par_z));
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 128, EPI_LINEAR,
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 256, EPI_LINEAR,
                        epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE)));
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 128, EPI_LINEAR,
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 256, EPI_LINEAR,
                        epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE)));
         }
         // split-linear projections of the parents' LSTM state
@@ -848,14 +854,14 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
             EpiParams e = epi_linear(ACT_NONE, c->sh.p, 3 * HID, c->sc, 3 * HID, 6 * HID);
             e.split_col = 3 * HID;
-            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 128, EPI_LINEAR, e));
+            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e));
         }
         // embed
         {
             EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
             e.rowbias = c->ctxb;
             e.rowbias_ld = HID;
-            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 128, EPI_LINEAR, e));
+            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e));
         }
         // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
         DevBuf* xin = &c->xa;
@@ -906,21 +912,21 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             LAUNCH_CHECK();
         }
         // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
-        CHECK(gemm(c, st, io->images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 128, EPI_LINEAR,
+        CHECK(gemm(c, st, io->images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 256, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
         for (int s0 = 1; s0 <= N_NODES; s0 += c->slot_chunk) {
             ProfScope* dsc = new ProfScope(c, st, 2);
             const int ns = (s0 + c->slot_chunk <= N_NODES + 1) ? c->slot_chunk : N_NODES + 1 - s0;
             const int rows = ns * Bp;
-            CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 128, EPI_LINEAR,
+            CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 256, EPI_LINEAR,
                        epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
             {
                 EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
                 e.rowbias = c->rowbias2;
                 e.rowbias_ld = io->images_shared ? 0 : 2048;
-                CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 128, EPI_LINEAR, e));
+                CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 256, EPI_LINEAR, e));
             }
-            CHECK(gemm(c, st, rows, flat, {seg(c->x2, 0, 2048)}, c->dec3, 128, EPI_LINEAR,
+            CHECK(gemm(c, st, rows, flat, {seg(c->x2, 0, 2048)}, c->dec3, 256, EPI_LINEAR,
                        epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
             delete dsc;
             ProfScope tsc(c, st, 3);

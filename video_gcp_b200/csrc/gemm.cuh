@@ -76,7 +76,7 @@ struct EpiParams {
 
 struct GemmArgs {
     CUtensorMap a_map[GEMM_MAX_SEGS];
-    CUtensorMap w_map;
+    CUtensorMap w_map;       // box = 64 columns x (BN / cluster size) rows
     ASeg seg[GEMM_MAX_SEGS];
     int n_seg;
     const bf16* w;   // packed weights [N][K] (K contiguous)
@@ -169,16 +169,23 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
                                                float (&acc)[32]) {
     const int cand = row % g.Bp;
     if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += __ldg(p.bias + col0 + i);
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+        }
     }
     if (EPI == EPI_LINEAR || EPI == EPI_GN) {
         if (col0 >= p.n_valid) return;
         const int nvalid = min(32, p.n_valid - col0);
         if (p.rowbias != nullptr) {
-            const float* rb = p.rowbias + (size_t)cand * p.rowbias_ld + col0;
+            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)cand * p.rowbias_ld + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] += __ldg(rb + i);
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(rb + i);
+                acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+            }
         }
         if (EPI == EPI_GN) {
             // torch GroupNorm: biased variance over the channels of one group, eps 1e-5
@@ -307,15 +314,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const int tiles_n = args.N / BN;
     const int tiles_m = args.rows / GEMM_BM;
-    const int n_tiles = tiles_m * tiles_n;
     const int num_kb = args.K / GEMM_BK;
+    // Thread-block clusters of C CTAs along M share the weight tile: every CTA fetches 1/C of it and TMA
+    // multicasts the slice into all C shared memories, cutting L2->SM operand traffic (the bound of this
+    // kernel at BN=256: 48 KB per k-block and CTA without multicast, 16 + 32/C KB with it).
+    const uint32_t C = cluster_nctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+    const int n_work = (tiles_m / (int)C) * tiles_n;          // work item = (tile_n, group of C consecutive tile_m)
+    const int work0 = blockIdx.x / (int)C, work_stride = gridDim.x / (int)C;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < args.n_seg; ++s) tma_prefetch_desc(&args.a_map[s]);
         tma_prefetch_desc(&args.w_map);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], C);       // released by the UMMA issuer of every CTA in the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
@@ -326,6 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();             // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -334,8 +349,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+            const int slice_rows = BN / (int)C;
+            for (int work = work0; work < n_work; work += work_stride) {
+                const int grp = work / tiles_n, tile_n = work - grp * tiles_n;
+                const int tile_m = grp * (int)C + (int)crank;
                 int kb = 0;
                 for (int s = 0; s < args.n_seg; ++s) {
                     const ASeg& sg = args.seg[s];
@@ -346,7 +363,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         tma_load_2d(sa, &args.a_map[s], &full_bar[stage], c0 + kk, row0);
-                        tma_load_2d(sa + Cfg::A_BYTES, &args.w_map, &full_bar[stage], kb * GEMM_BK, tile_n * BN);
+                        if (C == 1)
+                            tma_load_2d(sa + Cfg::A_BYTES, &args.w_map, &full_bar[stage], kb * GEMM_BK, tile_n * BN);
+                        else
+                            tma_load_2d_mcast(sa + Cfg::A_BYTES + crank * slice_rows * 128, &args.w_map, &full_bar[stage],
+                                              kb * GEMM_BK, tile_n * BN + (int)crank * slice_rows, cmask);
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int work = work0; work < n_work; work += work_stride) {
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -373,7 +394,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);
+                    if (C == 1) umma_commit(&empty_bar[stage]);
+                    else umma_commit_mcast(&empty_bar[stage], cmask);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[as]);
@@ -388,8 +410,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int row_in_tile = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+        for (int work = work0; work < n_work; work += work_stride) {
+            const int grp = work / tiles_n, tile_n = work - grp * tiles_n;
+            const int tile_m = grp * (int)C + (int)crank;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const int row = tile_m * GEMM_BM + row_in_tile;
@@ -408,6 +431,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();             // no CTA exits while peers may still multicast into it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

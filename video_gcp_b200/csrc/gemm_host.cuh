@@ -50,23 +50,50 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
     return 0;
 }
 
+// Cluster size used for `rows`: the largest of {max_cluster, ..., 2, 1} that divides the number of M tiles.
+inline int gemm_cluster_size(int rows, int max_cluster) {
+    const int tiles_m = rows / GEMM_BM;
+    int c = max_cluster;
+    while (c > 1 && (tiles_m % c)) c >>= 1;
+    return c < 1 ? 1 : c;
+}
+
 template <int BN, int EPI>
-int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms) {
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster) {
     using Cfg = GemmCfg<BN>;
     static bool configured = false;
+    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // co-resident clusters per cluster size
     if (!configured) {
         GCP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES));
         configured = true;
     }
-    if (a.rows % GEMM_BM || a.N % BN || a.K % GEMM_BK) {
-        gcp_set_error("gemm: bad shape rows %d N %d K %d (BN %d)", a.rows, a.N, a.K, BN);
+    if (a.rows % GEMM_BM || a.N % BN || a.K % GEMM_BK || (a.rows / GEMM_BM) % cluster) {
+        gcp_set_error("gemm: bad shape rows %d N %d K %d (BN %d, cluster %d)", a.rows, a.N, a.K, BN, cluster);
         return -1;
     }
-    const int n_tiles = (a.rows / GEMM_BM) * (a.N / BN);
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a);
-    GCP_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters[cluster] == 0) {
+        cfg.gridDim = dim3(num_sms / cluster * cluster);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, EPI>, &cfg) != cudaSuccess || n <= 0) n = num_sms / cluster;
+        max_clusters[cluster] = n;
+    }
+    const int n_work = (a.rows / GEMM_BM / cluster) * (a.N / BN);
+    const int n_clusters = n_work < max_clusters[cluster] ? n_work : max_clusters[cluster];
+    cfg.gridDim = dim3(n_clusters * cluster);
+    GCP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, a));
     return 0;
 }
 
@@ -79,7 +106,7 @@ int launch_gemm_ref(const GemmArgs& a, int BN, cudaStream_t st) {
 }
 
 // dispatch on (BN, EPI, use_ref)
-inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStream_t st, int num_sms) {
+inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStream_t st, int num_sms, int cluster = 1) {
     if (use_ref) {
         switch (epi) {
             case EPI_LINEAR: return launch_gemm_ref<EPI_LINEAR>(a, BN, st);
@@ -89,14 +116,14 @@ inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStr
         }
     } else if (BN == 128) {
         switch (epi) {
-            case EPI_LINEAR: return launch_gemm_tc<128, EPI_LINEAR>(a, st, num_sms);
-            case EPI_GN: return launch_gemm_tc<128, EPI_GN>(a, st, num_sms);
+            case EPI_LINEAR: return launch_gemm_tc<128, EPI_LINEAR>(a, st, num_sms, cluster);
+            case EPI_GN: return launch_gemm_tc<128, EPI_GN>(a, st, num_sms, cluster);
         }
     } else if (BN == 256) {
         switch (epi) {
-            case EPI_LINEAR: return launch_gemm_tc<256, EPI_LINEAR>(a, st, num_sms);
-            case EPI_REPARAM: return launch_gemm_tc<256, EPI_REPARAM>(a, st, num_sms);
-            case EPI_LSTM: return launch_gemm_tc<256, EPI_LSTM>(a, st, num_sms);
+            case EPI_LINEAR: return launch_gemm_tc<256, EPI_LINEAR>(a, st, num_sms, cluster);
+            case EPI_REPARAM: return launch_gemm_tc<256, EPI_REPARAM>(a, st, num_sms, cluster);
+            case EPI_LSTM: return launch_gemm_tc<256, EPI_LSTM>(a, st, num_sms, cluster);
         }
     }
     gcp_set_error("gemm: unsupported BN %d / epilogue %d", BN, epi);
