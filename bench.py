@@ -261,7 +261,7 @@ def main():
                 "d2h_bytes_per_step": int(N * 4 + k * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "dec_tail2_kernel", "achieved": tail_tf, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "dec_tail3_kernel", "achieved": tail_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": tail_tf / peak_tf, "traffic": None, "peak_source": peak_src,
                      "ms_per_launch": tail_ms, "images_per_launch": tail_imgs},
         "roofline_step": {"bound": "tensor", "achieved": value / world * FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf,

@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../include/gcpb200.h"
-#include "dec_tail2.cuh"
+#include "dec_tail3.cuh"
 #include "gemm_host.cuh"
 #include "kernels_misc.cuh"
 
@@ -82,8 +82,8 @@ struct gcpb200_ctx {
     bool has_cost = false;
     EncoderWeights enc;
     DevMat dec1, dec2x, dec2s, dec3;
-    bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *w4m = nullptr, *w5m = nullptr, *s4 = nullptr;
-    float *b4 = nullptr, *b5 = nullptr;
+    bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *z4 = nullptr, *z5 = nullptr, *s4 = nullptr;
+    float *b4 = nullptr, *b5 = nullptr, *b5h = nullptr;
     // workspace
     float* lat_f32 = nullptr;
     DevBuf lat, hid, xa, xb, zeta, sh, ta, tb, s2b, x1, x2, x3, pairs;
@@ -399,22 +399,27 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
                     h5[(size_t)tap * 512 + (ci >> 3) * 256 + co * 8 + (ci & 7)] = __float2bfloat16(v);
                     p5[((size_t)co * 16 + ci) * 16 + tap] = __float2bfloat16(v);
                 }
-        // kx folded into N for the pipelined kernel (dec_tail2.cuh): [ky][kchunk][n=(kx,co)][8]
-        std::vector<bf16> m4(D2_W4_BYTES / 2), m5(D2_W5_BYTES / 2);
+        // Toeplitz weight arrays of the quad-row kernel (dec_tail3.cuh): Z[ky][half h][row = 16 b + co][8 ci], block b
+        // holds filter column kx = b - 3 (blocks 0-2 and 7-9 are zero).  conv 4: x-half of the input channels; conv 5:
+        // the 15 mixture-mean channels, pre-scaled by 1/2 (sigmoid(v) = 0.5 + 0.5 tanh(v/2), exact in bf16).
+        std::vector<bf16> z4(D3_W_BYTES / 2, __float2bfloat16(0.f)), z5(D3_W_BYTES / 2, __float2bfloat16(0.f));
         for (int ky = 0; ky < 4; ++ky)
-            for (int kx = 0; kx < 4; ++kx)
-                for (int ci = 0; ci < 16; ++ci) {
+            for (int h = 0; h < 2; ++h)
+                for (int b = 3; b < 7; ++b)
                     for (int co = 0; co < 16; ++co)
-                        m4[(size_t)ky * 1024 + (ci >> 3) * 512 + (kx * 16 + co) * 8 + (ci & 7)] =
-                            __float2bfloat16(w4->data[((size_t)co * 32 + ci) * 16 + ky * 4 + kx]);
-                    for (int co = 0; co < 32; ++co)
-                        m5[(size_t)ky * 2048 + (ci >> 3) * 1024 + (kx * 32 + co) * 8 + (ci & 7)] =
-                            __float2bfloat16(co < 30 ? w5->data[((size_t)co * 16 + ci) * 16 + ky * 4 + kx] : 0.f);
-                }
-        CHECK(dalloc(c, &c->w4m, m4.size(), false));
-        CHECK(dalloc(c, &c->w5m, m5.size(), false));
-        GCP_CUDA_CHECK(cudaMemcpy(c->w4m, m4.data(), m4.size() * 2, cudaMemcpyHostToDevice));
-        GCP_CUDA_CHECK(cudaMemcpy(c->w5m, m5.data(), m5.size() * 2, cudaMemcpyHostToDevice));
+                        for (int e = 0; e < 8; ++e) {
+                            const size_t o = (size_t)ky * (D3_Z_KY / 2) + h * (D3_Z_CHUNK / 2) + (16 * b + co) * 8 + e;
+                            const int ci = 8 * h + e, tap = ky * 4 + (b - 3);
+                            z4[o] = __float2bfloat16(w4->data[((size_t)co * 32 + ci) * 16 + tap]);
+                            if (co < 15) z5[o] = __float2bfloat16(0.5f * w5->data[((size_t)co * 16 + ci) * 16 + tap]);
+                        }
+        CHECK(dalloc(c, &c->z4, z4.size(), false));
+        CHECK(dalloc(c, &c->z5, z5.size(), false));
+        GCP_CUDA_CHECK(cudaMemcpy(c->z4, z4.data(), z4.size() * 2, cudaMemcpyHostToDevice));
+        GCP_CUDA_CHECK(cudaMemcpy(c->z5, z5.data(), z5.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<float> hb5h(16, 0.f);
+        for (int i = 0; i < 15; ++i) hb5h[i] = 0.5f * b5->data[i];
+        CHECK(upload_f32(c, &c->b5h, hb5h));
         CHECK(dalloc(c, &c->w4, h4.size(), false));
         CHECK(dalloc(c, &c->w5, h5.size(), false));
         CHECK(dalloc(c, &c->w4p, p4.size(), false));
@@ -646,7 +651,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->s2, Bp * 1024);
     rc |= dalloc(c, &c->rowbias2, Bp * 2048);
     rc |= dalloc(c, &c->skip_up, Bp * 2 * DT_PSTRIDE * 8);
-    rc |= dalloc(c, &c->s4, Bp * 1152 * 16);
+    rc |= dalloc(c, &c->s4, Bp * 256 * 64);
     rc |= dalloc(c, &c->exist_slot, ND);
     rc |= dalloc(c, &c->e_df, Bp * N_NODES * NZ_ENC);
     rc |= dalloc(c, &c->seq, Bp * MAX_LEN * NZ_ENC);
@@ -659,7 +664,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         gcpb200_destroy(c);
         return -1;
     }
-    cudaError_t e = cudaFuncSetAttribute(dec_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(dec_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
     if (e != cudaSuccess) {
@@ -908,7 +913,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
         LAUNCH_CHECK();
         if (!c->use_ref) {
-            skip_term_kernel<<<dim3(9, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
+            skip_term3_kernel<<<dim3(8, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
             LAUNCH_CHECK();
         }
         // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
@@ -942,17 +947,14 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
                 a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
                 dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
             } else {
-                DecTail2Args a;
+                DecTail3Args a;
                 memset(&a, 0, sizeof(a));
-                a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = io->images_shared ? 0 : 1152 * 16;
-                a.w4 = c->w4m; a.w5 = c->w5m; a.b5 = c->b5;
+                a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = io->images_shared ? 0 : 256 * 64;
+                a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
                 a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
-                // work unit = (candidate, run of slots); keep >= ~4 units per SM when B is small
-                int spu = ns;
-                while (spu > 4 && (long long)B * ((ns + spu - 1) / spu) < 4LL * c->sms) spu = (spu + 1) / 2;
-                a.slots_per_unit = spu;
-                const int units = B * ((ns + spu - 1) / spu);
-                dec_tail2_kernel<<<units < c->sms ? units : c->sms, D2_THREADS, D2_SMEM_BYTES, st>>>(a);
+                // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
+                const long long n_img = (long long)B * ns;
+                dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
             }
             LAUNCH_CHECK();
         }

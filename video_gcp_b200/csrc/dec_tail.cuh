@@ -1,5 +1,5 @@
 // Decoder tail: the two full-resolution convolutions of the GCP decoder, fused per node image.
-// (shared definitions + the SIMT verification kernel; the tcgen05 product kernel is in dec_tail2.cuh)
+// (shared definitions + the SIMT verification kernel; the tcgen05 product kernel is in dec_tail3.cuh)
 //
 //   x3 [16ch,16x16] --bilinear x2--> cat with up(skip s0 [16ch,16x16]) --ZeroPad(1,2,1,2)--> conv k4 (32->16)
 //   + bias, tanh = feat [16,32,32] --ZeroPad(1,2,1,2)--> conv k4 (16->30) + bias --> sigmoid on the 15 mixture
