@@ -400,6 +400,42 @@ int main() {
                            2.0 * r2 * N2 * K2 / (ms / 5 * 1e-3) / 1e12);
                 }
         }
+        // T7: where do the K <= 1024 linear GEMMs lose time?  Same launch with (a) full epilogue, (b) stores dropped
+        // (n_valid = 0: accumulators drained but nothing written), per decoder / projection shape.
+        {
+            struct Shape { int r, N, K; const char* what; };
+            const Shape shapes[] = {{65536, 1024, 128, "dec1"}, {65536, 2048, 1024, "dec2"}, {65536, 4096, 1024, "dec3 banded"},
+                                    {131072, 3072, 1024, "proj"}, {131072, 2048, 1024, "lstm-shape linear"}};
+            for (const Shape& sh : shapes) {
+                bf16* A2 = dev_bf16((size_t)sh.r * sh.K, 1.f);
+                bf16* W2 = dev_bf16((size_t)sh.N * sh.K, 0.02f);
+                float* b2 = dev_f32(sh.N, 0.1f);
+                bf16* o2 = dev_zero<bf16>((size_t)sh.r * sh.N);
+                GemmArgs g;
+                memset(&g, 0, sizeof(g));
+                g.n_seg = 1;
+                g.seg[0] = {A2, sh.K, 0, sh.K, ROW_LEVEL, 0, 0, {0}};
+                if (make_tmap_bf16(&g.a_map[0], A2, sh.r, sh.K, sh.K, 128)) return 2;
+                g.w = W2; g.w_ld = sh.K; g.rows = sh.r; g.N = sh.N; g.K = sh.K;
+                g.g = {1024, 0, 8};
+                g.epi.bias = b2; g.epi.act = ACT_RELU; g.epi.out_bf16 = o2; g.epi.out_bf16_ld = sh.N;
+                if (make_tmap_bf16(&g.w_map, W2, sh.N, sh.K, sh.K, 128)) return 2;
+                for (int nv : {sh.N, 0}) {
+                    g.epi.n_valid = nv;
+                    for (int i = 0; i < 2; ++i) launch_gemm(g, 256, EPI_LINEAR, false, 0, sms, 2);
+                    CK(cudaEventRecord(e0));
+                    for (int i = 0; i < 5; ++i) launch_gemm(g, 256, EPI_LINEAR, false, 0, sms, 2);
+                    CK(cudaEventRecord(e1));
+                    CK(cudaDeviceSynchronize());
+                    float ms;
+                    CK(cudaEventElapsedTime(&ms, e0, e1));
+                    printf("T7 %-18s %6dx%4dx%4d %s: %.3f ms, %.1f TFLOP/s, out %.2f TB/s\n", sh.what, sh.r, sh.N, sh.K,
+                           nv ? "full epilogue" : "no stores    ", ms / 5, 2.0 * sh.r * sh.N * sh.K / (ms / 5 * 1e-3) / 1e12,
+                           nv ? 2.0 * sh.r * sh.N / (ms / 5 * 1e-3) / 1e12 : 0.0);
+                }
+                cudaFree(A2); cudaFree(W2); cudaFree(b2); cudaFree(o2);
+            }
+        }
     }
     printf(n_fail ? "GEMM_TEST FAILED (%d)\n" : "GEMM_TEST PASSED\n", n_fail);
     return n_fail ? 1 : 0;

@@ -309,6 +309,9 @@ static void composite_filter(const float* w /*[4][4]*/, int n, const std::vector
                 }
 }
 
+// first input row of the 4-row K window of decoder layer 3's output band b (output rows 2b, 2b+1)
+static int dec3_window_row0(int b) { return b < 1 ? 0 : (b - 1 > 4 ? 4 : b - 1); }
+
 struct BNFold {
     std::vector<float> scale, shift;
 };
@@ -342,8 +345,11 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
     CHECK(fold_bn(ws, p + "pyramid-1.norm", 32, &bn2));
     {
         const std::vector<double> U = up_matrix(4);
+        // output column order of layer 2 = K order of layer 3: n = iy*256 + co*8 + ix (row-major bands of the 8x8 map),
+        // so that a band of layer-3 output rows reads a contiguous K window (see layer 3)
         std::vector<float> Wx((size_t)2048 * 1024), Wsk((size_t)2048 * 1024);
         std::vector<double> C;
+        auto col2 = [](int co, int o) { return (o >> 3) * 256 + co * 8 + (o & 7); };
         for (int co = 0; co < 32; ++co)
             for (int ci = 0; ci < 128; ++ci) {
                 composite_filter(w2->data + ((size_t)co * 128 + ci) * 16, 4, U, C);
@@ -351,29 +357,43 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
                 const int cil = ci & 63;
                 for (int o = 0; o < 64; ++o)
                     for (int i = 0; i < 16; ++i)
-                        dst[(size_t)(co * 64 + o) * 1024 + cil * 16 + i] = (float)(C[(size_t)o * 16 + i] * bn2.scale[co]);
+                        dst[(size_t)col2(co, o) * 1024 + cil * 16 + i] = (float)(C[(size_t)o * 16 + i] * bn2.scale[co]);
             }
         CHECK(upload_mat(c, &c->dec2x, 2048, 1024, [&](int n, int k) { return Wx[(size_t)n * 1024 + k]; }, nullptr));
         CHECK(upload_mat(c, &c->dec2s, 2048, 1024, [&](int n, int k) { return Wsk[(size_t)n * 1024 + k]; },
-                         [&](int n) { return bn2.shift[n / 64]; }));
+                         [&](int n) { return bn2.shift[(n & 255) >> 3]; }));
     }
-    // ---- layer 3: 32ch 8x8 -> up -> pad -> conv(32->16) -> BN -> ReLU, dense; output in plane layout
+    // ---- layer 3: 32ch 8x8 -> up -> pad -> conv(32->16) -> BN -> ReLU, as a banded dense map.  Output rows 2b, 2b+1
+    // of the 16x16 map only depend on input rows b-1 .. b+2, so each group of 256 output columns (plane, band b)
+    // multiplies a K window of 4 input rows (1024 of the 2048 inputs): half the MACs of the full composite.
+    // Output columns are in the plane layout the tail kernel reads: n = ((co>>3)*256 + oy*16 + ox)*8 + (co&7).
     const gcpb200_tensor* w3 = ws.get(p + "pyramid-0.conv.weight", 4);
     if (!w3) return -1;
     CHECK(fold_bn(ws, p + "pyramid-0.norm", 16, &bn3));
     {
         const std::vector<double> U = up_matrix(8);
-        std::vector<float> W3((size_t)4096 * 2048);
+        std::vector<float> W3((size_t)4096 * 1024, 0.f);
         std::vector<double> C;
+        double outside = 0.0;
         for (int co = 0; co < 16; ++co)
             for (int ci = 0; ci < 32; ++ci) {
                 composite_filter(w3->data + ((size_t)co * 32 + ci) * 16, 8, U, C);
                 for (int o = 0; o < 256; ++o) {
                     const size_t n3 = ((size_t)(co >> 3) * 256 + o) * 8 + (co & 7);
-                    for (int i = 0; i < 64; ++i) W3[n3 * 2048 + ci * 64 + i] = (float)(C[(size_t)o * 64 + i] * bn3.scale[co]);
+                    const int w0 = dec3_window_row0((o >> 4) >> 1);
+                    for (int i = 0; i < 64; ++i) {
+                        const int iy = i >> 3, ix = i & 7;
+                        const double v = C[(size_t)o * 64 + i] * bn3.scale[co];
+                        if (iy >= w0 && iy < w0 + 4) W3[n3 * 1024 + (iy - w0) * 256 + ci * 8 + ix] = (float)v;
+                        else outside += fabs(v);
+                    }
                 }
             }
-        CHECK(upload_mat(c, &c->dec3, 4096, 2048, [&](int n, int k) { return W3[(size_t)n * 2048 + k]; },
+        if (outside != 0.0) {
+            gcp_set_error("decoder layer 3: composite filter has weight outside its 4-row band (%g)", outside);
+            return -1;
+        }
+        CHECK(upload_mat(c, &c->dec3, 4096, 1024, [&](int n, int k) { return W3[(size_t)n * 1024 + k]; },
                          [&](int n) { return bn3.shift[((n >> 3) / 256) * 8 + (n & 7)]; }));
     }
     // ---- layers 4, 5: packed for the implicit-GEMM kernel + plain copies for the verification kernel
@@ -528,7 +548,7 @@ struct Seg {
     const DevBuf* buf;
     int col0, k_len, mode, row_base;
     int group_cols;
-    int group_col[6];
+    int group_col[16];
 };
 static Seg seg(const DevBuf& b, int col0, int k_len, int mode = ROW_LEVEL, int row_base = 0) {
     Seg s;
@@ -552,7 +572,7 @@ static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const st
         a.seg[i].row_mode = s.mode;
         a.seg[i].row_base = s.row_base;
         a.seg[i].group_cols = s.group_cols;
-        for (int q = 0; q < 6; ++q) a.seg[i].group_col[q] = s.group_col[q];
+        for (int q = 0; q < 16; ++q) a.seg[i].group_col[q] = s.group_col[q];
         K += s.k_len;
     }
     if (K != W.K) {
@@ -785,9 +805,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     ProfScope* scope = new ProfScope(c, st, 0);
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
-    encoder_kernel<<<n_img, 256, 0, st>>>(io->I_0, c->enc, c->lat_f32, c->lat.p, 0, c->s0, c->s2, c->s2b.p);
-    LAUNCH_CHECK();
-    encoder_kernel<<<n_img, 256, 0, st>>>(io->I_g, c->enc, c->lat_f32, c->lat.p, goal_row0, nullptr, nullptr, nullptr);
+    encoder_kernel<<<dim3(n_img, 2), ENC_THREADS, 0, st>>>(io->I_0, io->I_g, c->enc, c->lat_f32, c->lat.p, 0, goal_row0, c->s0, c->s2,
+                                                            c->s2b.p);
     LAUNCH_CHECK();
     if (io->images_shared) {
         broadcast_rows_kernel<<<(Bp * NZ_ENC + 255) / 256, 256, 0, st>>>(c->lat_f32, c->lat.p, 0, Bp, NZ_ENC);
@@ -931,8 +950,13 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
                 e.rowbias_ld = io->images_shared ? 0 : 2048;
                 CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 256, EPI_LINEAR, e));
             }
-            CHECK(gemm(c, st, rows, flat, {seg(c->x2, 0, 2048)}, c->dec3, 256, EPI_LINEAR,
-                       epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
+            {
+                Seg a3 = seg(c->x2, 0, 1024);      // banded: column group (plane, band) reads its own 4-row K window
+                a3.group_cols = 256;
+                for (int q = 0; q < 16; ++q) a3.group_col[q] = dec3_window_row0(q & 7) * 256;
+                CHECK(gemm(c, st, rows, flat, {a3}, c->dec3, 256, EPI_LINEAR,
+                           epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
+            }
             delete dsc;
             ProfScope tsc(c, st, 3);
             if (c->profile) {

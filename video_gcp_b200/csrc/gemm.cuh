@@ -43,7 +43,7 @@ struct ASeg {
     int row_mode;      // RowMode
     int row_base;      // ROW_LEVEL only: first array row of level-row 0 (views into bigger arrays)
     int group_cols;    // if > 0: output columns are split in groups of this many, each group reads a
-    int group_col[6];  //          different column window of the source: col0 + group_col[n / group_cols]
+    int group_col[16]; //          different column window of the source: col0 + group_col[n / group_cols]
 };
 
 struct EpiParams {
@@ -130,7 +130,10 @@ __device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32], i
             d4[i] = u;
         }
     } else {
-        for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+        // fully unrolled + predicated: a run-time index into v[] would move the accumulators to local memory
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
     }
 }
 __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int nvalid) {
@@ -139,7 +142,36 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], i
 #pragma unroll
         for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
-        for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) dst[i] = v[i];
+    }
+}
+
+// 32 rows x 32 bf16 columns of one warp, written as full 64-byte row segments: every thread parks its row piece in a
+// per-warp 2 KB shared-memory tile (16-byte cells XOR-swizzled by row), then lanes 4k..4k+3 store the four cells of
+// one row, 8 rows per instruction.  Storing straight from the accumulator registers (thread = row) issues four
+// half-sector writes per row and caps the GEMMs with wide bf16 outputs at ~0.8 TB/s (profiles/r1_gemm_store_path.txt).
+// `row0_ptr` = address of column col0 in the output row of lane 0; the 32 rows of a warp are consecutive.
+__device__ __forceinline__ void store_bf16x32_staged(uint4* stage, bf16* row0_ptr, size_t ld, const float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        stage[lane * 4 + (i ^ ((lane >> 1) & 3))] = u;
+    }
+    __syncwarp();
+    const int p = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2);
+        const uint4 u = stage[r * 4 + (p ^ ((r >> 1) & 3))];
+        *reinterpret_cast<uint4*>(row0_ptr + (size_t)r * ld + p * 8) = u;
     }
 }
 
@@ -166,7 +198,7 @@ __device__ __forceinline__ void group_norm_chunk(const EpiParams& p, int col0, f
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int col0,
-                                               float (&acc)[32]) {
+                                               float (&acc)[32], uint4* stage = nullptr) {
     const int cand = row % g.Bp;
     if (p.bias != nullptr) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -202,7 +234,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         if (p.split_col > 0) {
             if (col0 < p.split_col) {
                 const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
-                store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
+                if (stage != nullptr && nvalid >= 32)
+                    store_bf16x32_staged(stage, p.out_bf16 + (r - (threadIdx.x & 31)) * p.out_bf16_ld + col0, p.out_bf16_ld, acc);
+                else
+                    store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
             } else {
                 const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
                 store_f32x32(p.out_f32 + r * p.out_f32_ld + (col0 - p.split_col), acc, nvalid);
@@ -210,7 +245,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         } else {
             if (p.out_bf16 != nullptr) {
                 const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
-                store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
+                if (stage != nullptr && nvalid >= 32)
+                    store_bf16x32_staged(stage, p.out_bf16 + (r - (threadIdx.x & 31)) * p.out_bf16_ld + col0, p.out_bf16_ld, acc);
+                else
+                    store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
             }
             if (p.out_f32 != nullptr) {
                 const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
@@ -295,7 +333,8 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STORE_STAGE_BYTES = GEMM_EPI_WARPS * 2048;   // per-warp transpose tile of the bf16 store path
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STORE_STAGE_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -309,6 +348,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint64_t* tmem_full = empty_bar + Cfg::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint4* store_stage = reinterpret_cast<uint4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -422,7 +462,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 float acc[32];
                 __syncwarp();
                 tmem_ld32(t0 + ch * 32, acc);
-                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc);
+                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);

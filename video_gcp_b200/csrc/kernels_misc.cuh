@@ -61,38 +61,50 @@ __device__ __forceinline__ void enc_conv_s2(const float* in, float* out, const f
     }
 }
 
-// grid = n_images; image i is written to latent row slot*Bp + i.  If skip outputs are non-null the
-// post-activation layer-0 / layer-2 maps are stored (GetIntermediatesSequential, stride 2).
-__global__ void __launch_bounds__(256) encoder_kernel(const float* __restrict__ img, EncoderWeights W,
-                                                      float* lat_f32, bf16* lat_bf16, int lat_row0,
-                                                      float* skip0, float* skip2, bf16* skip2_bf16) {
+// grid = (n_images, 2): blockIdx.y = 0 encodes the start images (latent rows row0_a + i, skips stored), 1 the goal
+// images (latent rows row0_b + i).  1024 threads per image; activations stay in shared memory.  Skip outputs are the
+// post-activation layer-0 / layer-2 maps (GetIntermediatesSequential, stride 2).
+constexpr int ENC_THREADS = 1024;
+__global__ void __launch_bounds__(ENC_THREADS) encoder_kernel(const float* __restrict__ img_a, const float* __restrict__ img_b,
+                                                              EncoderWeights W, float* lat_f32, bf16* lat_bf16, int row0_a,
+                                                              int row0_b, float* skip0, float* skip2, bf16* skip2_bf16) {
     __shared__ float a0[3 * 32 * 32];
     __shared__ float a1[16 * 16 * 16];
     __shared__ float a2[32 * 8 * 8];
     __shared__ float a3[64 * 4 * 4];
     const int tid = threadIdx.x, i = blockIdx.x;
-    for (int k = tid; k < 3072; k += 256) a0[k] = img[(size_t)i * 3072 + k];
+    const bool goal = blockIdx.y != 0;
+    const float* img = goal ? img_b : img_a;
+    for (int k = tid; k < 3072; k += ENC_THREADS) a0[k] = img[(size_t)i * 3072 + k];
     __syncthreads();
-    enc_conv_s2<3, 16, 32>(a0, a1, W.w0, nullptr, nullptr, W.b0, tid, 256);
+    enc_conv_s2<3, 16, 32>(a0, a1, W.w0, nullptr, nullptr, W.b0, tid, ENC_THREADS);
     __syncthreads();
-    enc_conv_s2<16, 32, 16>(a1, a2, W.w1, W.sc1, W.sh1, nullptr, tid, 256);
+    enc_conv_s2<16, 32, 16>(a1, a2, W.w1, W.sc1, W.sh1, nullptr, tid, ENC_THREADS);
     __syncthreads();
-    enc_conv_s2<32, 64, 8>(a2, a3, W.w2, W.sc2, W.sh2, nullptr, tid, 256);
+    enc_conv_s2<32, 64, 8>(a2, a3, W.w2, W.sc2, W.sh2, nullptr, tid, ENC_THREADS);
     __syncthreads();
-    if (skip0 != nullptr) {
-        for (int k = tid; k < 4096; k += 256) skip0[(size_t)i * 4096 + k] = a1[k];
-        for (int k = tid; k < 1024; k += 256) {
+    if (!goal && skip0 != nullptr) {
+        for (int k = tid; k < 4096; k += ENC_THREADS) skip0[(size_t)i * 4096 + k] = a1[k];
+        for (int k = tid; k < 1024; k += ENC_THREADS) {
             skip2[(size_t)i * 1024 + k] = a3[k];
             skip2_bf16[(size_t)i * 1024 + k] = __float2bfloat16_rn(a3[k]);
         }
     }
-    if (tid < 128) {
-        float s = __ldg(W.b3 + tid);
-        const float* wp = W.w3 + (size_t)tid * 1024;
-        for (int k = 0; k < 1024; ++k) s = fmaf(a3[k], __ldg(wp + k), s);
-        const size_t r = (size_t)lat_row0 + i;
-        lat_f32[r * 128 + tid] = s;
-        lat_bf16[r * 128 + tid] = __float2bfloat16_rn(s);
+    {   // head: conv k4 valid on the 4x4 map = 1024 -> 128 linear; 8 threads per output, fixed summation order
+        const int o = tid >> 3, part = tid & 7;
+        const float* wp = W.w3 + (size_t)o * 1024 + part * 128;
+        const float* ap = a3 + part * 128;
+        float s = 0.f;
+        for (int k = 0; k < 128; ++k) s = fmaf(ap[k], __ldg(wp + k), s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (part == 0) {
+            s += __ldg(W.b3 + o);
+            const size_t r = (size_t)(goal ? row0_b : row0_a) + i;
+            lat_f32[r * 128 + o] = s;
+            lat_bf16[r * 128 + o] = __float2bfloat16_rn(s);
+        }
     }
 }
 
