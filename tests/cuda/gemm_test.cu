@@ -237,7 +237,7 @@ int main() {
         const size_t slot_rows = (size_t)257 * Bp;
         bf16* X = dev_bf16((size_t)rows * H, 1.f);
         bf16* SH = dev_bf16((size_t)rows * 1536, 1.f);
-        float* SC = dev_f32((size_t)rows * 1536, 1.f);
+        bf16* SC = dev_bf16((size_t)rows * 1536, 1.f);
         bf16* Wd = dev_bf16((size_t)N * K, 0.03f);
         float* bias = dev_f32(N, 0.2f);
         bf16* xn_tc = dev_zero<bf16>((size_t)rows * H);
@@ -307,7 +307,7 @@ int main() {
         const int rows = Bp << level, N = 2048, K = 1024;
         bf16* X = dev_bf16((size_t)rows * H, 1.f);
         bf16* SH = dev_bf16((size_t)rows * H, 1.f);
-        float* SC = dev_f32((size_t)rows * H, 1.f);
+        bf16* SC = dev_bf16((size_t)rows * H, 1.f);
         bf16* Wd = dev_bf16((size_t)N * K, 0.03f);
         float* bias = dev_f32(N, 0.2f);
         bf16* xn_tc = dev_zero<bf16>((size_t)rows * H);
@@ -340,7 +340,7 @@ int main() {
         const int rows = 131072, N = 2048, K = 1024, H = 512;
         bf16* X = dev_bf16((size_t)rows * H, 1.f);
         bf16* SH = dev_bf16((size_t)rows * H, 1.f);
-        float* SC = dev_f32((size_t)rows * H, 1.f);
+        bf16* SC = dev_bf16((size_t)rows * H, 1.f);
         bf16* Wd = dev_bf16((size_t)N * K, 0.03f);
         float* bias = dev_f32(N, 0.2f);
         bf16* xn = dev_zero<bf16>((size_t)rows * H);

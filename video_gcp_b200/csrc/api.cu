@@ -87,7 +87,7 @@ struct gcpb200_ctx {
     // workspace
     float* lat_f32 = nullptr;
     DevBuf lat, hid, xa, xb, zeta, sh, ta, tb, s2b, x1, x2, x3, pairs;
-    float *sc = nullptr, *ctxb = nullptr, *logits = nullptr, *s0 = nullptr, *s2 = nullptr, *rowbias2 = nullptr;
+    float *ctxb = nullptr, *logits = nullptr, *s0 = nullptr, *s2 = nullptr, *rowbias2 = nullptr;
     bf16* skip_up = nullptr;
     float *exist_slot = nullptr, *e_df = nullptr, *seq = nullptr, *rowcost = nullptr, *goal_tail = nullptr;
     long long* end_ind = nullptr;
@@ -656,8 +656,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= make_buf(c, &c->xa, NL, HID);
     rc |= make_buf(c, &c->xb, NL, HID);
     rc |= make_buf(c, &c->zeta, NL, NZ_VAE);
-    rc |= make_buf(c, &c->sh, NL, 3 * HID);
-    rc |= dalloc(c, &c->sc, NL * 3 * HID);
+    rc |= make_buf(c, &c->sh, NL, 6 * HID);    // projected parent state: [h0 h1 h2 | c0 c1 c2]
     rc |= make_buf(c, &c->ta, ND, 128);
     rc |= make_buf(c, &c->tb, ND, 128);
     rc |= make_buf(c, &c->s2b, Bp, 1024);
@@ -876,8 +875,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
             a.group_cols = b.group_cols = HID;
             for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
-            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 3 * HID, c->sc, 3 * HID, 6 * HID);
-            e.split_col = 3 * HID;
+            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
             CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e));
         }
         // embed
@@ -893,7 +891,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         for (int i = 0; i < N_LSTM; ++i) {
             EpiParams e;
             memset(&e, 0, sizeof(e));
-            e.c_prev = c->sc; e.c_prev_ld = 3 * HID; e.c_prev_col0 = i * HID;
+            e.c_prev = c->sh.p; e.c_prev_ld = 6 * HID; e.c_prev_col0 = (3 + i) * HID;
             e.out_bf16 = xout->p; e.out_bf16_ld = HID;
             e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
             e.write_hid = (l < DEPTH - 1);

@@ -67,7 +67,7 @@ struct EpiParams {
     float* mu_out;          // optional [B][n_nodes][nz]
     float* ls_out;
     // EPI_LSTM: torch.nn.LSTMCell update, gate order i,f,g,o
-    const float* c_prev;    // projected cell state [rows][c_prev_ld], column window c_prev_col0
+    const bf16* c_prev;     // projected cell state (bf16) [rows][c_prev_ld], column window c_prev_col0
     int c_prev_ld, c_prev_col0;
     bf16* hid;              // slot-major hidden state [slots*Bp][hid_ld]; h at hid_col0+u, c at +H
     int hid_ld, hid_col0, hidden;  // hidden = 512
@@ -296,9 +296,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
     } else if (EPI == EPI_LSTM) {
         // packed columns: [i(8) | f(8) | g(8) | o(8)] for hidden units u0 .. u0+7
         const int u0 = col0 >> 2;
-        const float4* c4 = reinterpret_cast<const float4*>(p.c_prev + (size_t)row * p.c_prev_ld + p.c_prev_col0 + u0);
-        const float4 ca = __ldg(c4), cb = __ldg(c4 + 1);
-        const float cprev[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        const uint4 cp = __ldg(reinterpret_cast<const uint4*>(p.c_prev + (size_t)row * p.c_prev_ld + p.c_prev_col0 + u0));
+        const __nv_bfloat162* cp2 = reinterpret_cast<const __nv_bfloat162*>(&cp);
+        float cprev[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __bfloat1622float2(cp2[i]);
+            cprev[2 * i] = t.x;
+            cprev[2 * i + 1] = t.y;
+        }
         float h[8], c[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
