@@ -55,7 +55,11 @@ typedef struct {
     const float* I_0;        /* [B,3,32,32] (or [1,3,32,32] if images_shared) fp32 in [-1,1] */
     const float* I_g;
     int images_shared;       /* 1: every candidate has the same start/goal image (a CEM call) */
-    const float* z;          /* [B,255,256] noise, depth-first node order */
+    const float* z;          /* [B,255,256] noise, depth-first node order (device) */
+    const float* z_host;     /* optional PINNED HOST copy of the noise: if non-NULL, `z` is only the device staging
+                                buffer; the library uploads z_host -> z level by level on its own copy stream,
+                                overlapped with the encoder and the upper tree levels (cem_simulator.py:19-26 does
+                                this copy up front with torch.tensor(..., device)) */
     const int64_t* end_ind;  /* [B] injected rollout length, or NULL: sample from the length predictor */
     uint64_t seed;           /* RNG seed for length sampling */
     int B;

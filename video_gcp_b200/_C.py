@@ -20,7 +20,7 @@ class Tensor(C.Structure):
 
 
 class RolloutIO(C.Structure):
-    _fields_ = [("I_0", C.c_void_p), ("I_g", C.c_void_p), ("images_shared", C.c_int), ("z", C.c_void_p),
+    _fields_ = [("I_0", C.c_void_p), ("I_g", C.c_void_p), ("images_shared", C.c_int), ("z", C.c_void_p), ("z_host", C.c_void_p),
                 ("end_ind", C.c_void_p), ("seed", C.c_uint64), ("B", C.c_int),
                 ("e_0", C.c_void_p), ("e_g", C.c_void_p), ("seq_len_logits", C.c_void_p),
                 ("end_ind_out", C.c_void_p), ("e_df", C.c_void_p), ("mu_df", C.c_void_p),

@@ -93,6 +93,9 @@ struct gcpb200_ctx {
     long long* end_ind = nullptr;
     long long* scratch_ei = nullptr;
     int* frame_node = nullptr;
+    // overlapped upload of host noise (gcpb200_rollout_io.z_host)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_start = nullptr, ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // optional phase profiling (CUDA events on the caller's stream)
     bool profile = false;
     struct ProfSpan { int phase; cudaEvent_t a, b; };
@@ -683,6 +686,22 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         gcpb200_destroy(c);
         return -1;
     }
+    {
+        cudaError_t ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_copy_start, cudaEventDisableTiming);
+        for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+        if (ce != cudaSuccess) {
+            gcp_set_error("copy stream / event creation failed: %s", cudaGetErrorString(ce));
+            gcpb200_destroy(c);
+            return -1;
+        }
+    }
+    // An SM cannot hold CTAs of kernels that ask for different shared-memory carve-outs: without this the persistent
+    // GEMM / decoder CTAs (200+ KB of shared memory) wait until every block of the upload kernel has left the SM and the
+    // "overlapped" upload serialises with the rollout (measured: tree 6.2 -> 11.1 ms).  So the upload kernel asks for the
+    // same (maximum) carve-out as those kernels, and it only uses 32 blocks (enough for 51 GB/s over PCIe) so that the
+    // small kernels of the rollout that run with the default carve-out still find SMs they can be scheduled on.
+    cudaFuncSetAttribute(upload_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaFuncSetAttribute(dec_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
@@ -697,6 +716,10 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
 
 extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
     if (!c) return;
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_copy_start) cudaEventDestroy(c->ev_copy_start);
+    for (int i = 0; i < 5; ++i)
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     for (void* p : c->allocs) cudaFree(p);
     delete c;
 }
@@ -801,6 +824,20 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     const int goal_row0 = 256 * Bp;
 
     ProfScope total_scope(c, st, 5);
+    if (io->z_host) {
+        // Noise upload, overlapped: the copy stream gathers the rows of levels 0-3, then levels 4, 5, 6, 7 one by one
+        // from pinned host memory; the rollout stream waits for each set just before the level that consumes it.
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy_start, st));       // earlier users of the staging buffer are done
+        GCP_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy_start, 0));
+        const int sets[5][3] = {{16, 15, 15}, {16, 7, 16}, {8, 3, 32}, {4, 1, 64}, {2, 0, 128}};   // node = a*k + b, k < cnt
+        for (int i = 0; i < 5; ++i) {
+            upload_rows_kernel<<<32, 128, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
+                                                                      reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
+                                                                      N_NODES, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
+            LAUNCH_CHECK();
+            GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy[i], c->copy_stream));
+        }
+    }
     ProfScope* scope = new ProfScope(c, st, 0);
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
@@ -843,6 +880,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         const LevelW& L = c->lvl[l];
         const LevelGeom g = {Bp, l, DEPTH};
         const int rows = Bp << l;
+        if (io->z_host && (l == 0 || l >= 4)) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_copy[l == 0 ? 0 : l - 3], 0));
         // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
         CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
         // prior p(z | e_l, e_r) and reparametrisation

@@ -347,6 +347,42 @@ __global__ void sample_noise_kernel(const float* __restrict__ mean, const float*
     reinterpret_cast<float4*>(z)[idx] = o;
 }
 
+// Upload of the noise of one set of tree levels straight from pinned host memory (zero-copy reads over PCIe):
+// rows (cand, node = a*k + b), k < cnt, of the [B][n_nodes][row4 float4] array.  Depth-first node index of level l,
+// position j is (2j+1)*2^(7-l) - 1, so "levels <= L" is (a,b,cnt) = (2^(7-L), a-1, 2^(L+1)-1) and level l alone is
+// (2^(8-l), 2^(7-l)-1, 2^l).
+// Launched with few, small blocks (128 threads, ~40 registers) so that it co-resides with the persistent GEMM / decoder
+// CTAs of the rollout stream instead of taking SMs away from them; PCIe needs < 1 MB of reads in flight.
+__global__ void __launch_bounds__(128) upload_rows_kernel(const float4* __restrict__ src_host, float4* __restrict__ dst,
+                                                          int n_cand, int n_nodes, int row4, int a, int b, int cnt) {
+    const size_t total = (size_t)n_cand * cnt * row4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent 16-byte host reads in flight per thread
+    for (; idx + 3 * stride < total; idx += 4 * stride) {
+        float4 v[4];
+        size_t off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t i = idx + u * stride;
+            const int e = i % row4;
+            const size_t r = i / row4;
+            const int k = r % cnt, c = r / cnt;
+            off[u] = ((size_t)c * n_nodes + (a * k + b)) * row4 + e;
+            v[u] = __ldcs(src_host + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[off[u]] = v[u];
+    }
+    for (; idx < total; idx += stride) {
+        const int e = idx % row4;
+        const size_t r = idx / row4;
+        const int k = r % cnt, c = r / cnt;
+        const size_t o = ((size_t)c * n_nodes + (a * k + b)) * row4 + e;
+        dst[o] = __ldcs(src_host + o);
+    }
+}
+
 // slot-major [n_slots*Bp][cols] (rows = slot, cand) -> candidate-major depth-first [B][n_nodes][cols]
 __global__ void slot_to_df_kernel(const float* __restrict__ src, int Bp, int n_cand, int n_nodes, int cols,
                                   int src_ld, float* __restrict__ dst) {

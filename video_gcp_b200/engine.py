@@ -86,20 +86,28 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
                 want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False):
-        """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32 cuda.
+        """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32, either on the device or a PINNED host
+        tensor; a host tensor is uploaded by the library level by level on its own copy stream, overlapped with
+        the encoder and the upper tree levels (out["z"] is the device copy, valid in stream order after the call).
         Outputs live in persistent buffers owned by the engine (overwritten by the next rollout) unless
         fresh=True."""
         dev = self.device
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
-        assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (N_NODES, NZ_VAE)
+        assert z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (N_NODES, NZ_VAE)
+        z_host = None
+        if not z.is_cuda:
+            if not z.is_pinned():
+                z = z.pin_memory()
+            z_host, z = z, self._buf("z_dev", (B, N_NODES, NZ_VAE))
+            self._z_host_ref = z_host          # keep the host buffer alive until the next call
         I_0 = I_0.to(**f32).contiguous()
         I_g = I_g.to(**f32).contiguous()
         if fresh:
             mk = lambda name, shape, dtype=torch.float32: torch.empty(*shape, device=dev, dtype=dtype)
         else:
             mk = self._buf
-        out = dict(e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
+        out = dict(z=z, e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
                    e_df=mk("e_df", (B, N_NODES, NZ_ENC)))
         if want_logits:
             out["seq_len_logits"] = mk("seq_len_logits", (B, MAX_LEN))
@@ -117,7 +125,7 @@ class Engine:
         if end_ind is not None:
             end_ind = end_ind.to(device=dev, dtype=torch.int64).contiguous()
         io = _C.RolloutIO(
-            _ptr(I_0), _ptr(I_g), int(images_shared), _ptr(z), _ptr(end_ind), int(seed), int(B),
+            _ptr(I_0), _ptr(I_g), int(images_shared), _ptr(z), _ptr(z_host), _ptr(end_ind), int(seed), int(B),
             _ptr(out["e_0"]), _ptr(out["e_g"]), _ptr(out.get("seq_len_logits")), _ptr(out["end_ind"]),
             _ptr(out["e_df"]), _ptr(out.get("mu_df")), _ptr(out.get("log_sigma_df")), _ptr(out.get("images_df")),
             _ptr(out.get("existence")), _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")),

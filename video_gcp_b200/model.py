@@ -223,7 +223,9 @@ class TreeModel(nn.Module):
         z = inputs.z
         if z.dim() == 5:
             z = z[..., 0, 0]
-        z = z.to(device=dev, dtype=torch.float32).contiguous()
+        if z.is_cuda or not (z.dtype == torch.float32 and z.is_pinned()):
+            z = z.to(device=dev, dtype=torch.float32)      # pinned fp32 host noise is uploaded by the library itself
+        z = z.contiguous()
         B = z.shape[0]
         inject = self.inject_end_ind
         if not (self._use_pred_length and self._hp.length_pred_weight > 0) and "end_ind" in inputs:
@@ -240,6 +242,7 @@ class TreeModel(nn.Module):
         inputs.e_g = res["e_g"][..., None, None]
         outputs.seq_len_logits = res["seq_len_logits"]
         outputs.end_ind = res["end_ind"]
+        outputs.z_device = res["z"]
         fields = dict(e_g_prime=res["e_df"][..., None, None])
         if "images_df" in res:
             fields["images"] = res["images_df"]

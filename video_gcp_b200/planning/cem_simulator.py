@@ -18,6 +18,7 @@ class DeviceRollouts:
         self.end_ind = torch.max(outputs.end_ind, torch.ones_like(outputs.end_ind))   # cem_simulator.py:31
         self.images_df = outputs.tree.df.images if "images" in outputs.tree._fields else None
         self.e_df = outputs.tree.df.e_g_prime[..., 0, 0]
+        self.z = outputs.z_device          # device copy of the noise that was rolled out
 
     def __len__(self):
         return int(self.end_ind.shape[0])
@@ -62,9 +63,11 @@ class GCPSimulator:
         dev = self._model.engine.device
         B = samples.shape[0]
         if isinstance(samples, torch.Tensor):
-            z = samples.to(device=dev, dtype=torch.float32)
+            # CUDA tensors stay where they are; pinned fp32 host tensors are uploaded by the library, overlapped
+            z = samples if (samples.is_cuda or (samples.dtype == torch.float32 and samples.is_pinned())) \
+                else samples.to(device=dev, dtype=torch.float32)
         else:
-            z = torch.as_tensor(np.ascontiguousarray(samples, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+            z = torch.as_tensor(np.ascontiguousarray(samples, dtype=np.float32)).pin_memory()
         # start / goal are converted on the host (12 KB each) and uploaded once: every candidate shares them
         input_dict = AttrDict(
             I_0=torch.as_tensor(np.asarray(state), dtype=torch.float32),
