@@ -31,6 +31,10 @@ UNIT = "rollouts/s"
 FLOP_PER_ROLLOUT = 16.754e9          # canonical work, BASELINE.md section 3 (8.377 GMAC)
 TAIL_FLOP_PER_IMAGE = 2 * (8.388608e6 + 7.8643e6)   # the two full-resolution decoder convolutions
 ELITE_FRAC = 0.1
+# DRAM traffic of one decoder-tail launch at 1024 candidates (65 280 node images): dram__bytes_read.sum +
+# dram__bytes_write.sum of one `ncu --set full` capture, profiles/r1e_dec_tail3_ncu_full.txt.  Algorithmic I/O of
+# the same launch is 534.8 MB read (bf16 layer-3 maps) + 802.2 MB written (fp32 images): no re-reads.
+TAIL_TRAFFIC_BYTES_B1024 = 537.23e6 + 758.86e6
 
 
 def workload(cands):
@@ -263,7 +267,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "dec_tail3_kernel", "achieved": tail_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": tail_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": tail_tf / peak_tf,
+                     "traffic": TAIL_TRAFFIC_BYTES_B1024 if B == 1024 else None,
+                     "traffic_note": "bytes per launch, ncu dram read+write (profiles/r1e_dec_tail3_ncu_full.txt)",
+                     "peak_source": peak_src,
                      "ms_per_launch": tail_ms, "images_per_launch": tail_imgs},
         "roofline_step": {"bound": "tensor", "achieved": value / world * FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf,
                           "unit": "TFLOP/s per GPU (canonical 16.75 GFLOP/rollout)",

@@ -289,6 +289,98 @@ def simulator_rollout(sd, state, goal, samples, end_ind, append_latent=True):
 
 
 # --------------------------------------------------------------------------------------------------
+# sequential GCP (config 3): VRNN prior rollout
+# --------------------------------------------------------------------------------------------------
+def seq_latent_rollout(sd, e0, eg, z, n_lstm=3):
+    """SequentialRecModule.forward + VRNNCell.forward/init_state with injected z, prior branch
+    (gcp/prediction/models/sequential.py:33-58; blox/torch/models/vrnn.py:54-110;
+    blox/torch/recurrent_modules.py:21-53,195-223,239-259).  The inference LSTM / q(z) are computed by the
+    reference but never reach the rollout outputs the planner reads, so they are not restated.
+
+    e0, eg [B,128]; z [B,T,256].  Per step t: p_z = prior(x_t); zeta = exp(log_sigma) * z_t + mu;
+    x_{t+1} = gen_lstm(cat(x_t, zeta, e0, eg)); x_0 = e0; LSTM state = init_module(cat(e0, eg)), laid out
+    [h0,c0,h1,c1,h2,c2] (var2state, recurrent_modules.py:183-187).
+    Returns encodings [B,T,128], mu/log_sigma [B,T,256]."""
+    cell = "dense_rec.lstm.cell."
+    g = cell + "gen_lstm."
+    ctx = torch.cat([e0, eg], 1)
+    state = mlp(sd, g + "init_module", ctx, n_layers=1, conv=False)
+    H = state.shape[1] // (2 * n_lstm)
+    hs = [state[:, 2 * i * H:(2 * i + 1) * H] for i in range(n_lstm)]
+    cs = [state[:, (2 * i + 1) * H:(2 * i + 2) * H] for i in range(n_lstm)]
+    x = e0
+    enc, mus, lss = [], [], []
+    for t in range(z.shape[1]):
+        pz = mlp(sd, cell + "prior", x)
+        mu, log_sigma = pz[:, :256], pz[:, 256:]
+        zeta = log_sigma.exp() * z[:, t] + mu
+        h_in = F.linear(torch.cat([x, zeta, ctx], 1), sd[g + "embed.weight"], sd[g + "embed.bias"])
+        for i in range(n_lstm):
+            hs[i], cs[i] = lstm_cell(h_in, hs[i], cs[i], sd[g + "lstm.%d.weight_ih" % i], sd[g + "lstm.%d.weight_hh" % i],
+                                     sd[g + "lstm.%d.bias_ih" % i], sd[g + "lstm.%d.bias_hh" % i])
+            h_in = hs[i]
+        x = F.linear(h_in, sd[g + "output.weight"], sd[g + "output.bias"])
+        enc.append(x)
+        mus.append(mu)
+        lss.append(log_sigma)
+    return dict(encodings=torch.stack(enc, 1), mu=torch.stack(mus, 1), log_sigma=torch.stack(lss, 1))
+
+
+def seq_rollout(sd, I_0, I_g, z, given_end_ind, decode=True):
+    """SequentialModel forward in val_mode with injected z, default phase='train' as the simulator calls it
+    (gcp/prediction/models/base_gcp.py:140-161,234-262,361-374; gcp/prediction/models/sequential.py:33-58,
+    78-94).  z [B,199,256]; given_end_ind [B] = inputs.end_ind (the simulator passes rollout_len - 1).
+
+    Returns e0, eg, seq_len_logits, encodings [B,199,128], mu, log_sigma, images [B,200,3,32,32] (frame 0 is
+    I_0 itself), model_enc_seq = pad(cat(e0, encodings)[:given_end_ind + 1]), actions, regressed_state."""
+    out = {}
+    e0, (s0, s2) = encoder(sd, I_0)
+    eg, _ = encoder(sd, I_g)
+    out["e0"], out["eg"] = e0, eg
+    out["seq_len_logits"] = length_logits(sd, e0, eg)
+    lat = seq_latent_rollout(sd, e0, eg, z)
+    out.update(lat)
+    B, T = z.shape[:2]
+    if decode:
+        imgs = decoder(sd, lat["encodings"].reshape(B * T, 128), s0.repeat_interleave(T, 0), s2.repeat_interleave(T, 0))
+        out["images"] = torch.cat([I_0[:, None], imgs.reshape(B, T, 3, 32, 32)], 1)
+    full = torch.cat([e0[:, None], lat["encodings"]], 1)
+    seqs = [full[b, :int(e) + 1] for b, e in enumerate(given_end_ind)]
+    enc_seq = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)
+    out["model_enc_seq"] = enc_seq
+    pairs = torch.cat([enc_seq[:, :-1], enc_seq[:, 1:]], 2)
+    out["actions"] = mlp(sd, "inv_mdl.action_pred", pairs.reshape(-1, 256), conv=False).reshape(B, -1, 2)
+    out["regressed_state"] = mlp(sd, "state_regressor", enc_seq.reshape(-1, 128), conv=False).reshape(B, -1, 2)
+    return out
+
+
+def seq_simulator_rollout(sd, state, goal, samples, end_ind, append_latent=True, rollout_len=200):
+    """GCPImageSimulator.rollout over the sequential model (gcp/planning/cem/cem_simulator.py:14-43,80-96) with
+    the sampled rollout length replaced by the injected `end_ind`.  samples numpy [B,199,256]."""
+    B = samples.shape[0]
+
+    def env2planner(img):
+        img = torch.tensor(np.repeat(img, B, 0), dtype=torch.float32)
+        if img.max() > 1.0:
+            img = img / 255.0
+        return img.permute(0, 3, 1, 2) * 2 - 1.0
+
+    out = seq_rollout(sd, env2planner(state), env2planner(goal), torch.tensor(samples, dtype=torch.float32),
+                      np.full(B, rollout_len - 1))
+    end = np.maximum(np.asarray(end_ind), 1)
+    full = torch.cat([out["e0"][:, None], out["encodings"]], 1)
+    preds = []
+    for b in range(B):
+        r = out["images"][b, :end[b] + 1].reshape(end[b] + 1, -1)
+        if append_latent:
+            r = torch.cat([r, full[b, :end[b] + 1]], -1)
+        preds.append(r.numpy())
+    cap = lambda v: [v[b, :end[b] + 1].numpy() for b in range(B)]
+    return dict(predictions=preds, actions=cap(out["actions"]), states=cap(out["regressed_state"]),
+                latents=cap(out["model_enc_seq"]))
+
+
+# --------------------------------------------------------------------------------------------------
 # costs, elites, refit
 # --------------------------------------------------------------------------------------------------
 def l2_image_cost(image_seqs, goal_raw, dense_cost=True, final_step_weight=1.0):

@@ -67,6 +67,22 @@ def gcp_tree_25room_config(**extra):
     return cfg
 
 
+def gcp_sequential_25room_config(**extra):
+    """The 25-room sequential GCP model config: experiments/prediction/25room/gcp_sequential/conf.py:20-43
+    layered over experiments/prediction/base_configs/gcp_sequential.py:9-14 (`add_weighted_pixel_copy`
+    popped as the experiment does; `attach_cost_mdl` is a training-time head and off by default here)."""
+    cfg = AttrDict(
+        one_step_planner='continuous', dense_rec_type='svg', hierarchy_levels=0,
+        state_dim=2, ngf=16, max_seq_len=200, nz_mid_lstm=1024, n_lstm_layers=3,
+        nz_mid=128, nz_enc=128, nz_vae=256, regress_length=True, attach_state_regressor=True,
+        attach_inv_mdl=True,
+        inv_mdl_params=AttrDict(n_actions=2, use_convs=False, build_encoder=False),
+        decoder_distribution='discrete_logistic_mixture',
+    )
+    cfg.update(extra)
+    return cfg
+
+
 def build_hparams(params):
     """defaults + overrides, the way BaseGCPModel.__init__ does it (base_gcp.py:30-41)."""
     hp = default_hparams()

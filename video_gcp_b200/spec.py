@@ -39,6 +39,21 @@ def _predictor(out, prefix, d_in, d_mid, d_out, n_layers, conv, ksz=(3, 3)):
     out["%s.head.%s.bias" % (prefix, lname)] = ((d_out,), B_)
 
 
+def _init_lstm_cell(out, prefix, d_in, d_out, H, L, reset_in, nz_mid):
+    """InitLSTMCell naming (blox/torch/recurrent_modules.py:126-162,239-253): CustomLSTMCell + init_module."""
+    out[prefix + ".initial_hidden"] = ((1, 2 * H * L), ZEROS)
+    out[prefix + ".embed.weight"] = ((H, d_in), W)
+    out[prefix + ".embed.bias"] = ((H,), B_)
+    for i in range(L):
+        out[prefix + ".lstm.%d.weight_ih" % i] = ((4 * H, H), LSTM_W)
+        out[prefix + ".lstm.%d.weight_hh" % i] = ((4 * H, H), LSTM_W)
+        out[prefix + ".lstm.%d.bias_ih" % i] = ((4 * H,), LSTM_B)
+        out[prefix + ".lstm.%d.bias_hh" % i] = ((4 * H,), LSTM_B)
+    out[prefix + ".output.weight"] = ((d_out, H), W)
+    out[prefix + ".output.bias"] = ((d_out,), B_)
+    _predictor(out, prefix + ".init_module", reset_in, nz_mid, 2 * H * L, 1, False)
+
+
 def n_conv_layers(img_sz):
     n = math.log2(img_sz)
     assert n == round(n) and n >= 3
@@ -101,9 +116,19 @@ def canonical_entries(hp):
         _predictor(out, "cost_mdl.cost_pred", 2 * 128, 128, 1, 3, False)        # CostModel defaults
     if hp.attach_state_regressor:
         _predictor(out, "state_regressor", hp.nz_enc, hp.nz_mid, hp.state_dim, hp.n_processing_layers, False)
+    H, L = hp.nz_mid_lstm, hp.n_lstm_layers
+    if hp.dense_rec_type == "svg":
+        # ---- sequential GCP: VRNNCell (blox/torch/models/vrnn.py:24-52) behind SequentialRecModule
+        # (gcp/prediction/models/sequential.py:15-31); no tree modules
+        cell = "dense_rec.lstm.cell."
+        ctx = 2 * hp.nz_enc if hp.context_every_step else 0
+        for name, d_in in (("inf_lstm", hp.nz_enc + ctx), ("gen_lstm", hp.nz_enc + hp.nz_vae + ctx)):
+            _init_lstm_cell(out, cell + name, d_in, hp.nz_enc, H, L, 2 * hp.nz_enc, hp.nz_mid)
+        _predictor(out, cell + "inf", hp.nz_enc, hp.nz_mid, 2 * hp.nz_vae, hp.n_processing_layers, True)
+        _predictor(out, cell + "prior", hp.nz_enc, hp.nz_mid, 2 * hp.nz_vae, hp.n_processing_layers, True)
+        return out
     # ---- tree modules (one per level when untied)
     n_mod = hp.hierarchy_levels if hp.untied_layers else 1
-    H, L = hp.nz_mid_lstm, hp.n_lstm_layers
     state_dim = 2 * H * L
     pred_in = 2 * hp.nz_enc + hp.nz_vae + (2 * hp.nz_enc if hp.context_every_step else 0)
     for k in range(n_mod):
@@ -134,6 +159,8 @@ def aliases(hp):
     """List of (alias_prefix, canonical_prefix): every key starting with canonical_prefix also appears
     with alias_prefix substituted."""
     al = [("dense_rec.decoder", "decoder")]
+    if hp.dense_rec_type == "svg":
+        return al
     n_mod = hp.hierarchy_levels if hp.untied_layers else 1
     for k in range(n_mod):
         tm = "tree_module.tree_modules.%d." % k if hp.untied_layers else "tree_module."

@@ -85,3 +85,19 @@ def synthetic_rollout_inputs(n_candidates, seed=0, z_std=1.0, shared_images=True
     end_ind = r.integers(end_ind_range[0], end_ind_range[1], size=(n_candidates,)).astype(np.int64)
     return dict(I_0=torch.from_numpy(I_0), I_g=torch.from_numpy(I_g), z=torch.from_numpy(z),
                 end_ind=torch.from_numpy(end_ind))
+
+
+def synthetic_seq_inputs(n_candidates, seed=0, z_std=1.0, shared_images=True, n_steps=199):
+    """Inputs of the sequential GCP rollout: start/goal images in [-1,1] and noise z [B,199,256] (one latent
+    per predicted frame), seeded."""
+    r = np.random.default_rng([int(seed), 54321])
+    nimg = 1 if shared_images else n_candidates
+    I_0 = r.uniform(-1, 1, size=(nimg, 3, 32, 32)).astype(np.float32)
+    I_g = r.uniform(-1, 1, size=(nimg, 3, 32, 32)).astype(np.float32)
+    if shared_images:
+        I_0 = np.repeat(I_0, n_candidates, 0)
+        I_g = np.repeat(I_g, n_candidates, 0)
+    z = (r.standard_normal(size=(n_candidates, n_steps, 256)) * z_std).astype(np.float32)
+    end_ind = r.integers(2, n_steps + 1, size=(n_candidates,)).astype(np.int64)
+    return dict(I_0=torch.from_numpy(I_0), I_g=torch.from_numpy(I_g), z=torch.from_numpy(z),
+                end_ind=torch.from_numpy(end_ind))
