@@ -3,6 +3,9 @@
  * This is the drop-in boundary: each entry point replaces one piece of the reference's Python hot path
  * (paths relative to the reference repository orybkin/video-gcp):
  *
+ *   gcpb200_seq_rollout    SequentialModel forward in val_mode: SequentialRecModule.forward + VRNNCell prior branch +
+ *                          decode_seq + run_auxilliary_models (gcp/prediction/models/sequential.py:33-58;
+ *                          blox/torch/models/vrnn.py:54-110; blox/torch/recurrent_modules.py:21-53,195-259)
  *   gcpb200_rollout        BaseGCPModel.forward in val_mode, i.e. run_encoder + get_end_ind +
  *                          TreeModel.predict_sequence + run_auxilliary_models
  *                          (gcp/prediction/models/base_gcp.py:140-161,184-262,
@@ -40,7 +43,14 @@ typedef struct {
     int attach_cost_mdl; /* 1: expect cost_mdl.cost_pred.* weights (learned cost available) */
     int use_ref_kernels; /* 1: verification mode, SIMT kernels instead of tcgen05 (tests only) */
     int decoder_slot_chunk; /* decoder processes this many tree slots per pass (0 = default 64) */
+    int model;           /* GCPB200_MODEL_TREE (0) or GCPB200_MODEL_SEQUENTIAL (1): which reference model the context
+                            holds (TreeModel, gcp/prediction/models/tree/tree.py:14; SequentialModel,
+                            gcp/prediction/models/sequential.py:104) */
 } gcpb200_config;
+
+#define GCPB200_MODEL_TREE 0
+#define GCPB200_MODEL_SEQUENTIAL 1
+#define GCPB200_SEQ_STEPS 199   /* max_seq_len - 1 predicted frames (sequential.py:50) */
 
 /* one fp32 host tensor of the reference state dict */
 typedef struct {
@@ -78,6 +88,35 @@ typedef struct {
     float* regressed_state;  /* [B,200,2] state regressor (use [:, :Lmax]) */
 } gcpb200_rollout_io;
 
+/* I/O of the sequential GCP rollout (SequentialModel forward in val_mode with injected z, default phase as the
+ * simulator calls it: gcp/prediction/models/sequential.py:33-58,78-94; blox/torch/models/vrnn.py:54-110;
+ * base_gcp.py:140-161,234-262).  The inference LSTM / q(z) of the VRNN cell do not reach any rollout output
+ * and are not computed. */
+typedef struct {
+    /* ---- inputs ---- */
+    const float* I_0;        /* [B,3,32,32] (or [1,3,32,32] if images_shared) fp32 in [-1,1] */
+    const float* I_g;
+    int images_shared;
+    const float* z;          /* [B,199,256] noise, one row per predicted frame (device) */
+    const int64_t* end_ind;  /* [B] injected predicted rollout length, or NULL: sample from the length predictor */
+    const int64_t* given_end_ind; /* [B] inputs.end_ind (the simulator passes rollout_len-1), or NULL = 199: length of
+                                     cat(e_0, encodings) kept in model_enc_seq (get_matched_pruned_seqs, base_gcp.py:361-374) */
+    uint64_t seed;
+    int B;
+    /* ---- outputs (any may be NULL) ---- */
+    float* e_0;              /* [B,128] */
+    float* e_g;              /* [B,128] */
+    float* seq_len_logits;   /* [B,200] */
+    int64_t* end_ind_out;    /* [B] */
+    float* encodings;        /* [B,199,128] predicted latents (outputs.dense_rec.encodings) */
+    float* mu;               /* [B,199,256] prior mean per step */
+    float* log_sigma;        /* [B,199,256] */
+    float* images;           /* [B,200,3,32,32]: frame 0 = I_0, frames 1..199 decoded (outputs.dense_rec.images) */
+    float* model_enc_seq;    /* [B,200,128] cat(e_0, encodings)[:given_end_ind+1], zero padded */
+    float* actions;          /* [B,200,2] inverse model on consecutive rows of model_enc_seq (use [:, :Lmax-1]) */
+    float* regressed_state;  /* [B,200,2] */
+} gcpb200_seq_io;
+
 const char* gcpb200_last_error(void);
 const char* gcpb200_version(void);
 
@@ -89,6 +128,14 @@ void gcpb200_destroy(gcpb200_ctx* ctx);
 int gcpb200_load_weights(gcpb200_ctx* ctx, const gcpb200_tensor* tensors, int n_tensors);
 
 int gcpb200_rollout(gcpb200_ctx* ctx, const gcpb200_rollout_io* io, void* stream);
+
+/* Sequential GCP rollout; the context must have been created with model = GCPB200_MODEL_SEQUENTIAL. */
+int gcpb200_seq_rollout(gcpb200_ctx* ctx, const gcpb200_seq_io* io, void* stream);
+
+/* L2 image cost over image sequences stored in time order, images [B,n_frames,3,32,32] (sequential model):
+ * L2ImageCost._compute on rollouts[i][:end_ind[i]+1] (gcp/planning/cem/cost_fcn.py:9-22,65-72). */
+int gcpb200_cost_l2_seq(gcpb200_ctx* ctx, const float* images, int n_frames, const int64_t* end_ind, const float* goal,
+                        int B, int dense, float final_step_weight, float* cost /* [B] */, void* stream);
 
 /* dst[c,t,:] = src[c, node_of_frame(c,t), :] for t <= end_ind[c], zeros after.  row_len % 4 == 0. */
 int gcpb200_prune_gather(gcpb200_ctx* ctx, const float* src_df, const int64_t* end_ind, int B, int row_len,

@@ -12,7 +12,10 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgcpb200.
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("max_candidates", C.c_int), ("attach_cost_mdl", C.c_int),
-                ("use_ref_kernels", C.c_int), ("decoder_slot_chunk", C.c_int)]
+                ("use_ref_kernels", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int)]
+
+
+MODEL_TREE, MODEL_SEQUENTIAL = 0, 1
 
 
 class Tensor(C.Structure):
@@ -28,6 +31,14 @@ class RolloutIO(C.Structure):
                 ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p)]
 
 
+class SeqIO(C.Structure):
+    _fields_ = [("I_0", C.c_void_p), ("I_g", C.c_void_p), ("images_shared", C.c_int), ("z", C.c_void_p),
+                ("end_ind", C.c_void_p), ("given_end_ind", C.c_void_p), ("seed", C.c_uint64), ("B", C.c_int),
+                ("e_0", C.c_void_p), ("e_g", C.c_void_p), ("seq_len_logits", C.c_void_p), ("end_ind_out", C.c_void_p),
+                ("encodings", C.c_void_p), ("mu", C.c_void_p), ("log_sigma", C.c_void_p), ("images", C.c_void_p),
+                ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "gcpb200_last_error": (C.c_char_p, []),
@@ -36,6 +47,9 @@ EXPORTS = {
     "gcpb200_destroy": (None, [C.c_void_p]),
     "gcpb200_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_int]),
     "gcpb200_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutIO), C.c_void_p]),
+    "gcpb200_seq_rollout": (C.c_int, [C.c_void_p, C.POINTER(SeqIO), C.c_void_p]),
+    "gcpb200_cost_l2_seq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                      C.c_void_p, C.c_void_p]),
     "gcpb200_prune_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gcpb200_cost_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                   C.c_void_p, C.c_void_p]),

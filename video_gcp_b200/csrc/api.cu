@@ -62,6 +62,12 @@ struct Mlp {              // BaseProcessingNet: in(+bias,LReLU) -> 3x[lin, Group
     int mid_k = 128;      // K of the mid/head layers (mid width padded to 64)
     int mid_valid = 128;  // columns written by in/mid layers
     int n_out = 0;
+    int n_mid = 3;        // number of [lin, GroupNorm, LReLU] layers (odd, so the body ends in ctx->tb)
+};
+struct SeqW {             // VRNNCell of the sequential GCP model (prior + gen_lstm; blox/torch/models/vrnn.py:24-52)
+    Mlp prior;            // 128 -> 128 x3 -> 512 (mu | log sigma, interleaved for the reparametrisation epilogue)
+    Mlp init;             // init_module: 256 -> 128 -> 6144, head rows packed [h0 h1 h2 | c0 c1 c2]
+    DevMat embed_main, embed_ctx, lstm[3], out;
 };
 struct LevelW {
     Mlp prior;
@@ -78,6 +84,17 @@ struct gcpb200_ctx {
     std::vector<void*> allocs;
     // weights
     LevelW lvl[8];
+    SeqW seqw;
+    int model = 0, n_slots = 257, lstm_hid = 512;
+    DevBuf hs[2];            // sequential: bf16 h state [Bp][3 * 1024], ping-pong by step parity
+    float* cs = nullptr;     // sequential: fp32 c state [Bp][3 * 1024]
+    // sequential: the 199-step recurrence (~2000 dependent launches) is captured once per (noise buffer, prior output
+    // buffers, B) into a CUDA graph and replayed; the host cost of a rollout drops from ~35 ms of launches to one
+    struct SeqGraph { const void *z, *mu, *ls; int B; cudaGraphExec_t exec; int64_t launches; };
+    std::vector<SeqGraph> seq_graphs;
+    bool seq_graph_on = true, seq_warm = false;
+    cudaStream_t seq_stream = nullptr;   // capture / replay stream (the caller's stream may be the legacy default stream,
+    cudaEvent_t ev_seq_fork = nullptr, ev_seq_join = nullptr;   // which cannot be captured); fork/join by events
     Mlp length_pred, existence, inv_mdl, state_reg, cost_mdl;
     bool has_cost = false;
     EncoderWeights enc;
@@ -92,6 +109,7 @@ struct gcpb200_ctx {
     float *exist_slot = nullptr, *e_df = nullptr, *seq = nullptr, *rowcost = nullptr, *goal_tail = nullptr;
     long long* end_ind = nullptr;
     long long* scratch_ei = nullptr;
+    long long* scratch_given = nullptr;
     int* frame_node = nullptr;
     // overlapped upload of host noise (gcpb200_rollout_io.z_host)
     cudaStream_t copy_stream = nullptr;
@@ -229,8 +247,9 @@ static int get_lin(const WStore& ws, const std::string& prefix, bool conv, bool 
 // head_perm: packed row -> original row (or -1 for a zero row); null = identity
 static int pack_mlp(gcpb200_ctx* c, const WStore& ws, const std::string& prefix, bool conv, int d_in, int mid,
                     int d_out, int head_N, const std::function<int(int)>& head_perm, Mlp* m, DevMat* head2 = nullptr,
-                    int head2_row0 = 0) {
+                    int head2_row0 = 0, int n_mid = 3) {
     Lin in, md[3], hd;
+    m->n_mid = n_mid;
     CHECK(get_lin(ws, prefix + ".input", conv, true, &in));
     if (in.I != d_in || in.O != mid) {
         gcp_set_error("%s.input: got [%d,%d], expected [%d,%d]", prefix.c_str(), in.O, in.I, mid, d_in);
@@ -241,7 +260,7 @@ static int pack_mlp(gcpb200_ctx* c, const WStore& ws, const std::string& prefix,
     m->gn_group = mid / 8;
     m->n_out = d_out;
     CHECK(upload_mat(c, &m->in, 128, d_in, [&](int n, int k) { return in.at(n, k); }, [&](int n) { return in.bias(n); }));
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < n_mid; ++i) {
         const std::string p = prefix + ".pyramid-" + std::to_string(i);
         CHECK(get_lin(ws, p, conv, false, &md[i]));
         CHECK(upload_mat(c, &m->mid[i], 128, m->mid_k, [&](int n, int k) { return md[i].at(n, k); }, nullptr));
@@ -484,6 +503,29 @@ static int pack_encoder(gcpb200_ctx* c, const WStore& ws) {
     return 0;
 }
 
+// LSTMCell weights packed for the EPI_LSTM epilogue: [W_ih | W_hh] along K, rows gate-interleaved so that a
+// 32-column accumulator chunk holds i,f,g,o of 8 hidden units: packed row p = tile*256 + chunk*32 + gate*8 + u
+// <-> gate*H + tile*64 + chunk*8 + u.
+static int pack_lstm_cell(gcpb200_ctx* c, const WStore& ws, const std::string& lp, int H, DevMat* d) {
+    const gcpb200_tensor *wih = ws.get(lp + "weight_ih", 2), *whh = ws.get(lp + "weight_hh", 2),
+                         *bih = ws.get(lp + "bias_ih", 1), *bhh = ws.get(lp + "bias_hh", 1);
+    if (!wih || !whh || !bih || !bhh) return -1;
+    if (wih->shape[0] != 4 * H || wih->shape[1] != H || whh->shape[1] != H) {
+        gcp_set_error("%sweight_ih: expected [%d,%d]", lp.c_str(), 4 * H, H);
+        return -1;
+    }
+    auto orig = [H](int p) {
+        const int tile = p >> 8, chunk = (p >> 5) & 7, gate = (p >> 3) & 3, u = p & 7;
+        return gate * H + tile * 64 + chunk * 8 + u;
+    };
+    return upload_mat(c, d, 4 * H, 2 * H,
+                      [&](int n, int k) {
+                          const int o = orig(n);
+                          return k < H ? wih->data[(size_t)o * H + k] : whh->data[(size_t)o * H + k - H];
+                      },
+                      [&](int n) { const int o = orig(n); return bih->data[o] + bhh->data[o]; });
+}
+
 static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     LevelW& L = c->lvl[l];
     const std::string tm = "tree_module.tree_modules." + std::to_string(l) + ".";
@@ -519,27 +561,49 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     CHECK(upload_mat(c, &L.embed_ctx, HID, 2 * NZ_ENC,
                      [&](int n, int k) { return we->data[(size_t)n * EIN + 2 * NZ_ENC + NZ_VAE + k]; },
                      [&](int n) { return be->data[n]; }));
-    for (int i = 0; i < N_LSTM; ++i) {
-        const std::string lp = sp + "lstm." + std::to_string(i) + ".";
-        const gcpb200_tensor *wih = ws.get(lp + "weight_ih", 2), *whh = ws.get(lp + "weight_hh", 2),
-                             *bih = ws.get(lp + "bias_ih", 1), *bhh = ws.get(lp + "bias_hh", 1);
-        if (!wih || !whh || !bih || !bhh) return -1;
-        // packed row p = tile*256 + chunk*32 + gate*8 + u  <->  gate*512 + tile*64 + chunk*8 + u
-        auto orig = [](int p) {
-            const int tile = p >> 8, chunk = (p >> 5) & 7, gate = (p >> 3) & 3, u = p & 7;
-            return gate * HID + tile * 64 + chunk * 8 + u;
-        };
-        CHECK(upload_mat(c, &L.lstm[i], 4 * HID, 2 * HID,
-                         [&](int n, int k) {
-                             const int o = orig(n);
-                             return k < HID ? wih->data[(size_t)o * HID + k] : whh->data[(size_t)o * HID + k - HID];
-                         },
-                         [&](int n) { const int o = orig(n); return bih->data[o] + bhh->data[o]; }));
-    }
+    for (int i = 0; i < N_LSTM; ++i) CHECK(pack_lstm_cell(c, ws, sp + "lstm." + std::to_string(i) + ".", HID, &L.lstm[i]));
     const gcpb200_tensor* wo = ws.get(sp + "output.weight", 2);
     const gcpb200_tensor* bo = ws.get(sp + "output.bias", 1);
     if (!wo || !bo) return -1;
     CHECK(upload_mat(c, &L.out, NZ_ENC, HID, [&](int n, int k) { return wo->data[(size_t)n * HID + k]; },
+                     [&](int n) { return bo->data[n]; }));
+    return 0;
+}
+
+// VRNNCell weights of the sequential model (dense_rec.lstm.cell.{prior,gen_lstm}); inf_lstm / inf are not on the
+// rollout path.
+static int pack_sequential(gcpb200_ctx* c, const WStore& ws) {
+    SeqW& S = c->seqw;
+    const std::string cell = "dense_rec.lstm.cell.", g = cell + "gen_lstm.";
+    const int H = c->lstm_hid;
+    auto reparam_perm = [](int p) {
+        const int tile = p >> 8, chunk = (p >> 5) & 7, part = (p >> 4) & 1, u = p & 15;
+        return part * 256 + tile * 128 + chunk * 16 + u;
+    };
+    CHECK(pack_mlp(c, ws, cell + "prior", true, NZ_ENC, NZ_MID, 2 * NZ_VAE, 512, reparam_perm, &S.prior));
+    // init_module head: reference columns [h0 c0 h1 c1 h2 c2] (var2state) -> packed [h0 h1 h2 | c0 c1 c2]
+    auto init_perm = [H](int p) {
+        const int is_c = p >= 3 * H, q = p - (is_c ? 3 * H : 0), layer = q / H, u = q % H;
+        return (2 * layer + is_c) * H + u;
+    };
+    CHECK(pack_mlp(c, ws, g + "init_module", false, 2 * NZ_ENC, NZ_MID, 6 * H, 6 * H, init_perm, &S.init, nullptr, 0, 1));
+    const gcpb200_tensor* we = ws.get(g + "embed.weight", 2);
+    const gcpb200_tensor* be = ws.get(g + "embed.bias", 1);
+    if (!we || !be) return -1;
+    const int EIN = 3 * NZ_ENC + NZ_VAE;   // 640 = [x, z, e_0, e_g]
+    if (we->shape[0] != H || we->shape[1] != EIN) {
+        gcp_set_error("gen_lstm.embed.weight: expected [%d,%d]", H, EIN);
+        return -1;
+    }
+    CHECK(upload_mat(c, &S.embed_main, H, NZ_ENC + NZ_VAE, [&](int n, int k) { return we->data[(size_t)n * EIN + k]; }, nullptr));
+    CHECK(upload_mat(c, &S.embed_ctx, H, 2 * NZ_ENC,
+                     [&](int n, int k) { return we->data[(size_t)n * EIN + NZ_ENC + NZ_VAE + k]; },
+                     [&](int n) { return be->data[n]; }));
+    for (int i = 0; i < N_LSTM; ++i) CHECK(pack_lstm_cell(c, ws, g + "lstm." + std::to_string(i) + ".", H, &S.lstm[i]));
+    const gcpb200_tensor* wo = ws.get(g + "output.weight", 2);
+    const gcpb200_tensor* bo = ws.get(g + "output.bias", 1);
+    if (!wo || !bo) return -1;
+    CHECK(upload_mat(c, &S.out, NZ_ENC, H, [&](int n, int k) { return wo->data[(size_t)n * H + k]; },
                      [&](int n) { return bo->data[n]; }));
     return 0;
 }
@@ -617,7 +681,7 @@ static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, Lev
     DevBuf* src = &c->ta;
     DevBuf* dst = &c->tb;
     LevelGeom flat = g;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < m.n_mid; ++i) {
         EpiParams e = epi_linear(ACT_LRELU, dst->p, dst->ld, nullptr, 0, m.mid_valid);
         e.gn_gamma = m.gam[i];
         e.gn_beta = m.bet[i];
@@ -625,7 +689,7 @@ static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, Lev
         CHECK(gemm(c, st, rows, flat, {seg(*src, 0, m.mid_k)}, m.mid[i], 128, EPI_GN, e));
         std::swap(src, dst);
     }
-    // after 3 swaps the result is in `src` == tb
+    // after an odd number of swaps the result is in `src` == tb
     return 0;
 }
 
@@ -650,16 +714,34 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     c->use_ref = cfg->use_ref_kernels != 0;
     c->Bp_max = (cfg->max_candidates + 127) / 128 * 128;
     c->slot_chunk = cfg->decoder_slot_chunk > 0 ? cfg->decoder_slot_chunk : 64;
+    c->model = cfg->model;
+    if (c->model != GCPB200_MODEL_TREE && c->model != GCPB200_MODEL_SEQUENTIAL) {
+        gcp_set_error("gcpb200_create: unknown model kind %d", cfg->model);
+        delete c;
+        return -1;
+    }
+    const bool is_seq = c->model == GCPB200_MODEL_SEQUENTIAL;
+    // latent rows are [slot][candidate]: tree = start, 255 in-order nodes, goal; sequential = frames 0..199, goal
+    c->n_slots = is_seq ? MAX_LEN + 1 : N_SLOTS;
+    c->lstm_hid = is_seq ? 2 * HID : HID;
     if (const char* e = getenv("GCPB200_GEMM_CLUSTER")) c->max_cluster = atoi(e) > 0 ? atoi(e) : 1;
-    const size_t Bp = c->Bp_max, NL = 128 * Bp, NS = (size_t)N_SLOTS * Bp, ND = 256 * Bp;
+    if (const char* e = getenv("GCPB200_SEQ_GRAPH")) c->seq_graph_on = atoi(e) != 0;
+    const size_t Bp = c->Bp_max, NL = is_seq ? Bp : 128 * Bp, NS = (size_t)c->n_slots * Bp, ND = 256 * Bp;
     int rc = 0;
     rc |= dalloc(c, &c->lat_f32, NS * NZ_ENC);
     rc |= make_buf(c, &c->lat, NS, NZ_ENC);
-    rc |= make_buf(c, &c->hid, NS, STATE);
-    rc |= make_buf(c, &c->xa, NL, HID);
-    rc |= make_buf(c, &c->xb, NL, HID);
+    if (is_seq) {
+        rc |= make_buf(c, &c->hs[0], Bp, 3 * c->lstm_hid);
+        rc |= make_buf(c, &c->hs[1], Bp, 3 * c->lstm_hid);
+        rc |= dalloc(c, &c->cs, Bp * 3 * c->lstm_hid);
+        rc |= make_buf(c, &c->xa, NL, c->lstm_hid);
+    } else {
+        rc |= make_buf(c, &c->hid, NS, STATE);
+        rc |= make_buf(c, &c->xa, NL, HID);
+        rc |= make_buf(c, &c->xb, NL, HID);
+        rc |= make_buf(c, &c->sh, NL, 6 * HID);    // projected parent state: [h0 h1 h2 | c0 c1 c2]
+    }
     rc |= make_buf(c, &c->zeta, NL, NZ_VAE);
-    rc |= make_buf(c, &c->sh, NL, 6 * HID);    // projected parent state: [h0 h1 h2 | c0 c1 c2]
     rc |= make_buf(c, &c->ta, ND, 128);
     rc |= make_buf(c, &c->tb, ND, 128);
     rc |= make_buf(c, &c->s2b, Bp, 1024);
@@ -667,7 +749,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= make_buf(c, &c->x2, (size_t)c->slot_chunk * Bp, 2048);
     rc |= make_buf(c, &c->x3, (size_t)c->slot_chunk * Bp, 4096);
     rc |= make_buf(c, &c->pairs, (size_t)MAX_LEN * Bp + 256, 256);
-    rc |= dalloc(c, &c->ctxb, Bp * HID);
+    rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
     rc |= dalloc(c, &c->s2, Bp * 1024);
@@ -681,6 +763,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->goal_tail, 256);
     rc |= dalloc(c, &c->end_ind, Bp);
     rc |= dalloc(c, &c->scratch_ei, 8);
+    rc |= dalloc(c, &c->scratch_given, Bp);
     rc |= dalloc(c, &c->frame_node, Bp * MAX_LEN);
     if (rc) {
         gcpb200_destroy(c);
@@ -690,6 +773,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         cudaError_t ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_copy_start, cudaEventDisableTiming);
         for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->seq_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_fork, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_join, cudaEventDisableTiming);
         if (ce != cudaSuccess) {
             gcp_set_error("copy stream / event creation failed: %s", cudaGetErrorString(ce));
             gcpb200_destroy(c);
@@ -716,7 +802,11 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
 
 extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
     if (!c) return;
+    for (auto& g : c->seq_graphs) cudaGraphExecDestroy(g.exec);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->seq_stream) cudaStreamDestroy(c->seq_stream);
+    if (c->ev_seq_fork) cudaEventDestroy(c->ev_seq_fork);
+    if (c->ev_seq_join) cudaEventDestroy(c->ev_seq_join);
     if (c->ev_copy_start) cudaEventDestroy(c->ev_copy_start);
     for (int i = 0; i < 5; ++i)
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -764,10 +854,14 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
     for (int i = 0; i < n; ++i) ws.m[tensors[i].name] = &tensors[i];
     CHECK(pack_encoder(c, ws));
     CHECK(pack_decoder(c, ws));
-    for (int l = 0; l < DEPTH; ++l) CHECK(pack_level(c, ws, l));
+    if (c->model == GCPB200_MODEL_SEQUENTIAL) {
+        CHECK(pack_sequential(c, ws));
+    } else {
+        for (int l = 0; l < DEPTH; ++l) CHECK(pack_level(c, ws, l));
+        CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128, nullptr,
+                       &c->existence));
+    }
     CHECK(pack_mlp(c, ws, "length_pred.p", true, 2 * NZ_ENC, NZ_MID, MAX_LEN, 256, nullptr, &c->length_pred));
-    CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128, nullptr,
-                   &c->existence));
     CHECK(pack_mlp(c, ws, "inv_mdl.action_pred", false, 2 * NZ_ENC, 128, 2, 128, nullptr, &c->inv_mdl));
     CHECK(pack_mlp(c, ws, "state_regressor", false, NZ_ENC, NZ_MID, 2, 128, nullptr, &c->state_reg));
     c->has_cost = false;
@@ -808,37 +902,23 @@ static int compute_frame_map(gcpb200_ctx* c, const long long* end_ind, int B, cu
     return 0;
 }
 
-extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, void* stream) {
-    if (!io) {
-        gcp_set_error("null io");
-        return -1;
-    }
-    CHECK(check_ready(c, io->B));
-    if (!io->I_0 || !io->I_g || !io->z) {
-        gcp_set_error("gcpb200_rollout: I_0, I_g and z are required");
-        return -1;
-    }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int B = io->B, Bp = (B + 127) / 128 * 128;
-    const LevelGeom flat = {Bp, 0, DEPTH};
-    const int goal_row0 = 256 * Bp;
+struct CommonIO {
+    const float *I_0, *I_g;
+    int images_shared;
+    const int64_t* end_ind;
+    uint64_t seed;
+    int B;
+    float *e_0, *e_g, *seq_len_logits;
+    int64_t* end_ind_out;
+};
 
-    ProfScope total_scope(c, st, 5);
-    if (io->z_host) {
-        // Noise upload, overlapped: the copy stream gathers the rows of levels 0-3, then levels 4, 5, 6, 7 one by one
-        // from pinned host memory; the rollout stream waits for each set just before the level that consumes it.
-        GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy_start, st));       // earlier users of the staging buffer are done
-        GCP_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy_start, 0));
-        const int sets[5][3] = {{16, 15, 15}, {16, 7, 16}, {8, 3, 32}, {4, 1, 64}, {2, 0, 128}};   // node = a*k + b, k < cnt
-        for (int i = 0; i < 5; ++i) {
-            upload_rows_kernel<<<32, 128, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
-                                                                      reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
-                                                                      N_NODES, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
-            LAUNCH_CHECK();
-            GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy[i], c->copy_stream));
-        }
-    }
-    ProfScope* scope = new ProfScope(c, st, 0);
+// Encoder on the start / goal images (latent slots 0 and goal_row0 / Bp, decoder skips of I_0) and the rollout length
+// (LengthPredictorModule + OneHotCategorical sample, or injected): BaseGCPModel.run_encoder + get_end_ind
+// (gcp/prediction/models/base_gcp.py:184-229).  Shared by the tree and the sequential model.
+static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& in, int Bp, int goal_row0) {
+    const CommonIO* io = &in;
+    const int B = in.B;
+    const LevelGeom flat = {Bp, 0, DEPTH};
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
     encoder_kernel<<<dim3(n_img, 2), ENC_THREADS, 0, st>>>(io->I_0, io->I_g, c->enc, c->lat_f32, c->lat.p, 0, goal_row0, c->s0, c->s2,
@@ -872,6 +952,138 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         LAUNCH_CHECK();
     }
     if (io->end_ind_out) GCP_CUDA_CHECK(cudaMemcpyAsync(io->end_ind_out, c->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+
+    return 0;
+}
+
+// Decoder over latent slots 1 .. n_dec (DecoderModule.decode_seq, blox/torch/encoder_decoder.py:358-372): three dense
+// composite layers as GEMMs + the implicit-GEMM tail kernel.  The image of (candidate c, slot s) goes to
+// images[(c * n_layout + s - 1) * 3072].
+static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int n_dec, float* images,
+                       int n_layout) {
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int n_skip = images_shared ? 1 : B;
+    skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
+    LAUNCH_CHECK();
+    if (!c->use_ref) {
+        skip_term3_kernel<<<dim3(8, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
+        LAUNCH_CHECK();
+    }
+    // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
+    CHECK(gemm(c, st, images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 256, EPI_LINEAR,
+               epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
+    for (int s0 = 1; s0 <= n_dec; s0 += c->slot_chunk) {
+        ProfScope* dsc = new ProfScope(c, st, 2);
+        const int ns = (s0 + c->slot_chunk <= n_dec + 1) ? c->slot_chunk : n_dec + 1 - s0;
+        const int rows = ns * Bp;
+        CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 256, EPI_LINEAR,
+                   epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
+        {
+            EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
+            e.rowbias = c->rowbias2;
+            e.rowbias_ld = images_shared ? 0 : 2048;
+            CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 256, EPI_LINEAR, e));
+        }
+        {
+            Seg a3 = seg(c->x2, 0, 1024);      // banded: column group (plane, band) reads its own 4-row K window
+            a3.group_cols = 256;
+            for (int q = 0; q < 16; ++q) a3.group_col[q] = dec3_window_row0(q & 7) * 256;
+            CHECK(gemm(c, st, rows, flat, {a3}, c->dec3, 256, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
+        }
+        delete dsc;
+        ProfScope tsc(c, st, 3);
+        if (c->profile) {
+            c->prof_tail_images += (long long)ns * B;
+            ++c->prof_tail_launches;
+        }
+        if (c->use_ref) {
+            DecTailArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = images_shared ? 0 : 2 * DT_PSTRIDE * 8;
+            a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
+            a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
+            dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
+        } else {
+            DecTail3Args a;
+            memset(&a, 0, sizeof(a));
+            a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = images_shared ? 0 : 256 * 64;
+            a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
+            a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
+            // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
+            const long long n_img = (long long)B * ns;
+            dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+        }
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// Inverse model on consecutive rows of the zero-padded latent sequence seq [B][200][128] and state regressor on every
+// row (InverseModel.full_seq_forward, inverse_mdl.py:110-134; base_gcp.py:252-256).
+static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const float* seq, const long long* end_ind, int B, float* actions,
+                          float* regressed_state) {
+    const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
+    const int rows = (B * MAX_LEN + 127) / 128 * 128;
+    const size_t np = (size_t)rows * 256;
+    make_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(seq, end_ind, nullptr, B, MAX_LEN, rows, c->pairs.p);
+    LAUNCH_CHECK();
+    if (actions) {
+        CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+        CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
+        GCP_CUDA_CHECK(cudaMemcpyAsync(actions, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (regressed_state) {
+        CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->pairs, 0, 128)}));
+        CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->state_reg.mid_k)}, c->state_reg.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
+        GCP_CUDA_CHECK(cudaMemcpyAsync(regressed_state, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, void* stream) {
+    if (!io) {
+        gcp_set_error("null io");
+        return -1;
+    }
+    CHECK(check_ready(c, io->B));
+    if (c->model != GCPB200_MODEL_TREE) {
+        gcp_set_error("gcpb200_rollout needs a context created with model = GCPB200_MODEL_TREE");
+        return -1;
+    }
+    if (!io->I_0 || !io->I_g || !io->z) {
+        gcp_set_error("gcpb200_rollout: I_0, I_g and z are required");
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = io->B, Bp = (B + 127) / 128 * 128;
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int goal_row0 = 256 * Bp;
+
+    ProfScope total_scope(c, st, 5);
+    if (io->z_host) {
+        // Noise upload, overlapped: the copy stream gathers the rows of levels 0-3, then levels 4, 5, 6, 7 one by one
+        // from pinned host memory; the rollout stream waits for each set just before the level that consumes it.
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy_start, st));       // earlier users of the staging buffer are done
+        GCP_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy_start, 0));
+        const int sets[5][3] = {{16, 15, 15}, {16, 7, 16}, {8, 3, 32}, {4, 1, 64}, {2, 0, 128}};   // node = a*k + b, k < cnt
+        for (int i = 0; i < 5; ++i) {
+            upload_rows_kernel<<<32, 128, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
+                                                                      reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
+                                                                      N_NODES, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
+            LAUNCH_CHECK();
+            GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy[i], c->copy_stream));
+        }
+    }
+    ProfScope* scope = new ProfScope(c, st, 0);
+    {
+        CommonIO cio = {io->I_0, io->I_g, io->images_shared, io->end_ind, io->seed, B, io->e_0, io->e_g, io->seq_len_logits,
+                        io->end_ind_out};
+        CHECK(run_encoder_length(c, st, cio, Bp, goal_row0));
+    }
+    const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
 
     delete scope;
     scope = new ProfScope(c, st, 1);
@@ -963,62 +1175,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = nullptr;
     // ---- 5. decoder over all 255 node latents
-    if (io->images_df) {
-        const int n_skip = io->images_shared ? 1 : B;
-        skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
-        LAUNCH_CHECK();
-        if (!c->use_ref) {
-            skip_term3_kernel<<<dim3(8, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
-            LAUNCH_CHECK();
-        }
-        // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
-        CHECK(gemm(c, st, io->images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 256, EPI_LINEAR,
-                   epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
-        for (int s0 = 1; s0 <= N_NODES; s0 += c->slot_chunk) {
-            ProfScope* dsc = new ProfScope(c, st, 2);
-            const int ns = (s0 + c->slot_chunk <= N_NODES + 1) ? c->slot_chunk : N_NODES + 1 - s0;
-            const int rows = ns * Bp;
-            CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 256, EPI_LINEAR,
-                       epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
-            {
-                EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
-                e.rowbias = c->rowbias2;
-                e.rowbias_ld = io->images_shared ? 0 : 2048;
-                CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 256, EPI_LINEAR, e));
-            }
-            {
-                Seg a3 = seg(c->x2, 0, 1024);      // banded: column group (plane, band) reads its own 4-row K window
-                a3.group_cols = 256;
-                for (int q = 0; q < 16; ++q) a3.group_col[q] = dec3_window_row0(q & 7) * 256;
-                CHECK(gemm(c, st, rows, flat, {a3}, c->dec3, 256, EPI_LINEAR,
-                           epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096)));
-            }
-            delete dsc;
-            ProfScope tsc(c, st, 3);
-            if (c->profile) {
-                c->prof_tail_images += (long long)ns * B;
-                ++c->prof_tail_launches;
-            }
-            if (c->use_ref) {
-                DecTailArgs a;
-                memset(&a, 0, sizeof(a));
-                a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = io->images_shared ? 0 : 2 * DT_PSTRIDE * 8;
-                a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
-                a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
-                dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
-            } else {
-                DecTail3Args a;
-                memset(&a, 0, sizeof(a));
-                a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = io->images_shared ? 0 : 256 * 64;
-                a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
-                a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = N_NODES;
-                // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
-                const long long n_img = (long long)B * ns;
-                dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
-            }
-            LAUNCH_CHECK();
-        }
-    }
+    if (io->images_df) CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES));
 
     ProfScope asc(c, st, 4);
     // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
@@ -1029,26 +1186,177 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
                                                                            NZ_ENC / 4, seq);
         LAUNCH_CHECK();
-        if (io->actions || io->regressed_state) {
-            const int rows = (B * MAX_LEN + 127) / 128 * 128;
-            const size_t np = (size_t)rows * 256;
-            make_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(seq, c->end_ind, nullptr, B, MAX_LEN, rows, c->pairs.p);
-            LAUNCH_CHECK();
-            if (io->actions) {
-                CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
-                CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
-                           epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-                GCP_CUDA_CHECK(cudaMemcpyAsync(io->actions, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
-            }
-            if (io->regressed_state) {
-                CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->pairs, 0, 128)}));
-                CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->state_reg.mid_k)}, c->state_reg.head, 128, EPI_LINEAR,
-                           epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-                GCP_CUDA_CHECK(cudaMemcpyAsync(io->regressed_state, c->rowcost, (size_t)B * MAX_LEN * 2 * 4,
-                                               cudaMemcpyDeviceToDevice, st));
-            }
-        }
+        if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, c->end_ind, B, io->actions, io->regressed_state));
     }
+    return 0;
+}
+
+// Sequential GCP rollout (config 3).  Latent rows are time-major: slot t (rows [t*Bp, (t+1)*Bp)) holds x_t, the latent
+// of frame t (x_0 = e_0), slot 200 the goal latent.  Per step t = 0..198, all on rows = Bp:
+//   prior(x_t) -> (mu, log sigma) -> zeta = exp(log sigma) * z_t + mu            (row-MLP GEMMs, EPI_GN / EPI_REPARAM)
+//   embed(cat(x_t, zeta)) + context term                                           (EPI_LINEAR + per-candidate row bias)
+//   3 x LSTMCell(1024): gates GEMM [x | h_prev] (K = 2048, N = 4096) + fused cell update, c kept in fp32 in place,
+//                       h ping-pongs between two bf16 arrays by step parity       (EPI_LSTM)
+//   x_{t+1} = W_o h_2 + b_o -> slot t+1                                             (EPI_LINEAR)
+extern "C" int gcpb200_seq_rollout(gcpb200_ctx* c, const gcpb200_seq_io* io, void* stream) {
+    if (!io) {
+        gcp_set_error("null io");
+        return -1;
+    }
+    CHECK(check_ready(c, io->B));
+    if (c->model != GCPB200_MODEL_SEQUENTIAL) {
+        gcp_set_error("gcpb200_seq_rollout needs a context created with model = GCPB200_MODEL_SEQUENTIAL");
+        return -1;
+    }
+    if (!io->I_0 || !io->I_g || !io->z) {
+        gcp_set_error("gcpb200_seq_rollout: I_0, I_g and z are required");
+        return -1;
+    }
+    if ((io->mu == nullptr) != (io->log_sigma == nullptr)) {
+        gcp_set_error("mu and log_sigma must be given together");
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = io->B, Bp = (B + 127) / 128 * 128, T = GCPB200_SEQ_STEPS, H = c->lstm_hid;
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int goal_row0 = MAX_LEN * Bp;
+    const SeqW& S = c->seqw;
+
+    ProfScope total_scope(c, st, 5);
+    ProfScope* scope = new ProfScope(c, st, 0);
+    {
+        CommonIO cio = {io->I_0, io->I_g, io->images_shared, io->end_ind, io->seed, B, io->e_0, io->e_g, io->seq_len_logits,
+                        io->end_ind_out};
+        CHECK(run_encoder_length(c, st, cio, Bp, goal_row0));
+    }
+    const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
+    delete scope;
+    scope = new ProfScope(c, st, 1);
+    auto recurrence = [&](cudaStream_t st) -> int {
+    // context term of the embed layer (constant over the steps) and the initial LSTM state (InitLSTMCell.init_state)
+    CHECK(gemm(c, st, Bp, flat, ctx_in, S.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, H, H)));
+    CHECK(mlp_body(c, st, S.init, Bp, flat, ctx_in));
+    {
+        EpiParams e = epi_linear(ACT_NONE, c->hs[0].p, 3 * H, c->cs, 3 * H, 6 * H);
+        e.split_col = 3 * H;
+        CHECK(gemm(c, st, Bp, flat, {seg(c->tb, 0, S.init.mid_k)}, S.init.head, 256, EPI_LINEAR, e));
+    }
+    for (int t = 0; t < T; ++t) {
+        const DevBuf& hcur = c->hs[t & 1];
+        const DevBuf& hnxt = c->hs[(t & 1) ^ 1];
+        const Seg x_t = seg(c->lat, 0, NZ_ENC, ROW_LEVEL, t * Bp);
+        CHECK(mlp_body(c, st, S.prior, Bp, flat, {x_t}));
+        {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.z = io->z; e.n_cand = B; e.nz = NZ_VAE; e.z_node = t; e.z_nodes = T;
+            e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
+            e.mu_out = io->mu; e.ls_out = io->log_sigma;
+            CHECK(gemm(c, st, Bp, flat, {seg(c->tb, 0, S.prior.mid_k)}, S.prior.head, 256, EPI_REPARAM, e));
+        }
+        {
+            EpiParams e = epi_linear(ACT_NONE, c->xa.p, H, nullptr, 0, H);
+            e.rowbias = c->ctxb;
+            e.rowbias_ld = H;
+            CHECK(gemm(c, st, Bp, flat, {x_t, seg(c->zeta, 0, NZ_VAE)}, S.embed_main, 256, EPI_LINEAR, e));
+        }
+        for (int i = 0; i < N_LSTM; ++i) {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.c_f32 = c->cs; e.c_f32_ld = 3 * H; e.c_prev_col0 = i * H;
+            e.out_bf16 = hnxt.p + i * H; e.out_bf16_ld = 3 * H;
+            e.hidden = H;
+            const Seg xin = i == 0 ? seg(c->xa, 0, H) : seg(hnxt, (i - 1) * H, H);
+            CHECK(gemm(c, st, Bp, flat, {xin, seg(hcur, i * H, H)}, S.lstm[i], 256, EPI_LSTM, e));
+        }
+        const size_t o = (size_t)(t + 1) * Bp * NZ_ENC;
+        CHECK(gemm(c, st, Bp, flat, {seg(hnxt, 2 * H, H)}, S.out, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, c->lat.p + o, NZ_ENC, c->lat_f32 + o, NZ_ENC, NZ_ENC)));
+    }
+    return 0;
+    };
+    if (c->seq_graph_on && c->seq_warm && !c->use_ref) {
+        gcpb200_ctx::SeqGraph* hit = nullptr;
+        for (auto& g : c->seq_graphs)
+            if (g.z == io->z && g.mu == io->mu && g.ls == io->log_sigma && g.B == B) hit = &g;
+        if (hit == nullptr) {
+            const int64_t l0 = c->launches;
+            GCP_CUDA_CHECK(cudaStreamBeginCapture(c->seq_stream, cudaStreamCaptureModeRelaxed));
+            const int rc = recurrence(c->seq_stream);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(c->seq_stream, &graph);
+            if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+                if (graph) cudaGraphDestroy(graph);
+                if (rc == 0) gcp_set_error("sequential rollout: stream capture failed: %s", cudaGetErrorString(ce));
+                return -1;
+            }
+            gcpb200_ctx::SeqGraph g = {io->z, io->mu, io->log_sigma, B, nullptr, c->launches - l0};
+            c->launches = l0;
+            const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) {
+                gcp_set_error("sequential rollout: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+                return -1;
+            }
+            if (c->seq_graphs.size() >= 8) {
+                cudaGraphExecDestroy(c->seq_graphs.front().exec);
+                c->seq_graphs.erase(c->seq_graphs.begin());
+            }
+            c->seq_graphs.push_back(g);
+            hit = &c->seq_graphs.back();
+        }
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_seq_fork, st));
+        GCP_CUDA_CHECK(cudaStreamWaitEvent(c->seq_stream, c->ev_seq_fork, 0));
+        GCP_CUDA_CHECK(cudaGraphLaunch(hit->exec, c->seq_stream));
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_seq_join, c->seq_stream));
+        GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_seq_join, 0));
+        c->launches += hit->launches;
+    } else {
+        CHECK(recurrence(st));
+        c->seq_warm = true;
+    }
+    delete scope;
+    scope = new ProfScope(c, st, 4);
+    if (io->encodings) {
+        const size_t n = (size_t)B * T * NZ_ENC;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, Bp, B, T, NZ_ENC, NZ_ENC, io->encodings);
+        LAUNCH_CHECK();
+    }
+    delete scope;
+    scope = nullptr;
+    if (io->images) {
+        copy_frame0_kernel<<<(B * 768 + 255) / 256, 256, 0, st>>>(io->I_0, io->images_shared, B, MAX_LEN, io->images);
+        LAUNCH_CHECK();
+        CHECK(run_decoder(c, st, io->images_shared, B, Bp, T, io->images + 3072, MAX_LEN));
+    }
+    ProfScope asc(c, st, 4);
+    if (io->model_enc_seq || io->actions || io->regressed_state) {
+        // inputs.end_ind decides how much of cat(e_0, encodings) is kept (phase = 'train' branch, base_gcp.py:238-239)
+        const long long* given = reinterpret_cast<const long long*>(io->given_end_ind);
+        if (given == nullptr) {
+            fill_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(c->scratch_given, MAX_LEN - 1, B);
+            LAUNCH_CHECK();
+            given = c->scratch_given;
+        }
+        float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
+        const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
+        seq_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, given, Bp, B, MAX_LEN, seq);
+        LAUNCH_CHECK();
+        if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, given, B, io->actions, io->regressed_state));
+    }
+    return 0;
+}
+
+extern "C" int gcpb200_cost_l2_seq(gcpb200_ctx* c, const float* images, int n_frames, const int64_t* end_ind, const float* goal,
+                                   int B, int dense, float final_step_weight, float* cost, void* stream) {
+    CHECK(check_ready(c, B));
+    if (n_frames < 2) {
+        gcp_set_error("gcpb200_cost_l2_seq: n_frames = %d", n_frames);
+        return -1;
+    }
+    cost_l2_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(images, nullptr, reinterpret_cast<const long long*>(end_ind),
+                                                                            goal, n_frames, n_frames, dense, final_step_weight, cost);
+    LAUNCH_CHECK();
     return 0;
 }
 

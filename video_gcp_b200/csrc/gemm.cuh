@@ -66,12 +66,15 @@ struct EpiParams {
     int nz;                 // 256
     float* mu_out;          // optional [B][n_nodes][nz]
     float* ls_out;
+    int z_node, z_nodes;    // z_nodes > 0: every row reads noise row z_node of z_nodes (sequential rollout, step t)
     // EPI_LSTM: torch.nn.LSTMCell update, gate order i,f,g,o
     const bf16* c_prev;     // projected cell state (bf16) [rows][c_prev_ld], column window c_prev_col0
     int c_prev_ld, c_prev_col0;
     bf16* hid;              // slot-major hidden state [slots*Bp][hid_ld]; h at hid_col0+u, c at +H
     int hid_ld, hid_col0, hidden;  // hidden = 512
     int write_hid;
+    float* c_f32;           // non-null: fp32 cell state [rows][c_f32_ld], window c_prev_col0, updated in place
+    int c_f32_ld;           //           (sequential rollout: 199 chained steps keep c in fp32)
 };
 
 struct GemmArgs {
@@ -259,8 +262,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         // packed columns: [mu(16) | log_sigma(16)] for latent dims d0 .. d0+15
         const int d0 = col0 >> 1;
         const int j = row / g.Bp;
-        const int node = slot_of(g, j, ROW_SELF) - 1;  // depth-first node index
-        const int n_nodes = (1 << g.depth) - 1;
+        const int node = p.z_nodes > 0 ? p.z_node : slot_of(g, j, ROW_SELF) - 1;  // depth-first node index / time step
+        const int n_nodes = p.z_nodes > 0 ? p.z_nodes : (1 << g.depth) - 1;
         float zeta[16];
         if (cand < p.n_cand) {
             const size_t zoff = ((size_t)cand * n_nodes + node) * p.nz + d0;
@@ -296,14 +299,22 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
     } else if (EPI == EPI_LSTM) {
         // packed columns: [i(8) | f(8) | g(8) | o(8)] for hidden units u0 .. u0+7
         const int u0 = col0 >> 2;
-        const uint4 cp = __ldg(reinterpret_cast<const uint4*>(p.c_prev + (size_t)row * p.c_prev_ld + p.c_prev_col0 + u0));
-        const __nv_bfloat162* cp2 = reinterpret_cast<const __nv_bfloat162*>(&cp);
         float cprev[8];
+        float4* cf = nullptr;
+        if (p.c_f32 != nullptr) {
+            cf = reinterpret_cast<float4*>(p.c_f32 + (size_t)row * p.c_f32_ld + p.c_prev_col0 + u0);
+            const float4 a = cf[0], b = cf[1];
+            cprev[0] = a.x; cprev[1] = a.y; cprev[2] = a.z; cprev[3] = a.w;
+            cprev[4] = b.x; cprev[5] = b.y; cprev[6] = b.z; cprev[7] = b.w;
+        } else {
+            const uint4 cp = __ldg(reinterpret_cast<const uint4*>(p.c_prev + (size_t)row * p.c_prev_ld + p.c_prev_col0 + u0));
+            const __nv_bfloat162* cp2 = reinterpret_cast<const __nv_bfloat162*>(&cp);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 t = __bfloat1622float2(cp2[i]);
-            cprev[2 * i] = t.x;
-            cprev[2 * i + 1] = t.y;
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(cp2[i]);
+                cprev[2 * i] = t.x;
+                cprev[2 * i + 1] = t.y;
+            }
         }
         float h[8], c[8];
 #pragma unroll
@@ -321,6 +332,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         cv.x = pack_bf16x2(c[0], c[1]); cv.y = pack_bf16x2(c[2], c[3]);
         cv.z = pack_bf16x2(c[4], c[5]); cv.w = pack_bf16x2(c[6], c[7]);
         *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.out_bf16_ld + u0) = hv;
+        if (cf != nullptr) {
+            cf[0] = make_float4(c[0], c[1], c[2], c[3]);
+            cf[1] = make_float4(c[4], c[5], c[6], c[7]);
+        }
         if (p.write_hid) {
             const size_t r = (size_t)map_row(g, ROW_SELF, row);
             bf16* hrow = p.hid + r * p.hid_ld + p.hid_col0 + u0;

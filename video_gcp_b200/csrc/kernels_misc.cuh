@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) cost_l2_kernel(const float* __restrict__ 
     float acc = 0.f;
     for (int t = warp; t <= last; t += 8) {
         if (!dense && t != last) continue;
-        const int node = frame_node[c * lcap + t];
+        const int node = frame_node != nullptr ? frame_node[c * lcap + t] : t;   // null map: frames stored in time order
         const float4* p = reinterpret_cast<const float4*>(images) + ((size_t)c * n_nodes + node) * 768;
         float s = 0.f;
 #pragma unroll 4
@@ -392,6 +392,37 @@ __global__ void slot_to_df_kernel(const float* __restrict__ src, int Bp, int n_c
     const int node = (idx / cols) % n_nodes;
     const int c = idx / ((size_t)cols * n_nodes);
     dst[idx] = src[((size_t)(node + 1) * Bp + c) * src_ld + k];
+}
+
+// Sequential rollout: time-major latent rows [n_frames][Bp][128] (slot t = latent of frame t) -> candidate-major
+// zero-padded sequence dst[c][t][:] = t <= end_ind[c] ? src[t][c][:] : 0  (pad_sequence of cat(e_0, encodings)[:end+1],
+// gcp/prediction/models/sequential.py:78-94, base_gcp.py:242).  Thread per float4.
+__global__ void seq_gather_kernel(const float* __restrict__ src, const long long* __restrict__ end_ind, int Bp, int n_cand,
+                                  int lcap, float* __restrict__ dst) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * lcap * 32) return;
+    const int k = idx & 31;
+    const int t = (idx >> 5) % lcap;
+    const int c = idx / ((size_t)32 * lcap);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t <= (int)end_ind[c]) v = __ldg(reinterpret_cast<const float4*>(src) + ((size_t)t * Bp + c) * 32 + k);
+    reinterpret_cast<float4*>(dst)[idx] = v;
+}
+
+// Sequential rollout: frame 0 of every candidate's image sequence is the start image itself
+// (gcp/prediction/models/sequential.py:57).  images [B][n_frames][3072]; I_0 [B or 1][3072].
+__global__ void copy_frame0_kernel(const float* __restrict__ I_0, int shared, int n_cand, int n_frames,
+                                   float* __restrict__ images) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * 768) return;
+    const int k = idx % 768, c = idx / 768;
+    reinterpret_cast<float4*>(images)[(size_t)c * n_frames * 768 + k] =
+        __ldg(reinterpret_cast<const float4*>(I_0) + (shared ? 0 : (size_t)c * 768) + k);
+}
+
+__global__ void fill_i64_kernel(long long* p, long long v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {

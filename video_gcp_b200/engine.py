@@ -10,6 +10,7 @@ import torch
 from . import _C
 
 N_NODES, NZ_ENC, NZ_VAE, MAX_LEN = 255, 128, 256, 200
+SEQ_STEPS = MAX_LEN - 1
 
 
 def _ptr(t):
@@ -24,7 +25,7 @@ class Engine:
     """One context = one device.  Not thread-safe (same as the reference model object)."""
 
     def __init__(self, device, max_candidates=1024, attach_cost_mdl=False, use_ref_kernels=False,
-                 decoder_slot_chunk=0):
+                 decoder_slot_chunk=0, model="tree"):
         if not torch.cuda.is_available():
             raise _C.GcpB200Error("video_gcp_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = _C.load()
@@ -34,8 +35,10 @@ class Engine:
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.max_candidates = int(max_candidates)
         self.attach_cost_mdl = bool(attach_cost_mdl)
+        self.model = model
+        kind = {"tree": _C.MODEL_TREE, "sequential": _C.MODEL_SEQUENTIAL}[model]
         cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(use_ref_kernels),
-                        int(decoder_slot_chunk))
+                        int(decoder_slot_chunk), kind)
         h = C.c_void_p()
         with torch.cuda.device(self.index):
             _C.check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
@@ -133,6 +136,55 @@ class Engine:
         with torch.cuda.device(self.index):
             _C.check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
         return out
+
+    def seq_rollout(self, I_0, I_g, z, end_ind=None, given_end_ind=None, seed=0, images_shared=False, want_images=True,
+                    want_prior=False, want_aux=True, want_logits=True, fresh=False):
+        """Sequential GCP rollout.  z: [B,199,256] fp32 device tensor.  Returns dict of device tensors (persistent
+        buffers unless fresh=True): e_0, e_g, end_ind, encodings [B,199,128], images [B,200,3,32,32], ..."""
+        dev = self.device
+        B = z.shape[0]
+        f32 = dict(device=dev, dtype=torch.float32)
+        z = z.to(**f32).contiguous()
+        assert tuple(z.shape[1:]) == (SEQ_STEPS, NZ_VAE)
+        I_0 = I_0.to(**f32).contiguous()
+        I_g = I_g.to(**f32).contiguous()
+        if fresh:
+            mk = lambda name, shape, dtype=torch.float32: torch.empty(*shape, device=dev, dtype=dtype)
+        else:
+            mk = self._buf
+        out = dict(z=z, e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
+                   encodings=mk("encodings", (B, SEQ_STEPS, NZ_ENC)))
+        if want_logits:
+            out["seq_len_logits"] = mk("seq_len_logits", (B, MAX_LEN))
+        if want_prior:
+            out["mu"] = mk("seq_mu", (B, SEQ_STEPS, NZ_VAE))
+            out["log_sigma"] = mk("seq_log_sigma", (B, SEQ_STEPS, NZ_VAE))
+        if want_images:
+            out["images"] = mk("seq_images", (B, MAX_LEN, 3, 32, 32))
+        if want_aux:
+            out["model_enc_seq"] = mk("model_enc_seq", (B, MAX_LEN, NZ_ENC))
+            out["actions"] = mk("actions", (B, MAX_LEN, 2))
+            out["regressed_state"] = mk("regressed_state", (B, MAX_LEN, 2))
+        i64 = lambda t: None if t is None else t.to(device=dev, dtype=torch.int64).contiguous()
+        end_ind, given_end_ind = i64(end_ind), i64(given_end_ind)
+        io = _C.SeqIO(
+            _ptr(I_0), _ptr(I_g), int(images_shared), _ptr(z), _ptr(end_ind), _ptr(given_end_ind), int(seed), int(B),
+            _ptr(out["e_0"]), _ptr(out["e_g"]), _ptr(out.get("seq_len_logits")), _ptr(out["end_ind"]),
+            _ptr(out["encodings"]), _ptr(out.get("mu")), _ptr(out.get("log_sigma")), _ptr(out.get("images")),
+            _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")), _ptr(out.get("regressed_state")))
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_seq_rollout(self.h, C.byref(io), _stream()))
+        return out
+
+    def cost_l2_seq(self, images, end_ind, goal, dense=True, final_step_weight=1.0):
+        """L2 image cost over time-ordered image sequences images [B,n_frames,3,32,32] cut at end_ind."""
+        B, n_frames = images.shape[:2]
+        cost = self._buf("cost_l2", (B,))
+        goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cost_l2_seq(self.h, _ptr(images), int(n_frames), _ptr(end_ind.contiguous()), _ptr(goal), B,
+                                                  int(dense), float(final_step_weight), _ptr(cost), _stream()))
+        return cost
 
     def prune_gather(self, src_df, end_ind):
         """src_df [B,255,D...] -> [B,200,D] with frames 0..end_ind in order, zeros after."""

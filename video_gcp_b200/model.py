@@ -133,19 +133,24 @@ class TreeDenseRec(nn.Module):
         return [buf[i, :e + 1].reshape(e + 1, *shape) for i, e in enumerate(ends)], None
 
 
-class TreeModel(nn.Module):
+class _GCPModelBase(nn.Module):
+    """Shared surface of the reference's BaseGCPModel on the planner path (base_gcp.py:29-66,140-161): parameters
+    registered under the reference's state-dict keys, lazy engine + weight packing, `val_mode()`."""
+
+    ENGINE_KIND = "tree"
+
+    def _check_config(self, hp):
+        raise NotImplementedError
+
+    def _make_dense_rec(self):
+        raise NotImplementedError
+
     def __init__(self, params, logger=None, max_candidates=1024, use_ref_kernels=False):
         super().__init__()
         self._logger = logger
         self._hp = build_hparams(params)
         hp = self._hp
-        if not (hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
-                and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
-                and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
-                and hp.lstm_init == "mlp" and hp.matching_type == "balanced" and hp.use_skips
-                and hp.decoder_distribution == "discrete_logistic_mixture" and not hp.add_weighted_pixel_copy):
-            raise NotImplementedError("libgcpb200 is specialised to the 25-room GCP-tree configuration "
-                                      "(experiments/control/25room/gcp_tree/mod_hyper.py)")
+        self._check_config(hp)
         canon = spec.canonical_entries(hp)
         tensors = {}
         for key, (shape, kind) in canon.items():
@@ -169,7 +174,7 @@ class TreeModel(nn.Module):
         self.return_images = True
         self.inject_end_ind = None      # parity harness: replaces the sampled rollout length
         self.seed = 0
-        self.__dict__["dense_rec_impl"] = TreeDenseRec(self)
+        self.__dict__["dense_rec_impl"] = self._make_dense_rec()
 
     # the reference registers `dense_rec` as a module holding the decoder alias; ours only needs methods
     def __getattr__(self, name):
@@ -185,7 +190,7 @@ class TreeModel(nn.Module):
             if dev.type != "cuda":
                 dev = next(self.parameters()).device
             self._engine = Engine(dev, self._max_candidates, attach_cost_mdl=self._hp.attach_cost_mdl,
-                                  use_ref_kernels=self._use_ref_kernels)
+                                  use_ref_kernels=self._use_ref_kernels, model=self.ENGINE_KIND)
             self._dirty = True
         if self._dirty:
             sd = {k: v for k, v in nn.Module.state_dict(self).items() if k in set(self._canonical_keys)}
@@ -211,25 +216,47 @@ class TreeModel(nn.Module):
         finally:
             self._val_mode, self._use_pred_length = False, False
 
-    # ------------------------------------------------------------------------------------------
-    def forward(self, inputs, phase="train"):
+    def _rollout_args(self, inputs, n_rows):
+        """Checks shared by the rollouts: val_mode only, injected noise, which rollout length to use."""
         if not self._val_mode:
             raise NotImplementedError("only the prior rollout (`with model.val_mode():`) is implemented; the "
                                       "training-time inference path is out of scope for libgcpb200")
         if "z" not in inputs:
             raise NotImplementedError("the rollout needs injected noise `inputs.z` (as the CEM simulator provides)")
-        eng = self.engine
-        dev = eng.device
         z = inputs.z
         if z.dim() == 5:
             z = z[..., 0, 0]
+        assert z.shape[1] == n_rows, "z must be [B,%d,256]" % n_rows
+        inject = self.inject_end_ind
+        if not (self._use_pred_length and self._hp.length_pred_weight > 0) and "end_ind" in inputs:
+            inject = inputs.end_ind      # base_gcp.py:222: predicted length only when _use_pred_length
+        return z, inject
+
+
+class TreeModel(_GCPModelBase):
+    ENGINE_KIND = "tree"
+
+    def _check_config(self, hp):
+        if not (hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
+                and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
+                and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
+                and hp.lstm_init == "mlp" and hp.matching_type == "balanced" and hp.use_skips
+                and hp.decoder_distribution == "discrete_logistic_mixture" and not hp.add_weighted_pixel_copy):
+            raise NotImplementedError("libgcpb200 is specialised to the 25-room GCP-tree configuration "
+                                      "(experiments/control/25room/gcp_tree/mod_hyper.py)")
+
+    def _make_dense_rec(self):
+        return TreeDenseRec(self)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, inputs, phase="train"):
+        z, inject = self._rollout_args(inputs, N_NODES)
+        eng = self.engine
+        dev = eng.device
         if z.is_cuda or not (z.dtype == torch.float32 and z.is_pinned()):
             z = z.to(device=dev, dtype=torch.float32)      # pinned fp32 host noise is uploaded by the library itself
         z = z.contiguous()
         B = z.shape[0]
-        inject = self.inject_end_ind
-        if not (self._use_pred_length and self._hp.length_pred_weight > 0) and "end_ind" in inputs:
-            inject = inputs.end_ind      # base_gcp.py:222: predicted length only when _use_pred_length
         shared = bool(inputs.get("images_shared", False))
         outputs = AttrDict()
         inputs.reference_tensor = inputs.I_0
@@ -259,6 +286,84 @@ class TreeModel(nn.Module):
         outputs["_pruned_e_g_prime"] = res["model_enc_seq"]
         if "images_df" in res:
             outputs.pruned_prediction = _LazyPruned(self, outputs)
+        return outputs
+
+
+class SequentialDenseRec(nn.Module):
+    """Sampling API of gcp/prediction/models/sequential.py:78-101 ('basic' scheme): frames are already in time
+    order, frame 0 is the start image and `encodings` gets e_0 prepended."""
+
+    def __init__(self, model):
+        super().__init__()
+        object.__setattr__(self, "_model", model)
+
+    def get_sample_with_len(self, i_ex, length, outputs, inputs, pruning_scheme, name=None):
+        if pruning_scheme != "basic":
+            raise NotImplementedError("only the 'basic' pruning scheme is on the planner path")
+        length = int(length)
+        if name is None:
+            return outputs.dense_rec.images[i_ex, :length], None
+        if name == "encodings":
+            return torch.cat((inputs.e_0[i_ex][None], outputs.dense_rec.encodings[i_ex]), 0)[:length], None
+        return outputs.dense_rec[name][i_ex, :length], None
+
+    def get_all_samples_with_len(self, end_idxs, outputs, inputs, pruning_scheme, name=None):
+        return [self.get_sample_with_len(b, int(end_idxs[b]) + 1, outputs, inputs, pruning_scheme, name=name)[0]
+                for b in range(end_idxs.shape[0])], None
+
+
+class SequentialModel(_GCPModelBase):
+    """Drop-in for the reference's sequential GCP model on the planner path
+    (gcp/prediction/models/sequential.py:104-134; experiments/prediction/25room/gcp_sequential/conf.py)."""
+    ENGINE_KIND = "sequential"
+
+    def _check_config(self, hp):
+        if not (hp.dense_rec_type == "svg" and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
+                and hp.nz_mid_lstm == 1024 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
+                and hp.max_seq_len == 200 and hp.use_skips and hp.context_every_step and hp.prior_type == "learned"
+                and not hp.action_conditioned_pred
+                and hp.decoder_distribution == "discrete_logistic_mixture" and not hp.add_weighted_pixel_copy):
+            raise NotImplementedError("libgcpb200 is specialised to the 25-room sequential GCP configuration "
+                                      "(experiments/prediction/25room/gcp_sequential/conf.py)")
+
+    def _make_dense_rec(self):
+        return SequentialDenseRec(self)
+
+    def forward(self, inputs, phase="train"):
+        z, inject = self._rollout_args(inputs, MAX_LEN - 1)
+        eng = self.engine
+        dev = eng.device
+        z = z.to(device=dev, dtype=torch.float32).contiguous()
+        B = z.shape[0]
+        shared = bool(inputs.get("images_shared", False))
+        outputs = AttrDict()
+        inputs.reference_tensor = inputs.I_0
+        if "start_ind" not in inputs:
+            inputs.start_ind = torch.zeros(B, dtype=torch.long, device=dev)
+        # phase == 'train' (the simulator's default): model_enc_seq is cut at inputs.end_ind, not at the predicted
+        # length (base_gcp.py:238-239 -> get_matched_pruned_seqs); otherwise at outputs.end_ind (sequential.py:133-134)
+        given = inputs.end_ind if (phase == "train" and "end_ind" in inputs) else None
+        res = eng.seq_rollout(inputs.I_0, inputs.I_g, z, end_ind=inject, given_end_ind=given, seed=self.seed,
+                              images_shared=shared, want_images=self.return_images, want_prior=self.return_prior)
+        self.seed += 1
+        inputs.e_0 = res["e_0"][..., None, None]
+        inputs.e_g = res["e_g"][..., None, None]
+        outputs.seq_len_logits = res["seq_len_logits"]
+        outputs.end_ind = res["end_ind"]
+        outputs.z_device = res["z"]
+        dr = AttrDict(encodings=res["encodings"][..., None, None])
+        if "images" in res:
+            dr.images = res["images"]
+        if "mu" in res:
+            dr.p_z_mu = res["mu"][..., None, None]
+            dr.p_z_log_sigma = res["log_sigma"][..., None, None]
+        outputs.dense_rec = dr
+        if phase != "train":
+            raise NotImplementedError("only the simulator's default phase='train' aux path is implemented")
+        lmax = int(given.max()) + 1 if given is not None else MAX_LEN
+        inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
+        outputs.actions = res["actions"][:, :lmax - 1]
+        outputs.regressed_state = res["regressed_state"][:, :lmax]
         return outputs
 
 

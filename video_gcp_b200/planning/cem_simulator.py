@@ -16,9 +16,15 @@ class DeviceRollouts:
     def __init__(self, model, inputs, outputs, goal_chw):
         self.model, self.inputs, self.outputs, self.goal_chw = model, inputs, outputs, goal_chw
         self.end_ind = torch.max(outputs.end_ind, torch.ones_like(outputs.end_ind))   # cem_simulator.py:31
+        self.z = outputs.z_device          # device copy of the noise that was rolled out
+        self.sequential = "tree" not in outputs
+        if self.sequential:
+            # sequential model: frames / latents are stored in time order (frame 0 = start image, latent 0 = e_0)
+            self.images_seq = outputs.dense_rec.get("images")
+            self.enc_seq = outputs.dense_rec.encodings[..., 0, 0]
+            return
         self.images_df = outputs.tree.df.images if "images" in outputs.tree._fields else None
         self.e_df = outputs.tree.df.e_g_prime[..., 0, 0]
-        self.z = outputs.z_device          # device copy of the noise that was rolled out
 
     def __len__(self):
         return int(self.end_ind.shape[0])
@@ -28,10 +34,16 @@ class DeviceRollouts:
         eng = self.model.engine
         ends = self.end_ind.tolist()
         sel = list(range(len(ends))) if idx is None else [int(i) for i in idx]
-        sel_t = torch.as_tensor(sel, device=self.e_df.device)
+        sel_t = torch.as_tensor(sel, device=self.end_ind.device)
         end_sel = self.end_ind[sel_t]
-        img = eng.prune_gather(self.images_df[sel_t], end_sel)
-        lat = eng.prune_gather(self.e_df[sel_t], end_sel)
+        if self.sequential:
+            # cem_simulator.py:45-58 with SequentialRecModule.get_sample_with_len (sequential.py:78-94); `latents`
+            # is inputs.model_enc_seq capped to the predicted length (cem_simulator.py:41)
+            img = self.images_seq[sel_t].reshape(len(sel), self.images_seq.shape[1], -1)
+            lat = torch.cat([self.inputs.e_0[sel_t][:, None, :, 0, 0], self.enc_seq[sel_t]], 1)
+        else:
+            img = eng.prune_gather(self.images_df[sel_t], end_sel)
+            lat = eng.prune_gather(self.e_df[sel_t], end_sel)
         if append_latent:
             img = torch.cat([img, lat], -1)
         img, lat = img.cpu().numpy(), lat.cpu().numpy()
@@ -59,7 +71,8 @@ class GCPSimulator:
         return input_dict
 
     def rollout_device(self, state, goal_state, samples, rollout_len):
-        """samples: numpy [B,255,256] or a CUDA tensor (kept on device).  Returns DeviceRollouts."""
+        """samples: numpy [B,255,256] ([B,199,256] for the sequential model) or a CUDA tensor (kept on device).
+        Returns DeviceRollouts."""
         dev = self._model.engine.device
         B = samples.shape[0]
         if isinstance(samples, torch.Tensor):

@@ -52,6 +52,9 @@ class L2ImageCost(CostFcn, ImageCost):
         self.engine = engine
 
     def device_cost(self, ro):
+        if ro.sequential:
+            return ro.model.engine.cost_l2_seq(ro.images_seq, ro.end_ind, ro.goal_chw, self._dense_cost,
+                                               self._final_step_weight)
         return ro.model.engine.cost_l2(ro.images_df, ro.end_ind, ro.goal_chw, self._dense_cost, self._final_step_weight)
 
     def __call__(self, cem_outputs, goal):
