@@ -381,6 +381,65 @@ def seq_simulator_rollout(sd, state, goal, samples, end_ind, append_latent=True,
 
 
 # --------------------------------------------------------------------------------------------------
+# adaptive-binding GCP-tree (config 4): pixel-copy decoder + distance-predictor pruning
+# --------------------------------------------------------------------------------------------------
+def decoder_pixel_copy(sd, lat, s0, s2, I_0, I_g, return_all=False):
+    """DecoderModule.forward with PixelCopyDecoder and the Gaussian output head (blox/torch/encoder_decoder.py:
+    56-97,235-259,197-203,341-356): same trunk as `decoder`; gen = tanh(conv(pad(feat))), mask =
+    softmax_channel(conv(pad(feat))), image = mask_0 I_0 + mask_1 I_g + mask_2 gen.
+    lat [M,128]; s0, s2, I_0, I_g already replicated per node (decode_seq :358-372)."""
+    p = "decoder.net.net."
+    x = F.conv_transpose2d(lat[:, :, None, None], sd[p + "net.conv.weight"])
+    x = F.relu(_bn(sd, p + "net.norm", x))
+    x = torch.cat([x, s2], 1)
+    x = F.relu(_bn(sd, p + "pyramid-1.norm", _up_pad_conv(x, sd[p + "pyramid-1.conv.weight"], None)))
+    x = F.relu(_bn(sd, p + "pyramid-0.norm", _up_pad_conv(x, sd[p + "pyramid-0.conv.weight"], None)))
+    x = torch.cat([x, s0], 1)
+    feat = torch.tanh(_up_pad_conv(x, sd[p + "additional_conv_layer.conv.weight"],
+                                   sd[p + "additional_conv_layer.conv.bias"]))
+    fp = F.pad(feat, (1, 2, 1, 2))
+    gen = torch.tanh(F.conv2d(fp, sd["decoder.net.gen_head.conv.weight"], sd["decoder.net.gen_head.conv.bias"]))
+    mask = torch.softmax(F.conv2d(fp, sd["decoder.net.mask_head.conv.weight"], sd["decoder.net.mask_head.conv.bias"]), 1)
+    images = (mask.unsqueeze(2) * torch.stack([I_0, I_g, gen], 1)).sum(1)          # mask_and_merge :253-259
+    if return_all:
+        return images, mask, gen
+    return images
+
+
+def adaptive_rollout(sd, I_0, I_g, z, threshold=0.5, decode=True):
+    """Adaptive-binding TreeModel forward in val_mode with injected z (gcp/prediction/models/base_gcp.py:140-161;
+    tree.py:42-67; adaptive_binding/adaptive.py:62-77).  The tree recursion is the GCP-tree's; images come from
+    the pixel-copy decoder; AdaptiveBinding.prune_sequence drops node n > 0 (depth-first order) when
+    sigmoid(distance_predictor(e_{n-1}, e_n)) > learned_pruning_threshold.
+
+    Returns e0, eg, seq_len_logits, tree (df tensors), images_df [B,255,3,32,32], distances [B,254],
+    keep [B,255] bool, pruned_images / pruned_latents (lists)."""
+    out = {}
+    e0, (s0, s2) = encoder(sd, I_0)
+    eg, _ = encoder(sd, I_g)
+    out["e0"], out["eg"] = e0, eg
+    out["seq_len_logits"] = length_logits(sd, e0, eg)
+    tree = tree_rollout(sd, e0, eg, z)
+    out["tree"] = tree
+    B = e0.shape[0]
+    rep = lambda t: t.repeat_interleave(N_NODES, 0)
+    if decode:
+        imgs = decoder_pixel_copy(sd, tree["e"].reshape(B * N_NODES, 128), rep(s0), rep(s2), rep(I_0), rep(I_g))
+        out["images_df"] = imgs.reshape(B, N_NODES, 3, 32, 32)
+    lat = tree["e"]
+    pairs = torch.cat([lat[:, :-1], lat[:, 1:]], 2).reshape(-1, 256)
+    dist = mlp(sd, "tree_module.tree_modules.0.binding.distance_predictor", pairs).reshape(B, N_NODES - 1)
+    out["distances"] = dist
+    close = torch.sigmoid(dist) > threshold
+    keep = ~torch.cat([torch.zeros_like(close[:, :1]), close], 1)
+    out["keep"] = keep
+    if decode:
+        out["pruned_images"] = [out["images_df"][b][keep[b]] for b in range(B)]
+    out["pruned_latents"] = [lat[b][keep[b]] for b in range(B)]
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # costs, elites, refit
 # --------------------------------------------------------------------------------------------------
 def l2_image_cost(image_seqs, goal_raw, dense_cost=True, final_step_weight=1.0):

@@ -28,7 +28,7 @@ _DEFAULTS = dict(
     regress_index=False, regress_length=False, inv_mdl_params={}, train_inv_mdl_full_seq=False,
     cost_mdl_params={}, learned_pruning_threshold=0.5, untied_layers=False, supervised_decoder=False,
     states_inference=False, dense_rec_type='none', one_step_planner='discrete', binding='frames',
-    randomize_length=False, randomize_start=False,
+    randomize_length=False, randomize_start=False, learn_matching_temp=True, matching_temp=1.0,
 )
 
 
@@ -62,6 +62,21 @@ def gcp_tree_25room_config(**extra):
         attach_inv_mdl=True,
         inv_mdl_params=AttrDict(n_actions=2, use_convs=False, build_encoder=False),
         untied_layers=True, decoder_distribution='discrete_logistic_mixture',
+    )
+    cfg.update(extra)
+    return cfg
+
+
+def gcp_adaptive_25room_config(**extra):
+    """The adaptive-binding GCP-tree model with the 25-room network sizes (config 4): experiments/prediction/
+    base_configs/gcp_adaptive.py:6-11 over base_tree.py:11-20, sizes of experiments/prediction/25room/gcp_tree/conf.py.
+    Pixel-copy decoder with a Gaussian output distribution, distance-predictor pruning, no auxiliary heads."""
+    cfg = AttrDict(
+        one_step_planner='sh_pred', binding='loss', seq_enc='conv', tree_lstm='split_linear',
+        lstm_init='mlp', dense_rec_type='node_prob', add_weighted_pixel_copy=True,
+        matching_type='dtw_image', learn_matching_temp=False, attentive_inference=True,
+        ngf=16, max_seq_len=200, hierarchy_levels=8, nz_mid_lstm=512, n_lstm_layers=3,
+        nz_mid=128, nz_enc=128, nz_vae=256, regress_length=True, untied_layers=True,
     )
     cfg.update(extra)
     return cfg

@@ -53,7 +53,7 @@ def _init_tensor(shape, kind):
         n = shape[0]
         b[n // 4:n // 2] = 1.0
         return b
-    if kind in (spec.BN_W, spec.GN_W, spec.BN_RV):
+    if kind in (spec.BN_W, spec.GN_W, spec.BN_RV, spec.ONES):
         return torch.ones(shape)
     if kind == spec.BN_NBT:
         return torch.zeros(shape, dtype=torch.long)

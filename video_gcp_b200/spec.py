@@ -15,6 +15,7 @@ from collections import OrderedDict
 # kinds drive initialisation (model.py) and synthetic weights (synthetic.py)
 W, B_, BN_W, BN_B, BN_RM, BN_RV, BN_NBT, GN_W, GN_B, LSTM_W, LSTM_B, ZEROS = (
     "w", "b", "bn_w", "bn_b", "bn_rm", "bn_rv", "bn_nbt", "gn_w", "gn_b", "lstm_w", "lstm_b", "zeros")
+ONES = "ones"
 
 
 def _bn(out, prefix, c):
@@ -80,6 +81,14 @@ def decoder_entries(hp, prefix="decoder"):
     n_out = 10 * hp.input_nc if hp.decoder_distribution == "discrete_logistic_mixture" else hp.input_nc
     out[prefix + ".net.gen_head.conv.weight"] = ((n_out, hp.ngf, 4, 4), W)
     out[prefix + ".net.gen_head.conv.bias"] = ((n_out,), B_)
+    if hp.add_weighted_pixel_copy:
+        # PixelCopyDecoder (blox/torch/encoder_decoder.py:235-259): mask over [I_0, I_g, generated]
+        out[prefix + ".net.mask_head.conv.weight"] = ((3, hp.ngf, 4, 4), W)
+        out[prefix + ".net.mask_head.conv.bias"] = ((3,), B_)
+    if hp.decoder_distribution == "gaussian":
+        # ProbabilisticConvDecoder (encoder_decoder.py:171-173): constant output log-sigma + its updater handle
+        out[prefix + ".log_sigma"] = ((), ZEROS)
+        out[prefix + ".sigma_updater.parameter"] = ((), ZEROS)
     return out
 
 
@@ -135,6 +144,20 @@ def canonical_entries(hp):
         tm = "tree_module.tree_modules.%d." % k if hp.untied_layers else "tree_module."
         _predictor(out, tm + "prior", 2 * hp.nz_enc, hp.nz_mid, 2 * hp.nz_vae, hp.n_processing_layers, True)
         _predictor(out, tm + "inference.q", 3 * hp.nz_enc, hp.nz_mid, 2 * hp.nz_vae, hp.n_processing_layers, True)
+        if hp.attentive_inference:
+            # AttentiveInference (gcp/prediction/models/adaptive_binding/attentive_inference.py); training only
+            at = tm + "inference.attention."
+            _predictor(out, at + "query_net", 2 * hp.nz_enc, hp.nz_mid, hp.nz_attn_key, hp.n_processing_layers, True)
+            for i in range(hp.n_attention_layers):
+                al = at + "attention_layers.%d." % i
+                out[al + "temperature"] = ((1,), ONES)
+                for nm, d in (("q_linear", hp.nz_attn_key), ("k_linear", hp.nz_attn_key), ("v_linear", hp.nz_enc),
+                              ("out", hp.nz_enc)):
+                    out[al + nm + ".weight"] = ((d, d), W)
+                    out[al + nm + ".bias"] = ((d,), B_)
+                _predictor(out, at + "predictor_layers.%d" % i, hp.nz_enc, hp.nz_mid, hp.nz_attn_key, 2, True)
+            out[at + "out.weight"] = ((hp.nz_enc, hp.nz_enc), W)
+            out[at + "out.bias"] = ((hp.nz_enc,), B_)
         sp = tm + "subgoal_pred."
         out[sp + "initial_hidden"] = ((1, state_dim), ZEROS)
         out[sp + "embed.weight"] = ((H, pred_in), W)
@@ -151,7 +174,12 @@ def canonical_entries(hp):
             out[sp + "projections.%d.bias" % i] = ((H,), B_)
         _predictor(out, tm + "lstm_initializer.net", 2 * hp.nz_enc + hp.nz_vae, hp.init_mlp_mid_sz,
                    2 * state_dim, hp.init_mlp_layers, True)
-        _predictor(out, tm + "binding.existence_predictor", hp.nz_enc, hp.nz_mid, 1, hp.n_processing_layers, True)
+        if "dtw" in hp.matching_type:
+            # AdaptiveBinding (gcp/prediction/models/adaptive_binding/adaptive.py:18-31)
+            out[tm + "binding.temp"] = ((1,), ONES)
+            _predictor(out, tm + "binding.distance_predictor", 2 * hp.nz_enc, hp.nz_mid, 1, hp.n_processing_layers, True)
+        else:
+            _predictor(out, tm + "binding.existence_predictor", hp.nz_enc, hp.nz_mid, 1, hp.n_processing_layers, True)
     return out
 
 

@@ -54,6 +54,8 @@ def _make(key, shape, kind, seed):
         return b
     if kind == spec.ZEROS:
         return np.zeros(shape, dtype=np.float32)
+    if kind == spec.ONES:
+        return np.ones(shape, dtype=np.float32)
     raise ValueError(kind)
 
 
