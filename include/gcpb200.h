@@ -43,13 +43,16 @@ typedef struct {
     int attach_cost_mdl; /* 1: expect cost_mdl.cost_pred.* weights (learned cost available) */
     int use_ref_kernels; /* 1: verification mode, SIMT kernels instead of tcgen05 (tests only) */
     int decoder_slot_chunk; /* decoder processes this many tree slots per pass (0 = default 64) */
-    int model;           /* GCPB200_MODEL_TREE (0) or GCPB200_MODEL_SEQUENTIAL (1): which reference model the context
+    int model;           /* GCPB200_MODEL_TREE (0), _SEQUENTIAL (1) or _TREE_ADAPTIVE (2): which reference model the context
                             holds (TreeModel, gcp/prediction/models/tree/tree.py:14; SequentialModel,
                             gcp/prediction/models/sequential.py:104) */
 } gcpb200_config;
 
 #define GCPB200_MODEL_TREE 0
 #define GCPB200_MODEL_SEQUENTIAL 1
+#define GCPB200_MODEL_TREE_ADAPTIVE 2   /* TreeModel with base_configs/gcp_adaptive.py: pixel-copy decoder
+                                           (blox/torch/encoder_decoder.py:235-259) and AdaptiveBinding pruning
+                                           (gcp/prediction/models/adaptive_binding/adaptive.py:62-77) */
 #define GCPB200_SEQ_STEPS 199   /* max_seq_len - 1 predicted frames (sequential.py:50) */
 
 /* one fp32 host tensor of the reference state dict */
@@ -86,6 +89,11 @@ typedef struct {
     float* model_enc_seq;    /* [B,200,128] pruned latents, zero padded */
     float* actions;          /* [B,200,2] inverse model on consecutive pruned latents (use [:, :Lmax-1]) */
     float* regressed_state;  /* [B,200,2] state regressor (use [:, :Lmax]) */
+    /* ---- GCPB200_MODEL_TREE_ADAPTIVE only (existence / model_enc_seq / actions / regressed_state must be NULL) ---- */
+    float* distances;        /* [B,254] distance-predictor logits of consecutive depth-first nodes */
+    int32_t* pruned_nodes;   /* [B,255] depth-first indices of the kept nodes, in order (first pruned_len[c] valid) */
+    int32_t* pruned_len;     /* [B] number of kept nodes: node 0 and every node n with sigmoid(distance[n-1]) <= threshold */
+    float prune_threshold;   /* learned_pruning_threshold (0 -> the reference default 0.5) */
 } gcpb200_rollout_io;
 
 /* I/O of the sequential GCP rollout (SequentialModel forward in val_mode with injected z, default phase as the
@@ -140,6 +148,16 @@ int gcpb200_cost_l2_seq(gcpb200_ctx* ctx, const float* images, int n_frames, con
 /* dst[c,t,:] = src[c, node_of_frame(c,t), :] for t <= end_ind[c], zeros after.  row_len % 4 == 0. */
 int gcpb200_prune_gather(gcpb200_ctx* ctx, const float* src_df, const int64_t* end_ind, int B, int row_len,
                          float* dst /* [B,200,row_len] */, void* stream);
+
+/* dst[c,t,:] = src_df[c, nodes[c,t], :] for t < len[c], zeros after: materialises outputs.pruned_prediction of the
+ * adaptive model (adaptive.py:75) from the node lists gcpb200_rollout returned.  row_len % 4 == 0. */
+int gcpb200_gather_nodes(gcpb200_ctx* ctx, const float* src_df, const int32_t* nodes /* [B,255] */,
+                         const int32_t* len /* [B] */, int B, int row_len, float* dst /* [B,255,row_len] */, void* stream);
+
+/* L2 image cost over the frames listed in nodes[c,:len[c]] (CostFcn.__call__ on pruned predictions). */
+int gcpb200_cost_l2_nodes(gcpb200_ctx* ctx, const float* images_df, const int32_t* nodes, const int32_t* len,
+                          const float* goal, int B, int dense, float final_step_weight, float* cost /* [B] */,
+                          void* stream);
 
 /* goal: [3,32,32] in [-1,1].  dense != 0: sum over frames, else last frame only. */
 int gcpb200_cost_l2(gcpb200_ctx* ctx, const float* images_df, const int64_t* end_ind, const float* goal, int B,

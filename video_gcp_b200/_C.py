@@ -15,7 +15,7 @@ class Config(C.Structure):
                 ("use_ref_kernels", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int)]
 
 
-MODEL_TREE, MODEL_SEQUENTIAL = 0, 1
+MODEL_TREE, MODEL_SEQUENTIAL, MODEL_TREE_ADAPTIVE = 0, 1, 2
 
 
 class Tensor(C.Structure):
@@ -28,7 +28,9 @@ class RolloutIO(C.Structure):
                 ("e_0", C.c_void_p), ("e_g", C.c_void_p), ("seq_len_logits", C.c_void_p),
                 ("end_ind_out", C.c_void_p), ("e_df", C.c_void_p), ("mu_df", C.c_void_p),
                 ("log_sigma_df", C.c_void_p), ("images_df", C.c_void_p), ("existence", C.c_void_p),
-                ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p)]
+                ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p),
+                ("distances", C.c_void_p), ("pruned_nodes", C.c_void_p), ("pruned_len", C.c_void_p),
+                ("prune_threshold", C.c_float)]
 
 
 class SeqIO(C.Structure):
@@ -50,6 +52,10 @@ EXPORTS = {
     "gcpb200_seq_rollout": (C.c_int, [C.c_void_p, C.POINTER(SeqIO), C.c_void_p]),
     "gcpb200_cost_l2_seq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                       C.c_void_p, C.c_void_p]),
+    "gcpb200_gather_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "gcpb200_cost_l2_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_float, C.c_void_p, C.c_void_p]),
     "gcpb200_prune_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gcpb200_cost_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                   C.c_void_p, C.c_void_p]),

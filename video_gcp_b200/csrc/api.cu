@@ -95,8 +95,9 @@ struct gcpb200_ctx {
     bool seq_graph_on = true, seq_warm = false;
     cudaStream_t seq_stream = nullptr;   // capture / replay stream (the caller's stream may be the legacy default stream,
     cudaEvent_t ev_seq_fork = nullptr, ev_seq_join = nullptr;   // which cannot be captured); fork/join by events
-    Mlp length_pred, existence, inv_mdl, state_reg, cost_mdl;
-    bool has_cost = false;
+    Mlp length_pred, existence, inv_mdl, state_reg, cost_mdl, distance_pred;
+    bool has_cost = false, has_inv = false, has_state = false;
+    int pair_rows = 0;       // rows of the `pairs` / `rowcost` scratch arrays
     EncoderWeights enc;
     DevMat dec1, dec2x, dec2s, dec3;
     bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *z4 = nullptr, *z5 = nullptr, *s4 = nullptr;
@@ -424,6 +425,30 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
     const gcpb200_tensor* w5 = ws.get("decoder.net.gen_head.conv.weight", 4);
     const gcpb200_tensor* b5 = ws.get("decoder.net.gen_head.conv.bias", 1);
     if (!w4 || !b4 || !w5 || !b5) return -1;
+    // Head channel c of the final convolution: DLM head = the 30 gen_head rows (15 mixture means + 15 scales); pixel-copy
+    // head (adaptive model) = 3 gen_head rows followed by the 3 mask_head rows.
+    const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;
+    const gcpb200_tensor *wm = nullptr, *bm = nullptr;
+    if (pc) {
+        wm = ws.get("decoder.net.mask_head.conv.weight", 4);
+        bm = ws.get("decoder.net.mask_head.conv.bias", 1);
+        if (!wm || !bm) return -1;
+    }
+    if (w5->shape[0] != (pc ? 3 : 30)) {
+        gcp_set_error("decoder.net.gen_head.conv.weight has %d output channels, expected %d", (int)w5->shape[0], pc ? 3 : 30);
+        return -1;
+    }
+    const int n_head = pc ? 6 : 30;
+    auto head_w = [&](int co, int ci, int tap) -> float {
+        if (co >= n_head) return 0.f;
+        if (pc && co >= 3) return wm->data[((size_t)(co - 3) * 16 + ci) * 16 + tap];
+        return w5->data[((size_t)co * 16 + ci) * 16 + tap];
+    };
+    auto head_b = [&](int co) -> float {
+        if (co >= n_head) return 0.f;
+        if (pc && co >= 3) return bm->data[co - 3];
+        return b5->data[co];
+    };
     {
         std::vector<bf16> h4(DT_W4_BYTES / 2), h5(DT_W5_BYTES / 2), p4(16 * 32 * 16), p5(32 * 16 * 16);
         for (int tap = 0; tap < 16; ++tap)
@@ -437,7 +462,7 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
         for (int tap = 0; tap < 16; ++tap)
             for (int ci = 0; ci < 16; ++ci)
                 for (int co = 0; co < 32; ++co) {
-                    const float v = co < 30 ? w5->data[((size_t)co * 16 + ci) * 16 + tap] : 0.f;
+                    const float v = head_w(co, ci, tap);
                     h5[(size_t)tap * 512 + (ci >> 3) * 256 + co * 8 + (ci & 7)] = __float2bfloat16(v);
                     p5[((size_t)co * 16 + ci) * 16 + tap] = __float2bfloat16(v);
                 }
@@ -453,14 +478,15 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
                             const size_t o = (size_t)ky * (D3_Z_KY / 2) + h * (D3_Z_CHUNK / 2) + (16 * b + co) * 8 + e;
                             const int ci = 8 * h + e, tap = ky * 4 + (b - 3);
                             z4[o] = __float2bfloat16(w4->data[((size_t)co * 32 + ci) * 16 + tap]);
-                            if (co < 15) z5[o] = __float2bfloat16(0.5f * w5->data[((size_t)co * 16 + ci) * 16 + tap]);
+                            if (pc) { if (co < 6) z5[o] = __float2bfloat16(head_w(co, ci, tap)); }
+                            else if (co < 15) z5[o] = __float2bfloat16(0.5f * head_w(co, ci, tap));
                         }
         CHECK(dalloc(c, &c->z4, z4.size(), false));
         CHECK(dalloc(c, &c->z5, z5.size(), false));
         GCP_CUDA_CHECK(cudaMemcpy(c->z4, z4.data(), z4.size() * 2, cudaMemcpyHostToDevice));
         GCP_CUDA_CHECK(cudaMemcpy(c->z5, z5.data(), z5.size() * 2, cudaMemcpyHostToDevice));
         std::vector<float> hb5h(16, 0.f);
-        for (int i = 0; i < 15; ++i) hb5h[i] = 0.5f * b5->data[i];
+        for (int i = 0; i < (pc ? 6 : 15); ++i) hb5h[i] = (pc ? 1.0f : 0.5f) * head_b(i);
         CHECK(upload_f32(c, &c->b5h, hb5h));
         CHECK(dalloc(c, &c->w4, h4.size(), false));
         CHECK(dalloc(c, &c->w5, h5.size(), false));
@@ -471,7 +497,7 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
         GCP_CUDA_CHECK(cudaMemcpy(c->w4p, p4.data(), p4.size() * 2, cudaMemcpyHostToDevice));
         GCP_CUDA_CHECK(cudaMemcpy(c->w5p, p5.data(), p5.size() * 2, cudaMemcpyHostToDevice));
         std::vector<float> hb4(b4->data, b4->data + 16), hb5(32, 0.f);
-        for (int i = 0; i < 30; ++i) hb5[i] = b5->data[i];
+        for (int i = 0; i < n_head; ++i) hb5[i] = head_b(i);
         CHECK(upload_f32(c, &c->b4, hb4));
         CHECK(upload_f32(c, &c->b5, hb5));
     }
@@ -715,7 +741,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     c->Bp_max = (cfg->max_candidates + 127) / 128 * 128;
     c->slot_chunk = cfg->decoder_slot_chunk > 0 ? cfg->decoder_slot_chunk : 64;
     c->model = cfg->model;
-    if (c->model != GCPB200_MODEL_TREE && c->model != GCPB200_MODEL_SEQUENTIAL) {
+    if (c->model != GCPB200_MODEL_TREE && c->model != GCPB200_MODEL_SEQUENTIAL && c->model != GCPB200_MODEL_TREE_ADAPTIVE) {
         gcp_set_error("gcpb200_create: unknown model kind %d", cfg->model);
         delete c;
         return -1;
@@ -748,7 +774,8 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= make_buf(c, &c->x1, (size_t)c->slot_chunk * Bp, 1024);
     rc |= make_buf(c, &c->x2, (size_t)c->slot_chunk * Bp, 2048);
     rc |= make_buf(c, &c->x3, (size_t)c->slot_chunk * Bp, 4096);
-    rc |= make_buf(c, &c->pairs, (size_t)MAX_LEN * Bp + 256, 256);
+    c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? N_NODES : MAX_LEN) * Bp + 256);
+    rc |= make_buf(c, &c->pairs, (size_t)c->pair_rows, 256);
     rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
@@ -759,12 +786,12 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->exist_slot, ND);
     rc |= dalloc(c, &c->e_df, Bp * N_NODES * NZ_ENC);
     rc |= dalloc(c, &c->seq, Bp * MAX_LEN * NZ_ENC);
-    rc |= dalloc(c, &c->rowcost, ((size_t)MAX_LEN * Bp + 256) * 2);
+    rc |= dalloc(c, &c->rowcost, (size_t)c->pair_rows * 2);
     rc |= dalloc(c, &c->goal_tail, 256);
     rc |= dalloc(c, &c->end_ind, Bp);
     rc |= dalloc(c, &c->scratch_ei, 8);
     rc |= dalloc(c, &c->scratch_given, Bp);
-    rc |= dalloc(c, &c->frame_node, Bp * MAX_LEN);
+    rc |= dalloc(c, &c->frame_node, Bp * 256);
     if (rc) {
         gcpb200_destroy(c);
         return -1;
@@ -789,6 +816,8 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     // small kernels of the rollout that run with the default carve-out still find SMs they can be scheduled on.
     cudaFuncSetAttribute(upload_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaFuncSetAttribute(dec_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dec_tail3_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
     if (e != cudaSuccess) {
@@ -858,12 +887,19 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
         CHECK(pack_sequential(c, ws));
     } else {
         for (int l = 0; l < DEPTH; ++l) CHECK(pack_level(c, ws, l));
-        CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128, nullptr,
-                       &c->existence));
+        if (c->model == GCPB200_MODEL_TREE_ADAPTIVE)
+            CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.distance_predictor", true, 2 * NZ_ENC, NZ_MID, 1, 128,
+                           nullptr, &c->distance_pred));
+        else
+            CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128,
+                           nullptr, &c->existence));
     }
     CHECK(pack_mlp(c, ws, "length_pred.p", true, 2 * NZ_ENC, NZ_MID, MAX_LEN, 256, nullptr, &c->length_pred));
-    CHECK(pack_mlp(c, ws, "inv_mdl.action_pred", false, 2 * NZ_ENC, 128, 2, 128, nullptr, &c->inv_mdl));
-    CHECK(pack_mlp(c, ws, "state_regressor", false, NZ_ENC, NZ_MID, 2, 128, nullptr, &c->state_reg));
+    // auxiliary heads exist only when the model config attaches them (attach_inv_mdl / attach_state_regressor)
+    c->has_inv = ws.m.count("inv_mdl.action_pred.input.linear.weight") != 0;
+    c->has_state = ws.m.count("state_regressor.input.linear.weight") != 0;
+    if (c->has_inv) CHECK(pack_mlp(c, ws, "inv_mdl.action_pred", false, 2 * NZ_ENC, 128, 2, 128, nullptr, &c->inv_mdl));
+    if (c->has_state) CHECK(pack_mlp(c, ws, "state_regressor", false, NZ_ENC, NZ_MID, 2, 128, nullptr, &c->state_reg));
     c->has_cost = false;
     if (c->cfg.attach_cost_mdl) {
         CHECK(pack_mlp(c, ws, "cost_mdl.cost_pred", false, 2 * NZ_ENC, 128, 1, 128, nullptr, &c->cost_mdl));
@@ -960,7 +996,8 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
 // composite layers as GEMMs + the implicit-GEMM tail kernel.  The image of (candidate c, slot s) goes to
 // images[(c * n_layout + s - 1) * 3072].
 static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int n_dec, float* images,
-                       int n_layout) {
+                       int n_layout, const float* I_0 = nullptr, const float* I_g = nullptr) {
+    const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;   // pixel-copy head: needs the start / goal images
     const LevelGeom flat = {Bp, 0, DEPTH};
     const int n_skip = images_shared ? 1 : B;
     skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
@@ -1003,6 +1040,7 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
             a.x3 = c->x3.p; a.skip_up = c->skip_up; a.skip_stride = images_shared ? 0 : 2 * DT_PSTRIDE * 8;
             a.w4 = c->w4; a.w5 = c->w5; a.b4 = c->b4; a.b5 = c->b5;
             a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
+            a.head = pc; a.src0 = I_0; a.srcg = I_g; a.src_stride = images_shared ? 0 : 3072;
             dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
         } else {
             DecTail3Args a;
@@ -1012,7 +1050,9 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
             a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
             // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
             const long long n_img = (long long)B * ns;
-            dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+            a.src0 = I_0; a.srcg = I_g; a.src_stride = images_shared ? 0 : 3072;
+            if (pc) dec_tail3_pc_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+            else dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
         }
         LAUNCH_CHECK();
     }
@@ -1026,6 +1066,10 @@ static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const float* seq, con
     const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
     const int rows = (B * MAX_LEN + 127) / 128 * 128;
     const size_t np = (size_t)rows * 256;
+    if ((actions && !c->has_inv) || (regressed_state && !c->has_state)) {
+        gcp_set_error("actions / regressed_state requested but the loaded state dict has no inv_mdl / state_regressor weights");
+        return -1;
+    }
     make_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(seq, end_ind, nullptr, B, MAX_LEN, rows, c->pairs.p);
     LAUNCH_CHECK();
     if (actions) {
@@ -1049,8 +1093,17 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         return -1;
     }
     CHECK(check_ready(c, io->B));
-    if (c->model != GCPB200_MODEL_TREE) {
-        gcp_set_error("gcpb200_rollout needs a context created with model = GCPB200_MODEL_TREE");
+    if (c->model != GCPB200_MODEL_TREE && c->model != GCPB200_MODEL_TREE_ADAPTIVE) {
+        gcp_set_error("gcpb200_rollout needs a context created with model = GCPB200_MODEL_TREE or _TREE_ADAPTIVE");
+        return -1;
+    }
+    const bool adaptive = c->model == GCPB200_MODEL_TREE_ADAPTIVE;
+    if (adaptive && (io->existence || io->model_enc_seq || io->actions || io->regressed_state)) {
+        gcp_set_error("the adaptive model has no existence predictor / balanced pruning heads (use distances, pruned_nodes)");
+        return -1;
+    }
+    if (!adaptive && (io->distances || io->pruned_nodes || io->pruned_len)) {
+        gcp_set_error("distances / pruned_nodes need a context created with model = GCPB200_MODEL_TREE_ADAPTIVE");
         return -1;
     }
     if (!io->I_0 || !io->I_g || !io->z) {
@@ -1175,7 +1228,29 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = nullptr;
     // ---- 5. decoder over all 255 node latents
-    if (io->images_df) CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES));
+    if (io->images_df) CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES, io->I_0, io->I_g));
+    if (adaptive && (io->distances || io->pruned_nodes || io->pruned_len)) {
+        // AdaptiveBinding.prune_sequence: distance predictor on consecutive depth-first latents, then compaction
+        ProfScope dsc(c, st, 4);
+        if (!io->pruned_nodes || !io->pruned_len) {
+            gcp_set_error("pruned_nodes and pruned_len must be given together");
+            return -1;
+        }
+        const int rows = (B * N_NODES + 127) / 128 * 128;
+        make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(e_df, c->end_ind, nullptr, B, N_NODES, rows,
+                                                                                       c->pairs.p);
+        LAUNCH_CHECK();
+        CHECK(mlp_body(c, st, c->distance_pred, rows, flat, {seg(c->pairs, 0, 256)}));
+        CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->distance_pred.mid_k)}, c->distance_pred.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 1, 1)));
+        if (io->distances)
+            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->distances, (N_NODES - 1) * 4, c->rowcost, N_NODES * 4, (N_NODES - 1) * 4, B,
+                                             cudaMemcpyDeviceToDevice, st));
+        const float thr = io->prune_threshold > 0.f ? io->prune_threshold : 0.5f;
+        adaptive_prune_kernel<<<B, 256, 0, st>>>(c->rowcost, N_NODES, N_NODES, logf(thr / (1.0f - thr)), io->pruned_nodes,
+                                                 io->pruned_len, nullptr);
+        LAUNCH_CHECK();
+    }
 
     ProfScope asc(c, st, 4);
     // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
@@ -1356,6 +1431,31 @@ extern "C" int gcpb200_cost_l2_seq(gcpb200_ctx* c, const float* images, int n_fr
     }
     cost_l2_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(images, nullptr, reinterpret_cast<const long long*>(end_ind),
                                                                             goal, n_frames, n_frames, dense, final_step_weight, cost);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_gather_nodes(gcpb200_ctx* c, const float* src_df, const int32_t* nodes, const int32_t* len, int B,
+                                    int row_len, float* dst, void* stream) {
+    CHECK(check_ready(c, B));
+    if (row_len % 4 || !src_df || !nodes || !len || !dst) {
+        gcp_set_error("gcpb200_gather_nodes: bad arguments (row_len must be a multiple of 4)");
+        return -1;
+    }
+    const size_t n = (size_t)B * N_NODES * (row_len / 4);
+    gather_nodes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_df, nodes, len, B, N_NODES,
+                                                                                                      row_len / 4, dst);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_cost_l2_nodes(gcpb200_ctx* c, const float* images_df, const int32_t* nodes, const int32_t* len,
+                                     const float* goal, int B, int dense, float final_step_weight, float* cost, void* stream) {
+    CHECK(check_ready(c, B));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    len_to_end_kernel<<<(B + 255) / 256, 256, 0, st>>>(len, c->scratch_given, B);
+    LAUNCH_CHECK();
+    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, nodes, c->scratch_given, goal, N_NODES, N_NODES, dense, final_step_weight, cost, 0);
     LAUNCH_CHECK();
     return 0;
 }

@@ -44,6 +44,12 @@ struct DecTailArgs {
     int slot0, n_slots;    // this launch decodes slots slot0 .. slot0+n_slots-1 (slot = node + 1)
     int n_nodes;           // 255
     int slots_per_unit;    // work unit = (candidate, run of slots)
+    // head = 1: pixel-copy head (PixelCopyDecoder, blox/torch/encoder_decoder.py:235-259): w5/b5 rows 0-2 = gen_head,
+    // 3-5 = mask_head; image = softmax(mask)_0 I_0 + softmax(mask)_1 I_g + softmax(mask)_2 tanh(gen)
+    int head;
+    const float* src0;     // [n_cand or 1][3][32][32] start image
+    const float* srcg;     // goal image
+    int src_stride;        // elements between candidates (0: shared)
 };
 
 // bilinear x2 (align_corners=False) source rows/weights for output index o of an n-long input
@@ -145,13 +151,25 @@ __global__ void __launch_bounds__(256) dec_tail_ref_kernel(const __grid_constant
         const int y = p / DT_WP, x = p - y * DT_WP;
         if (x >= 32) continue;
         float rgb[3] = {0.f, 0.f, 0.f};
-        for (int co = 0; co < 15; ++co) {
+        float v6[6];
+        for (int co = 0; co < (a.head ? 6 : 15); ++co) {
             float s = 0.f;
             for (int ci = 0; ci < 16; ++ci)
                 for (int tap = 0; tap < 16; ++tap)
                     s = fmaf(in_at(in5, ci, p + (tap >> 2) * DT_WP + (tap & 3)),
                              __bfloat162float(w5p[(co * 16 + ci) * 16 + tap]), s);
-            rgb[co % 3] += sigmoidf_(s + a.b5[co]);
+            if (a.head) v6[co] = s + a.b5[co];
+            else rgb[co % 3] += sigmoidf_(s + a.b5[co]);
+        }
+        if (a.head) {
+            const float mx = fmaxf(v6[3], fmaxf(v6[4], v6[5]));
+            const float e0 = __expf(v6[3] - mx), e1 = __expf(v6[4] - mx), e2 = __expf(v6[5] - mx);
+            const float inv = 1.0f / (e0 + e1 + e2);
+            const float* s0 = a.src0 + (size_t)cand * a.src_stride;
+            const float* sg = a.srcg + (size_t)cand * a.src_stride;
+            for (int k = 0; k < 3; ++k)
+                img[k * 1024 + y * 32 + x] = (e0 * s0[k * 1024 + y * 32 + x] + e1 * sg[k * 1024 + y * 32 + x] + e2 * tanhf_(v6[k])) * inv;
+            continue;
         }
         for (int k = 0; k < 3; ++k) img[k * 1024 + y * 32 + x] = rgb[k] * 0.4f - 1.0f;
     }

@@ -61,6 +61,11 @@ struct DecTail3Args {
     float* images;         // [B][n_nodes][3][32][32]
     int Bp, n_cand, slot0, n_slots, n_nodes;
     unsigned long long* prof;   // optional [16]: per-role wait / work cycles
+    // pixel-copy head (dec_tail3_pc_kernel; PixelCopyDecoder, blox/torch/encoder_decoder.py:235-259): w5 holds gen_head
+    // (channels 0-2, unscaled) and mask_head (3-5), b5h their biases
+    const float* src0;     // [n_cand or 1][3][32][32] start image
+    const float* srcg;     // goal image
+    int src_stride;        // elements between candidates (0: shared)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -106,7 +111,9 @@ __device__ __forceinline__ void d3_conv_tile(uint32_t a_lo, uint32_t a_hi, uint3
 
 #define D3_T() (prof_on ? clock64() : 0ll)
 
-__global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_constant__ DecTail3Args a) {
+// HEAD 0: discrete-logistic-mixture mean (15 channels); HEAD 1: pixel-copy head (3 generated + 3 mask channels)
+template <int HEAD>
+__device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* in4 = smem + D3_OFF_IN4;
@@ -375,14 +382,17 @@ __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_c
         const int q = warp - 4;
         const int m = q * 32 + lane;
         uint32_t n5 = 0;
-        float bh[15];
+        constexpr int NCH = HEAD == 0 ? 15 : 6;
+        float bh[NCH];
 #pragma unroll
-        for (int i = 0; i < 15; ++i) bh[i] = bias5[i];
+        for (int i = 0; i < NCH; ++i) bh[i] = bias5[i];
         for (int n = 0; n < n_img; ++n) {
             const int img = img0 + n;
             const int cand = img / a.n_slots, sl = img - cand * a.n_slots;
             const int node = a.slot0 + sl - 1;
             float* out = a.images + ((size_t)cand * a.n_nodes + node) * 3072;
+            const float* src0 = HEAD == 1 ? a.src0 + (size_t)cand * a.src_stride : nullptr;
+            const float* srcg = HEAD == 1 ? a.srcg + (size_t)cand * a.src_stride : nullptr;
             for (int T = 0; T < 2; ++T, ++n5) {
                 const int b5 = n5 & (D3_NB - 1);
                 long long w0 = D3_T();
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_c
                 tc_fence_after();
                 const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + TM_D5 + b5 * 64;
                 float rgb[3][4];
+                float mk[2][4];          // HEAD 1: softmax weights of the start / goal image per pixel of the quad
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float d[32];
@@ -403,14 +414,37 @@ __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_c
                     }
 #pragma unroll
                     for (int j2 = 0; j2 < 2; ++j2) {
-                        float s[3] = {0.f, 0.f, 0.f};
+                        if (HEAD == 0) {
+                            float s[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int ch = 0; ch < 15; ++ch) s[ch % 3] += tanh_approx(d[16 * j2 + ch] + bh[ch]);
+                            for (int ch = 0; ch < 15; ++ch) s[ch % 3] += tanh_approx(d[16 * j2 + ch] + bh[ch]);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) rgb[k][3 - (2 * half + j2)] = 0.2f * s[k];
+                            for (int k = 0; k < 3; ++k) rgb[k][3 - (2 * half + j2)] = 0.2f * s[k];
+                        } else {
+                            const int px = 3 - (2 * half + j2);
+                            const float l0 = d[16 * j2 + 3] + bh[3], l1 = d[16 * j2 + 4] + bh[4], l2 = d[16 * j2 + 5] + bh[5];
+                            const float mx = fmaxf(l0, fmaxf(l1, l2));
+                            const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+                            const float inv = __fdividef(1.0f, e0 + e1 + e2);
+                            mk[0][px] = e0 * inv;
+                            mk[1][px] = e1 * inv;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) rgb[k][px] = e2 * inv * tanh_approx(d[16 * j2 + k] + bh[k]);
+                        }
                     }
                 }
                 const int oy = 16 * T + (m >> 3), c = m & 7;
+                if (HEAD == 1) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(src0 + k * 1024 + oy * 32 + 4 * c));
+                        const float4 pg = __ldg(reinterpret_cast<const float4*>(srcg + k * 1024 + oy * 32 + 4 * c));
+                        rgb[k][0] += mk[0][0] * p0.x + mk[1][0] * pg.x;
+                        rgb[k][1] += mk[0][1] * p0.y + mk[1][1] * pg.y;
+                        rgb[k][2] += mk[0][2] * p0.z + mk[1][2] * pg.z;
+                        rgb[k][3] += mk[0][3] * p0.w + mk[1][3] * pg.w;
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     *reinterpret_cast<float4*>(out + k * 1024 + oy * 32 + 4 * c) = make_float4(rgb[k][0], rgb[k][1], rgb[k][2], rgb[k][3]);
@@ -426,6 +460,13 @@ __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_c
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+}
+
+__global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_constant__ DecTail3Args a) {
+    dec_tail3_body<0>(a);
+}
+__global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_pc_kernel(const __grid_constant__ DecTail3Args a) {
+    dec_tail3_body<1>(a);
 }
 
 // per-candidate skip term of the 32->16 conv in the quad layout of dec_tail3:

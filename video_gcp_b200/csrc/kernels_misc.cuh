@@ -213,10 +213,10 @@ __global__ void make_pairs_kernel(const float* __restrict__ seq, const long long
 __global__ void __launch_bounds__(256) cost_l2_kernel(const float* __restrict__ images, const int* __restrict__ frame_node,
                                                       const long long* __restrict__ end_ind, const float* __restrict__ goal,
                                                       int n_nodes, int lcap, int dense, float final_w,
-                                                      float* __restrict__ cost) {
+                                                      float* __restrict__ cost, int min_last = 1) {
     __shared__ float part[8];
     const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int last = max((int)end_ind[c], 1);   // cem_simulator.py:31: end_ind = max(end_ind, 1)
+    const int last = max((int)end_ind[c], min_last);   // cem_simulator.py:31: end_ind = max(end_ind, 1)
     const float4* g4 = reinterpret_cast<const float4*>(goal);
     float acc = 0.f;
     for (int t = warp; t <= last; t += 8) {
@@ -418,6 +418,47 @@ __global__ void copy_frame0_kernel(const float* __restrict__ I_0, int shared, in
     const int k = idx % 768, c = idx / 768;
     reinterpret_cast<float4*>(images)[(size_t)c * n_frames * 768 + k] =
         __ldg(reinterpret_cast<const float4*>(I_0) + (shared ? 0 : (size_t)c * 768) + k);
+}
+
+// AdaptiveBinding.prune_sequence (gcp/prediction/models/adaptive_binding/adaptive.py:62-77): node 0 is always kept,
+// node n > 0 is dropped when sigmoid(distance[n-1]) > threshold, i.e. distance > logit(threshold).  One block per
+// candidate; the kept depth-first indices are compacted in order (ballot + warp prefix), len = their count.
+__global__ void __launch_bounds__(256) adaptive_prune_kernel(const float* __restrict__ dist, int dist_ld, int n_nodes,
+                                                             float logit_thr, int* __restrict__ nodes, int* __restrict__ len,
+                                                             long long* __restrict__ end_out) {
+    __shared__ int wsum[8];
+    const int c = blockIdx.x, n = threadIdx.x, warp = n >> 5, lane = n & 31;
+    const bool keep = n < n_nodes && (n == 0 || !(dist[(size_t)c * dist_ld + n - 1] > logit_thr));
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(b);
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    if (keep) nodes[(size_t)c * n_nodes + base + __popc(b & ((1u << lane) - 1u))] = n;
+    if (n == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        len[c] = tot;
+        if (end_out != nullptr) end_out[c] = tot - 1;
+    }
+}
+
+// dst[c][t][:] = t < len[c] ? src[c][nodes[c][t]][:] : 0   (thread per float4; lcap rows per candidate)
+__global__ void gather_nodes_kernel(const float* __restrict__ src, const int* __restrict__ nodes, const int* __restrict__ len,
+                                    int n_cand, int n_nodes, int d4, float* __restrict__ dst) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * n_nodes * d4) return;
+    const int k = idx % d4;
+    const int t = (idx / d4) % n_nodes;
+    const int c = idx / ((size_t)d4 * n_nodes);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len[c]) v = __ldg(reinterpret_cast<const float4*>(src) + ((size_t)c * n_nodes + nodes[(size_t)c * n_nodes + t]) * d4 + k);
+    reinterpret_cast<float4*>(dst)[idx] = v;
+}
+
+__global__ void len_to_end_kernel(const int* __restrict__ len, long long* __restrict__ end, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) end[i] = (long long)len[i] - 1;
 }
 
 __global__ void fill_i64_kernel(long long* p, long long v, int n) {

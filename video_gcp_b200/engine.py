@@ -36,7 +36,7 @@ class Engine:
         self.max_candidates = int(max_candidates)
         self.attach_cost_mdl = bool(attach_cost_mdl)
         self.model = model
-        kind = {"tree": _C.MODEL_TREE, "sequential": _C.MODEL_SEQUENTIAL}[model]
+        kind = {"tree": _C.MODEL_TREE, "sequential": _C.MODEL_SEQUENTIAL, "tree_adaptive": _C.MODEL_TREE_ADAPTIVE}[model]
         cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(use_ref_kernels),
                         int(decoder_slot_chunk), kind)
         h = C.c_void_p()
@@ -88,7 +88,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
-                want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False):
+                want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False,
+                prune_threshold=0.5):
         """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32, either on the device or a PINNED host
         tensor; a host tensor is uploaded by the library level by level on its own copy stream, overlapped with
         the encoder and the upper tree levels (out["z"] is the device copy, valid in stream order after the call).
@@ -119,6 +120,13 @@ class Engine:
             out["log_sigma_df"] = mk("log_sigma_df", (B, N_NODES, NZ_VAE))
         if want_images:
             out["images_df"] = mk("images_df", (B, N_NODES, 3, 32, 32))
+        adaptive = self.model == "tree_adaptive"
+        if adaptive:
+            # AdaptiveBinding: distance-predictor logits + the kept (depth-first) node list per candidate
+            want_existence = want_aux = False
+            out["distances"] = mk("distances", (B, N_NODES - 1))
+            out["pruned_nodes"] = mk("pruned_nodes", (B, N_NODES), torch.int32)
+            out["pruned_len"] = mk("pruned_len", (B,), torch.int32)
         if want_existence:
             out["existence"] = mk("existence", (B, N_NODES))
         if want_aux:
@@ -132,7 +140,8 @@ class Engine:
             _ptr(out["e_0"]), _ptr(out["e_g"]), _ptr(out.get("seq_len_logits")), _ptr(out["end_ind"]),
             _ptr(out["e_df"]), _ptr(out.get("mu_df")), _ptr(out.get("log_sigma_df")), _ptr(out.get("images_df")),
             _ptr(out.get("existence")), _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")),
-            _ptr(out.get("regressed_state")))
+            _ptr(out.get("regressed_state")), _ptr(out.get("distances")), _ptr(out.get("pruned_nodes")),
+            _ptr(out.get("pruned_len")), float(prune_threshold))
         with torch.cuda.device(self.index):
             _C.check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
         return out
@@ -184,6 +193,26 @@ class Engine:
         with torch.cuda.device(self.index):
             _C.check(self.lib.gcpb200_cost_l2_seq(self.h, _ptr(images), int(n_frames), _ptr(end_ind.contiguous()), _ptr(goal), B,
                                                   int(dense), float(final_step_weight), _ptr(cost), _stream()))
+        return cost
+
+    def gather_nodes(self, src_df, nodes, length):
+        """src_df [B,255,D...] -> [B,255,D] with rows nodes[c,:length[c]] in order, zeros after (adaptive pruning)."""
+        B = src_df.shape[0]
+        flat = src_df.reshape(B, N_NODES, -1).contiguous()
+        D = flat.shape[2]
+        dst = torch.empty(B, N_NODES, D, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_gather_nodes(self.h, _ptr(flat), _ptr(nodes.contiguous()), _ptr(length.contiguous()), B, D,
+                                                   _ptr(dst), _stream()))
+        return dst
+
+    def cost_l2_nodes(self, images_df, nodes, length, goal, dense=True, final_step_weight=1.0):
+        B = images_df.shape[0]
+        cost = self._buf("cost_l2", (B,))
+        goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cost_l2_nodes(self.h, _ptr(images_df), _ptr(nodes.contiguous()), _ptr(length.contiguous()),
+                                                    _ptr(goal), B, int(dense), float(final_step_weight), _ptr(cost), _stream()))
         return cost
 
     def prune_gather(self, src_df, end_ind):

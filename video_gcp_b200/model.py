@@ -234,9 +234,20 @@ class _GCPModelBase(nn.Module):
 
 
 class TreeModel(_GCPModelBase):
+    """GCP-tree model.  Two configurations are supported, selected by the hyper-parameters exactly as in the
+    reference (same class, gcp/prediction/models/tree/tree.py:14): the balanced 25-room planner model
+    (mod_hyper.py) and the adaptive-binding model (base_configs/gcp_adaptive.py: pixel-copy decoder +
+    distance-predictor pruning, no auxiliary heads)."""
     ENGINE_KIND = "tree"
 
     def _check_config(self, hp):
+        if ("dtw" in hp.matching_type and hp.add_weighted_pixel_copy and hp.decoder_distribution == "gaussian"
+                and hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
+                and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
+                and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
+                and hp.lstm_init == "mlp" and hp.use_skips and not hp.attach_inv_mdl and not hp.attach_state_regressor):
+            self.ENGINE_KIND = "tree_adaptive"
+            return
         if not (hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
                 and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
                 and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
@@ -263,7 +274,8 @@ class TreeModel(_GCPModelBase):
         if "start_ind" not in inputs:
             inputs.start_ind = torch.zeros(B, dtype=torch.long, device=dev)
         res = eng.rollout(inputs.I_0, inputs.I_g, z, end_ind=inject, seed=self.seed, images_shared=shared,
-                          want_images=self.return_images, want_prior=self.return_prior)
+                          want_images=self.return_images, want_prior=self.return_prior,
+                          prune_threshold=self._hp.learned_pruning_threshold)
         self.seed += 1
         inputs.e_0 = res["e_0"][..., None, None]
         inputs.e_g = res["e_g"][..., None, None]
@@ -278,6 +290,14 @@ class TreeModel(_GCPModelBase):
             fields["p_z_log_sigma"] = res["log_sigma_df"][..., None, None]
         outputs.tree = TreeView(fields, self._hp.hierarchy_levels)
         outputs.dense_rec = AttrDict()
+        if self.ENGINE_KIND == "tree_adaptive":
+            # AdaptiveBinding.prune_sequence (adaptive.py:62-77): the kept nodes as index lists; pruned_prediction is
+            # materialised from them on first use
+            outputs.distance_predictor = AttrDict(distances=res["distances"])
+            outputs.pruned_nodes, outputs.pruned_len = res["pruned_nodes"], res["pruned_len"]
+            if "images_df" in res:
+                outputs.pruned_prediction = _LazyNodePruned(self, outputs, res["images_df"])
+            return outputs
         outputs.existence_predictor = AttrDict(existence=res["existence"])
         lmax = int(res["end_ind"].max()) + 1
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
@@ -376,6 +396,28 @@ class _LazyPruned:
     def _get(self):
         if self._v is None:
             self._v = self._m.dense_rec.get_all_samples_with_len(None, self._o, None, "basic")[0]
+        return self._v
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
+class _LazyNodePruned:
+    """`outputs.pruned_prediction` of the adaptive model: list of [L_i,3,32,32]; gathered on first use."""
+
+    def __init__(self, model, outputs, images_df):
+        self._m, self._o, self._img, self._v = model, outputs, images_df, None
+
+    def _get(self):
+        if self._v is None:
+            buf = self._m.engine.gather_nodes(self._img, self._o.pruned_nodes, self._o.pruned_len)
+            self._v = [buf[i, :n].reshape(n, 3, 32, 32) for i, n in enumerate(self._o.pruned_len.tolist())]
         return self._v
 
     def __iter__(self):
