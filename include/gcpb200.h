@@ -16,6 +16,9 @@
  *   gcpb200_cost_learned   ImageWrappedLearnedCostFcn / LearnedCostEstimate list branch
  *                          (gcp/planning/cem/cost_fcn.py:79-116) with TestTimeCostModel.forward
  *                          (gcp/prediction/models/auxilliary_models/cost_mdl.py:138-145)
+ *   gcpb200_cost_pairs     LearnedCostEstimate ndarray / list branches on row pairs, as HierarchicalTreeLatentOptimizer uses them
+ *                          (gcp/planning/cem/cost_fcn.py:84-97; gcp/planning/tree_optimizer.py:96-99,145-150)
+ *   gcpb200_infer_action   ImageCEMPolicy._infer_action: encoder + inverse model (gcp/planning/planner_policy.py:215-221)
  *   gcpb200_topk           CEMPlanner._get_best_rollouts argsort + slice (gcp/planning/cem/cem_planner.py:124-135)
  *   gcpb200_refit          FlatCEMSampler.fit (gcp/planning/cem/sampler.py:44-46)
  *   gcpb200_sample_noise   FlatCEMSampler.sample (gcp/planning/cem/sampler.py:40-42), on device
@@ -166,6 +169,24 @@ int gcpb200_cost_l2(gcpb200_ctx* ctx, const float* images_df, const int64_t* end
 /* cost[c] = sum over consecutive pairs of cat(latents of c, goal_seq) of the learned pairwise cost. */
 int gcpb200_cost_learned(gcpb200_ctx* ctx, const float* e_df, const int64_t* end_ind, int B,
                          const float* goal_seq /* [Lg,128] */, int Lg, float* cost /* [B] */, void* stream);
+
+/* Learned pairwise cost on arbitrary row pairs of a latent table lat [R,128] (device):
+ *   seg_off == NULL: cost[i] = cost_pred(cat(lat[idx1[i]], lat[idx2[i]])), i < n -- LearnedCostEstimate.__call__, ndarray
+ *     branch (gcp/planning/cem/cost_fcn.py:84-87) with TestTimeCostModel.forward (cost_mdl.py:138-145), as the hierarchical
+ *     optimiser calls it on (start, subgoal) and (subgoal, goal) latents (gcp/planning/tree_optimizer.py:96-99);
+ *   seg_off != NULL (device int32[n_seg+1], ascending, seg_off[n_seg] <= n): cost[s] = sum of the pair costs
+ *     seg_off[s] .. seg_off[s+1]-1 -- the list branch (cost_fcn.py:88-97) on segments (tree_optimizer.py:145-150).
+ * idx1 / idx2: device int32[n].  n <= 200 * max_candidates. */
+int gcpb200_cost_pairs(gcpb200_ctx* ctx, const float* lat, const int32_t* idx1, const int32_t* idx2, int n,
+                       const int32_t* seg_off, int n_seg, float* cost, void* stream);
+
+/* Closed-loop execution step (ImageCEMPolicy._infer_action, gcp/planning/planner_policy.py:215-221):
+ * enc = encoder(img); action = inv_mdl.action_pred(cat(enc, target_latent)) (InverseModel.run_single,
+ * gcp/prediction/models/auxilliary_models/inverse_mdl.py:221-224).  img [n,3,32,32] fp32 in [-1,1], target_latent
+ * [n,128], action [n,2], enc [n,128] or NULL; all device pointers.  Uses the rollout workspace: stream-order it with
+ * the rollouts of the same context. */
+int gcpb200_infer_action(gcpb200_ctx* ctx, const float* img, const float* target_latent, int n, float* action /* [n,2] */,
+                         float* enc /* [n,128] or NULL */, void* stream);
 
 /* indices (and values) of the k lowest costs in ascending order; ties broken by index. */
 int gcpb200_topk(gcpb200_ctx* ctx, const float* cost, int N, int k, int32_t* idx /* [k] */, float* val /* [k] or NULL */,

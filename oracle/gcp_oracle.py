@@ -288,6 +288,21 @@ def simulator_rollout(sd, state, goal, samples, end_ind, append_latent=True):
                 latents=cap(out["model_enc_seq"]))
 
 
+def infer_action(sd, current_img, target_latent):
+    """ImageCEMPolicy._infer_action (gcp/planning/planner_policy.py:215-221): closed-loop execution step.
+    current_img numpy [1,H,W,3] (env range, [0,1] or 0..255); target_latent numpy [128] (next latent of the plan).
+    enc = encoder(env2planner(img)) (cem_simulator.py:87-96); action = inv_mdl.action_pred(enc, target)
+    (InverseModel.run_single, inverse_mdl.py:221-224).  Returns (action [2], enc [128])."""
+    img = torch.as_tensor(np.asarray(current_img), dtype=torch.float32)
+    if img.max() > 1.0:
+        img = img / 255.0
+    img = img.permute(0, 3, 1, 2) * 2 - 1.0
+    enc, _ = encoder(sd, img)
+    tgt = torch.as_tensor(np.asarray(target_latent), dtype=torch.float32)[None]
+    act = mlp(sd, "inv_mdl.action_pred", torch.cat([enc, tgt], 1), conv=False)
+    return act[0].numpy(), enc[0].numpy()
+
+
 # --------------------------------------------------------------------------------------------------
 # sequential GCP (config 3): VRNN prior rollout
 # --------------------------------------------------------------------------------------------------

@@ -1532,6 +1532,63 @@ extern "C" int gcpb200_cost_learned(gcpb200_ctx* c, const float* e_df, const int
     return 0;
 }
 
+extern "C" int gcpb200_cost_pairs(gcpb200_ctx* c, const float* lat, const int32_t* idx1, const int32_t* idx2, int n,
+                                  const int32_t* seg_off, int n_seg, float* cost, void* stream) {
+    CHECK(check_ready(c, 1));
+    if (!c->has_cost) {
+        gcp_set_error("learned cost needs attach_cost_mdl=1 and cost_mdl.cost_pred.* weights");
+        return -1;
+    }
+    const int rows = (n + 127) / 128 * 128;
+    if (n <= 0 || rows > c->pair_rows) {
+        gcp_set_error("gcpb200_cost_pairs: n = %d outside (0, %d]", n, c->pair_rows / 128 * 128);
+        return -1;
+    }
+    if (seg_off != nullptr && n_seg <= 0) {
+        gcp_set_error("gcpb200_cost_pairs: seg_off given but n_seg = %d", n_seg);
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const LevelGeom flat = {rows, 0, DEPTH};
+    make_pairs_idx_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(lat, idx1, lat, idx2, n, rows, c->pairs.p);
+    LAUNCH_CHECK();
+    CHECK(mlp_body(c, st, c->cost_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+    CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
+               epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 1, 1)));
+    if (seg_off != nullptr) {
+        seg_sum_kernel<<<n_seg, 32, 0, st>>>(c->rowcost, seg_off, cost);
+        LAUNCH_CHECK();
+    } else {
+        GCP_CUDA_CHECK(cudaMemcpyAsync(cost, c->rowcost, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+extern "C" int gcpb200_infer_action(gcpb200_ctx* c, const float* img, const float* target_latent, int n, float* action,
+                                    float* enc, void* stream) {
+    CHECK(check_ready(c, n));
+    if (c->model == GCPB200_MODEL_TREE_ADAPTIVE || !c->has_inv) {
+        gcp_set_error("gcpb200_infer_action needs inv_mdl.action_pred.* weights (attach_inv_mdl)");
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int rows = (n + 127) / 128 * 128;
+    const LevelGeom flat = {rows, 0, DEPTH};
+    // encoder on the current image(s): latent rows 0..n-1 of the workspace (the skip maps it also writes are scratch
+    // that every rollout recomputes)
+    encoder_kernel<<<dim3(n, 1), ENC_THREADS, 0, st>>>(img, img, c->enc, c->lat_f32, c->lat.p, 0, 0, c->s0, c->s2, c->s2b.p);
+    LAUNCH_CHECK();
+    if (enc) GCP_CUDA_CHECK(cudaMemcpyAsync(enc, c->lat_f32, (size_t)n * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));
+    make_pairs_idx_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(c->lat_f32, nullptr, target_latent, nullptr, n,
+                                                                                        rows, c->pairs.p);
+    LAUNCH_CHECK();
+    CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+    CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
+               epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
+    GCP_CUDA_CHECK(cudaMemcpyAsync(action, c->rowcost, (size_t)n * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 extern "C" int gcpb200_topk(gcpb200_ctx* c, const float* cost, int N, int k, int32_t* idx, float* val, void* stream) {
     if (!c || N <= 0 || k <= 0 || k > N) {
         gcp_set_error("gcpb200_topk: bad arguments (N %d, k %d)", N, k);

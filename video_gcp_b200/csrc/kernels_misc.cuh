@@ -242,6 +242,33 @@ __global__ void __launch_bounds__(256) cost_l2_kernel(const float* __restrict__ 
     }
 }
 
+// Pair rows for the learned pairwise networks from two row tables: pairs[r] = cat(a[ia[r]], b[ib[r]]) (a null index
+// list means row r itself).  Used by gcpb200_cost_pairs (LearnedCostEstimate ndarray branch, cost_fcn.py:84-87) and
+// gcpb200_infer_action (InverseModel.run_single, inverse_mdl.py:221-224).  Rows >= n are zero padding.
+__global__ void make_pairs_idx_kernel(const float* __restrict__ a, const int* __restrict__ ia, const float* __restrict__ b,
+                                      const int* __restrict__ ib, int n, int rows_padded, bf16* __restrict__ pairs) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows_padded * 256) return;
+    const int k = idx & 255;
+    const int row = (int)(idx >> 8);
+    float v = 0.f;
+    if (row < n) {
+        if (k < 128) v = a[(size_t)(ia != nullptr ? ia[row] : row) * 128 + k];
+        else v = b[(size_t)(ib != nullptr ? ib[row] : row) * 128 + (k - 128)];
+    }
+    pairs[idx] = __float2bfloat16_rn(v);
+}
+
+// cost[s] = sum of rowcost[seg_off[s] .. seg_off[s+1]) in a fixed (lane-strided, then butterfly) order: the summed
+// sequence cost of LearnedCostEstimate's list branch (cost_fcn.py:88-97).  One warp per segment.
+__global__ void seg_sum_kernel(const float* __restrict__ rowcost, const int* __restrict__ seg_off, float* __restrict__ cost) {
+    const int sgm = blockIdx.x, lane = threadIdx.x;
+    float s = 0.f;
+    for (int t = seg_off[sgm] + lane; t < seg_off[sgm + 1]; t += 32) s += rowcost[t];
+    s = warp_sum(s);
+    if (lane == 0) cost[sgm] = s;
+}
+
 // learned cost reduction: cost[c] = sum_{t <= end_ind[c]} rowcost[c*lcap + t] + tail
 __global__ void cost_sum_kernel(const float* __restrict__ rowcost, const long long* __restrict__ end_ind, int lcap,
                                 const float* __restrict__ tail, int n_tail, float* __restrict__ cost) {

@@ -243,6 +243,37 @@ class Engine:
                                                    goal_seq.shape[0], _ptr(cost), _stream()))
         return cost
 
+    def cost_pairs(self, lat, idx1, idx2, seg_off=None):
+        """Learned pairwise cost of row pairs (idx1[i], idx2[i]) of the latent table lat [R,128]; with seg_off
+        (int32 [n_seg+1]) the pair costs are summed per segment.  Index arrays may be host lists / numpy."""
+        as_i32 = lambda v: torch.as_tensor(v, dtype=torch.int32).to(self.device).contiguous()
+        lat = lat.to(device=self.device, dtype=torch.float32).contiguous()
+        idx1, idx2 = as_i32(idx1), as_i32(idx2)
+        n = int(idx1.shape[0])
+        assert idx2.shape[0] == n and lat.shape[-1] == NZ_ENC
+        n_seg = 0
+        if seg_off is not None:
+            seg_off = as_i32(seg_off)
+            n_seg = int(seg_off.shape[0]) - 1
+        cost = torch.empty(n_seg if seg_off is not None else n, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cost_pairs(self.h, _ptr(lat), _ptr(idx1), _ptr(idx2), n, _ptr(seg_off), n_seg,
+                                                 _ptr(cost), _stream()))
+        return cost
+
+    def infer_action(self, img, target_latent, want_enc=False):
+        """Closed-loop step: action = inv_mdl(cat(encoder(img), target_latent)).  img [n,3,32,32] in [-1,1]."""
+        f32 = dict(device=self.device, dtype=torch.float32)
+        img = img.to(**f32).contiguous()
+        target_latent = target_latent.to(**f32).reshape(img.shape[0], NZ_ENC).contiguous()
+        n = img.shape[0]
+        action = torch.empty(n, 2, **f32)
+        enc = torch.empty(n, NZ_ENC, **f32) if want_enc else None
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_infer_action(self.h, _ptr(img), _ptr(target_latent), n, _ptr(action), _ptr(enc),
+                                                   _stream()))
+        return (action, enc) if want_enc else action
+
     def topk(self, cost, k):
         N = cost.shape[0]
         idx = torch.empty(k, device=self.device, dtype=torch.int32)

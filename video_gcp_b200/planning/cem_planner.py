@@ -13,8 +13,8 @@ import torch
 import torch.distributed as dist
 
 from ..types import AttrDict, ParamDict
-from .cost_fcn import L2ImageCost
-from .sampler import FlatCEMSampler
+from .cost_fcn import L2ImageCost, LearnedCostEstimate
+from .sampler import FlatCEMSampler, ImageHierarchicalTreeCEMSampler
 
 
 class CEMPlanner:
@@ -121,4 +121,73 @@ class CEMPlanner:
 
 
 class ImageCEMPlanner(CEMPlanner):
+    pass
+
+
+class HierarchicalCEMPlanner(CEMPlanner):
+    """CEM planner for hierarchical optimisation (cem_planner.py:166-218 over CEMPlanner.__call__, :55-96): every
+    iteration rolls out the current proposals, optimises one more layer of the latent tree (best-of-N by learned
+    cost), and the final iteration's single optimised latent tree is rolled out as the plan.  Rollouts and all cost
+    inputs stay on the device; per iteration only the [n] costs and the chosen plan frames reach the host."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self._hp.sampling_rates_per_layer is not None:
+            assert self._hp.n_iters == len(self._hp.sampling_rates_per_layer) + 1
+
+    def _default_hparams(self):
+        d = super()._default_hparams()
+        d.update(ParamDict(horizon=None, cost_fcn=LearnedCostEstimate, cost_config={}, LL_cost_fcn=None,
+                           sampler=ImageHierarchicalTreeCEMSampler, n_level_hierarchy=None, sampling_rates_per_layer=None,
+                           n_ll_samples=5, sampler_rng="numpy"))
+        return d
+
+    def _build_cost(self):
+        # the learned cost network is the model's own cost_mdl.cost_pred (TestTimeCostModel loads those weights from
+        # the same checkpoint, cost_mdl.py:126-136)
+        cost_fcn = self._hp.cost_fcn(self._hp.cost_config, model=self._simulator._model)
+        if self._hp.LL_cost_fcn is not None:
+            raise NotImplementedError("a separate LL_cost_fcn is not on the 25-room planner path")
+        self._ll_cost_fcn = cost_fcn
+        return cost_fcn
+
+    def _build_sampler(self):
+        return self._hp.sampler(self._hp.sampler_clip_val, self._hp.max_seq_len, self._hp.action_dim, self._hp.initial_std,
+                                n_level_hierarchy=self._hp.n_level_hierarchy,
+                                sampling_rates_per_layer=self._hp.sampling_rates_per_layer,
+                                subgoal_cost_fcn=self._cost_fcn, ll_cost_fcn=self._ll_cost_fcn,
+                                n_ll_samples=self._hp.n_ll_samples, rng=self._hp.sampler_rng)
+
+    def _rollout_device(self, state, goal_state, samples):
+        """CEMPlanner._rollout (:115-122): chunks of max_rollout_bs, the remainder beyond the last full chunk is
+        dropped; one device call when everything fits the engine."""
+        bs = int(self._hp.max_rollout_bs)
+        n = samples.shape[0]
+        n_used = n if n <= bs else (n // bs) * bs
+        return self._simulator.rollout_device(state, goal_state, samples[:n_used], self._hp.max_seq_len)
+
+    def __call__(self, state, goal_state):
+        self._sampler.init()
+        logs = []
+        best_samples = best_scores = None
+        for it in range(self._hp.n_iters):
+            samples = self._sampler.sample(self._hp.batch_size)
+            ro = self._rollout_device(state, goal_state, samples)
+            best_rollouts, best_scores = self._sampler.optimize(ro, goal_state)
+            # cem_planner.py:214: the next proposals are drawn right after the optimisation step.  Only the last draw
+            # is used (it is the fully optimised tree); the numpy stream needs the others to stay reference-identical
+            if self._hp.sampler_rng == "numpy" or it == self._hp.n_iters - 1:
+                best_samples = self._sampler.sample(self._hp.batch_size)
+            logs.append(AttrDict(elite_rollouts=copy.deepcopy(best_rollouts), elite_scores=best_scores,
+                                 dists=self._sampler.get_dists(), goal_state=goal_state))
+        final = self._rollout_device(state, goal_state, best_samples).to_host(self._simulator._append_latent)
+        logs.append(AttrDict(elite_rollouts=copy.deepcopy(self._maybe_split_image(final.predictions)),
+                             elite_scores=best_scores, dists=self._sampler.get_dists(), goal_state=goal_state,
+                             elite_states=copy.deepcopy(final.states)))
+        self._logs.append(logs)
+        best_actions = self._get_action_plan(final, best_samples)
+        return final.predictions[0], best_actions[0], final.latents[0], best_scores[0]
+
+
+class HierarchicalImageCEMPlanner(HierarchicalCEMPlanner, ImageCEMPlanner):
     pass

@@ -96,11 +96,27 @@ class LearnedCostEstimate:
     def input_dim(self):
         return 128
 
+    @property
+    def engine(self):
+        return self._model.engine
+
     def device_cost(self, ro, goal_seq):
         return ro.model.engine.cost_learned(ro.e_df, ro.end_ind, goal_seq)
 
+    def pairs_device(self, lat, idx1, idx2, seg_off=None):
+        """Pair costs over rows of a device latent table (per pair, or summed per segment): what the hierarchical
+        optimiser evaluates (tree_optimizer.py:96-99,145-150).  Returns a device tensor."""
+        return self._model.engine.cost_pairs(lat, idx1, idx2, seg_off)
+
     def __call__(self, start_enc, goal_enc):
         eng = self._model.engine
+        if isinstance(start_enc, np.ndarray):
+            # cost of single start / goal pairs (cost_fcn.py:84-87): [n,128] x 2 -> [n,1]
+            a = np.asarray(start_enc, dtype=np.float32).reshape(-1, 128)
+            b = np.asarray(goal_enc, dtype=np.float32).reshape(-1, 128)
+            n = a.shape[0]
+            lat = torch.as_tensor(np.concatenate([a, b])).to(eng.device)
+            return eng.cost_pairs(lat, np.arange(n), n + np.arange(n)).cpu().numpy()[:, None]
         if isinstance(start_enc, list):
             out = np.zeros(len(start_enc), dtype=np.float32)
             buf, end = _lists_to_device(eng, start_enc, 128)

@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from ..types import AttrDict
+from .tree_optimizer import ImageHierarchicalTreeLatentOptimizer
 
 
 class CEMSampler:
@@ -84,3 +85,62 @@ class SimpleTreeCEMSampler(FlatCEMSampler):
         super().__init__(*args)
         self._n_steps = 2 ** n_level_hierarchy - 1
         self.init()
+
+
+class ImageHierarchicalTreeCEMSampler(SimpleTreeCEMSampler):
+    """Tree-GCP sampler that optimises the layers of the hierarchy sequentially, starting from the top, for image
+    prediction GCPs (sampler.py:83-143).  `rng`: "numpy" reproduces the reference's np.random stream, "device" draws
+    from the engine's Philox stream and keeps the proposals in HBM."""
+
+    def __init__(self, *args, sampling_rates_per_layer, subgoal_cost_fcn, ll_cost_fcn, n_ll_samples, rng="numpy", **kwargs):
+        self._sampling_rates_per_layer = sampling_rates_per_layer
+        self._subgoal_cost_fcn = subgoal_cost_fcn
+        self._ll_cost_fcn = ll_cost_fcn
+        self._n_ll_samples = n_ll_samples
+        self._rng = rng
+        self._optimizer = None
+        super().__init__(*args, **kwargs)
+        assert self._n_layer_hierarchy >= len(sampling_rates_per_layer)     # not enough layers in tree
+
+    def init(self):
+        if getattr(self, "_n_layer_hierarchy", None) is None or getattr(self, "_ll_cost_fcn", None) is None:
+            return      # base-class constructor calls init() before the tree parameters exist
+        self._optimizer = ImageHierarchicalTreeLatentOptimizer(
+            self._action_dim, list(self._sampling_rates_per_layer), self._n_layer_hierarchy, self._subgoal_cost_fcn,
+            self._ll_cost_fcn, self._n_ll_samples, engine=self.engine, rng=self._rng, seed=self._iter_seed())
+        self._iter += 1
+
+    def sample(self, n_samples):
+        z = self._optimizer.sample()
+        if isinstance(z, torch.Tensor):
+            return z.clamp(-self._clip_val, self._clip_val).contiguous()
+        return np.clip(z, -self._clip_val, self._clip_val)
+
+    def optimize(self, rollouts, goal):
+        best_rollout, best_cost = self._optimizer.optimize(rollouts, goal)
+        goal = np.asarray(goal, dtype=np.float32)
+        if (best_rollout[-1] != goal[0].transpose(2, 0, 1)).any():    # can happen if too few frames on right tree side
+            best_rollout = np.concatenate((best_rollout, goal.transpose(0, 3, 1, 2)))
+        if not hasattr(best_cost, "__len__"):
+            best_cost = [best_cost]
+        return [best_rollout], best_cost
+
+    def fit(*args, **kwargs):
+        """Does not support refitting distributions (sampler.py:113-115)."""
+
+    def get_dists(self):
+        return AttrDict(mean=0., std=1.)
+
+    def sync_host(self):
+        pass
+
+    @property
+    def append_latent(self):
+        return True     # latent rollouts are needed to compute subgoal costs
+
+    @property
+    def fully_optimized(self):
+        return self._optimizer.fully_optimized
+
+
+HierarchicalTreeCEMSampler = ImageHierarchicalTreeCEMSampler    # only the image variant is on the 25-room path
