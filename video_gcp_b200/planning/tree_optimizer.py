@@ -107,7 +107,8 @@ class ImageHierarchicalTreeLatentOptimizer:
         self._opt_z = None
         self._latest_z_samples = None
         self._engine, self._rng, self._seed = engine, rng, int(seed)
-        self._counter = _counter if _counter is not None else [0]     # shared Philox candidate counter (device rng)
+        self._counter = _counter if _counter is not None else [0, None, 0]   # device rng, shared by the whole tree:
+        # [next Philox candidate id, pool of latent rows drawn for the current sample() call, rows handed out]
         sampling_rates = list(sampling_rates)
         if sampling_rates:
             self._n_samples = sampling_rates.pop(0)
@@ -119,22 +120,36 @@ class ImageHierarchicalTreeLatentOptimizer:
             self._n_samples = final_layer_samples
             self._n_latents = 2 ** depth - 1
             self._children = None
-        self.mean = np.zeros((self._n_latents, self._latent_dim))
-        self.std = np.ones((self._n_latents, self._latent_dim))
+        self.mean, self.std = 0.0, 1.0          # N(0, 1) per latent element; never refit (sampler.py:113-115)
 
     # ------------------------------------------------------------------ sampling (tree_optimizer.py:46-72,142-143)
     def _sample(self, n):
         if self._rng == "numpy":
             return np.random.normal(loc=self.mean, scale=self.std, size=(self._n_samples, self._n_latents, self._latent_dim))[:n]
         rows = n * self._n_latents
-        blocks = -(-rows // 255)
-        z = self._engine.sample_noise(blocks, None, None, 1.0, self._seed, self._counter[0])
-        self._counter[0] += blocks
-        return z.reshape(-1, self._latent_dim)[:rows].reshape(n, self._n_latents, self._latent_dim)
+        pool = self._counter[1]
+        z = pool[self._counter[2]:self._counter[2] + rows]
+        self._counter[2] += rows
+        return z.reshape(n, self._n_latents, self._latent_dim)
 
-    def sample(self, below_opt_layer=False):
+    def _rows_needed(self, below):
+        """Latent rows one sample() call draws (device rng: drawn as ONE Philox launch, then sliced)."""
+        n = 0 if self._is_optimized else (1 if below else self._n_samples) * self._n_latents
+        if self._children is not None:
+            k = 1 if (self._is_optimized or below) else self._n_samples
+            nb = below or not self._is_optimized
+            n += sum(self._children[0][i]._rows_needed(nb) + self._children[1][i]._rows_needed(nb) for i in range(k))
+        return n
+
+    def sample(self, below_opt_layer=False, _top=True):
         """Latents of all layers, concatenated in depth-first node order: N for the layer being optimised, one for the
         layers above (their optimum) and below (not used for the decision)."""
+        if _top and self._rng != "numpy":
+            rows = self._rows_needed(below_opt_layer)
+            blocks = max(-(-rows // 255), 1)
+            pool = self._engine.sample_noise(blocks, None, None, 1.0, self._seed, self._counter[0])
+            self._counter[0] += blocks
+            self._counter[1:] = [pool.reshape(-1, self._latent_dim), 0]
         if self._is_optimized:
             z = self._opt_z[None]
         else:
@@ -146,7 +161,7 @@ class ImageHierarchicalTreeLatentOptimizer:
         dev = not isinstance(z, np.ndarray)
         samples = []
         for child_left, child_right, z_i in zip(self._children[0], self._children[1], z):
-            z_left, z_right = child_left.sample(next_below), child_right.sample(next_below)
+            z_left, z_right = child_left.sample(next_below, False), child_right.sample(next_below, False)
             assert z_left.shape == z_right.shape          # latent tree needs to be balanced
             n = z_left.shape[0]
             mid = z_i[0].expand(n, 1, -1) if dev else np.tile(z_i[0], (n, 1, 1))
