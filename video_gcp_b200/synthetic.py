@@ -103,3 +103,26 @@ def synthetic_seq_inputs(n_candidates, seed=0, z_std=1.0, shared_images=True, n_
     end_ind = r.integers(2, n_steps + 1, size=(n_candidates,)).astype(np.int64)
     return dict(I_0=torch.from_numpy(I_0), I_g=torch.from_numpy(I_g), z=torch.from_numpy(z),
                 end_ind=torch.from_numpy(end_ind))
+
+
+def synthetic_train_batch(batch_size, seed=0, end_ind=None, max_seq_len=200):
+    """A training batch of the 25-room dataset_spec shape (BASELINE config 1): traj_seq uniform(-1,1)
+    [B,T,3,32,32] zeroed past end_ind, end_ind ~ randint(10,T), pad_mask = (t <= end_ind), states N(0,1) [B,T,2],
+    actions N(0,1) [B,T-1,2], I_0 = traj[:,0], I_g = traj[b,end_ind_b]; plus the posterior noise eps [B,255,256]
+    (depth-first node order) and the numpy seed used for the auxiliary heads' pair sampling."""
+    r = np.random.default_rng([int(seed), 777])
+    T = max_seq_len
+    traj = r.uniform(-1, 1, size=(batch_size, T, 3, 32, 32)).astype(np.float32)
+    if end_ind is None:
+        end_ind = r.integers(10, T, size=(batch_size,))
+    end_ind = np.asarray(end_ind, dtype=np.int64)
+    pad = (np.arange(T)[None] <= end_ind[:, None]).astype(np.float32)
+    traj *= pad[:, :, None, None, None]
+    states = r.standard_normal(size=(batch_size, T, 2)).astype(np.float32)
+    actions = r.standard_normal(size=(batch_size, T - 1, 2)).astype(np.float32)
+    eps = r.standard_normal(size=(batch_size, 255, 256)).astype(np.float32)
+    t = torch.from_numpy
+    traj_t = t(traj)
+    return dict(traj_seq=traj_t, pad_mask=t(pad), end_ind=t(end_ind), states=t(states), actions=t(actions),
+                I_0=traj_t[:, 0].clone(), I_g=traj_t[torch.arange(batch_size), t(end_ind)].clone(), eps=t(eps),
+                np_seed=int(seed) + 1000)
