@@ -19,6 +19,10 @@
  *   gcpb200_cost_pairs     LearnedCostEstimate ndarray / list branches on row pairs, as HierarchicalTreeLatentOptimizer uses them
  *                          (gcp/planning/cem/cost_fcn.py:84-97; gcp/planning/tree_optimizer.py:96-99,145-150)
  *   gcpb200_infer_action   ImageCEMPolicy._infer_action: encoder + inverse model (gcp/planning/planner_policy.py:215-221)
+ *   gcpb200_forward_loss   training-phase forward + loss: BaseGCPModel.forward(phase='train') with the approximate posterior,
+ *                          TreeModel.loss and get_total_loss, as train.py:155-157 / :204-206 call them
+ *                          (gcp/prediction/models/base_gcp.py:140-304; tree/tree.py:42-79; tree/tree_module.py:67-157;
+ *                           tree/inference.py:16-41; tree/frame_binding.py:42-100)
  *   gcpb200_topk           CEMPlanner._get_best_rollouts argsort + slice (gcp/planning/cem/cem_planner.py:124-135)
  *   gcpb200_refit          FlatCEMSampler.fit (gcp/planning/cem/sampler.py:44-46)
  *   gcpb200_sample_noise   FlatCEMSampler.sample (gcp/planning/cem/sampler.py:40-42), on device
@@ -187,6 +191,65 @@ int gcpb200_cost_pairs(gcpb200_ctx* ctx, const float* lat, const int32_t* idx1, 
  * the rollouts of the same context. */
 int gcpb200_infer_action(gcpb200_ctx* ctx, const float* img, const float* target_latent, int n, float* action /* [n,2] */,
                          float* enc /* [n,128] or NULL */, void* stream);
+
+/* ---- training-phase forward + loss (BASELINE config 1: the 25-room prediction config, batch-statistic BatchNorm) ----
+ * One call = `output = model(inputs); losses = model.loss(inputs, output); losses.total = model.get_total_loss(...)`
+ * of the reference in .train() mode, forward only (no gradients: this is the validation pass of train.py:197-209).
+ * The reference's three random draws are inputs, so the call is deterministic: the posterior noise `eps`
+ * (q_z.sample(), blox/torch/dist.py:246-247), the inverse model's frame pair (inverse_mdl.py:88-98) and the cost model's
+ * frame pair + target (cost_mdl.py:100-113; the target is the host-side cost function applied to the ground-truth frames).
+ * Needs a GCPB200_MODEL_TREE context with attach_cost_mdl = 1 whose state dict held the training-only tensors
+ * (inf_encoder.*, tree_module.tree_modules.k.inference.q.*), and B <= 128. */
+#define GCPB200_LOSS_LEN_PRED 0
+#define GCPB200_LOSS_ACTION_RECONST 1
+#define GCPB200_LOSS_COST_ESTIMATION 2
+#define GCPB200_LOSS_STATE_REGRESSION 3
+#define GCPB200_LOSS_DENSE_IMG_REC 4
+#define GCPB200_LOSS_KL 5
+#define GCPB200_LOSS_EXISTENCE_PREDICTOR 6
+#define GCPB200_LOSS_ENTROPY 7
+#define GCPB200_LOSS_TOTAL 8
+#define GCPB200_N_LOSSES 9
+typedef struct {
+    /* ---- inputs (device) ---- */
+    const float* traj_seq;      /* [B,200,3,32,32] frames in [-1,1], zero past end_ind */
+    const float* pad_mask;      /* [B,200] 1 = real frame */
+    const int64_t* end_ind;     /* [B] index of the last real frame (>= 1) */
+    const float* I_0;           /* [B,3,32,32] */
+    const float* I_g;           /* [B,3,32,32] */
+    const float* states;        /* [B,200,2] traj_seq_states */
+    const float* actions;       /* [B,199,2] */
+    const float* eps;           /* [B,255,256] N(0,1) posterior noise, depth-first node order */
+    const int64_t* inv_t0;      /* [B] inverse-model frame pair: latent of frame t0 from the encoder, t1 from the tree */
+    const int64_t* inv_t1;
+    const int64_t* cost_start;  /* [B] cost-model pair (both from the tree's matched latents) */
+    const int64_t* cost_end;
+    const float* cost_target;   /* [B] ground-truth cost of that pair, or NULL: EuclideanPathLength of traj_seq[start..end]
+                                   (cost_fcn.py:49-54, the 25-room config's cost_fcn) computed on the device */
+    int B;
+    /* ---- outputs (device; losses required, the rest may be NULL) ---- */
+    float* losses;              /* [GCPB200_N_LOSSES] .value of each loss term, order above */
+    float* nll_per_frame;       /* [B,200] reconstruction NLL summed over the frame's 3x32x32 sub-pixels, times pad_mask */
+    float* kl_per_seq;          /* [B] */
+    float* e_0;                 /* [B,128] */
+    float* e_g;                 /* [B,128] */
+    float* enc_traj_seq;        /* [B,200,128] */
+    float* inf_enc_seq;         /* [B,200,128] */
+    float* seq_len_logits;      /* [B,200] */
+    float* e_df;                /* [B,255,128] node latents, depth-first */
+    float* p_mu;                /* [B,255,256] prior */
+    float* p_log_sigma;
+    float* q_mu;                /* [B,255,256] approximate posterior */
+    float* q_log_sigma;
+    int32_t* match_timesteps;   /* [B,255] frame index every node is matched to */
+    float* images_df;           /* [B,255,3,32,32] DLM mean image of every node (tree.df.images) */
+    float* existence;           /* [B,255] */
+    float* model_enc_seq;       /* [B,200,128] matched latents, zero padded */
+    float* regressed_state;     /* [B,200,2] */
+    float* inv_actions;         /* [B,2] */
+    float* cost_pred;           /* [B] */
+} gcpb200_train_io;
+int gcpb200_forward_loss(gcpb200_ctx* ctx, const gcpb200_train_io* io, void* stream);
 
 /* indices (and values) of the k lowest costs in ascending order; ties broken by index. */
 int gcpb200_topk(gcpb200_ctx* ctx, const float* cost, int N, int k, int32_t* idx /* [k] */, float* val /* [k] or NULL */,

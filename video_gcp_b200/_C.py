@@ -41,6 +41,19 @@ class SeqIO(C.Structure):
                 ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p)]
 
 
+LOSS_NAMES = ("len_pred", "action_reconst", "cost_estimation", "state_regression", "dense_img_rec", "kl",
+              "existence_predictor", "entropy", "total")          # GCPB200_LOSS_* order
+
+
+class TrainIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("traj_seq", "pad_mask", "end_ind", "I_0", "I_g", "states", "actions", "eps", "inv_t0", "inv_t1",
+                 "cost_start", "cost_end", "cost_target")] + [("B", C.c_int)] + [(n, C.c_void_p) for n in
+                ("losses", "nll_per_frame", "kl_per_seq", "e_0", "e_g", "enc_traj_seq", "inf_enc_seq", "seq_len_logits",
+                 "e_df", "p_mu", "p_log_sigma", "q_mu", "q_log_sigma", "match_timesteps", "images_df", "existence",
+                 "model_enc_seq", "regressed_state", "inv_actions", "cost_pred")]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "gcpb200_last_error": (C.c_char_p, []),
@@ -64,6 +77,7 @@ EXPORTS = {
     "gcpb200_cost_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
     "gcpb200_infer_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gcpb200_forward_loss": (C.c_int, [C.c_void_p, C.POINTER(TrainIO), C.c_void_p]),
     "gcpb200_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gcpb200_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gcpb200_sample_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_uint64,

@@ -13,6 +13,7 @@
 #include "dec_tail3.cuh"
 #include "gemm_host.cuh"
 #include "kernels_misc.cuh"
+#include "train_kernels.cuh"
 
 using namespace gcp;
 
@@ -71,6 +72,7 @@ struct SeqW {             // VRNNCell of the sequential GCP model (prior + gen_l
 };
 struct LevelW {
     Mlp prior;
+    Mlp q;                // approximate posterior q(z | e_l, e_r, e_tilde) (training path only; tree/inference.py:16-36)
     Mlp init;             // level 0 only; head rows [0,3072) -> left state, [3072,6144) -> right state
     DevMat init_head_r;   // second half of the init head
     DevMat proj, embed_main, embed_ctx, lstm[3], out;
@@ -115,6 +117,23 @@ struct gcpb200_ctx {
     // overlapped upload of host noise (gcpb200_rollout_io.z_host)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_start = nullptr, ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // ---- training-phase forward + loss (gcpb200_forward_loss)
+    bool has_train = false;
+    DevMat dec1t, dec2xt, dec2st, dec3t;          // decoder layers 1-3 without BatchNorm folding
+    float *bn_g[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // BatchNorm affine: encoder pyramid-0 (32), pyramid-1 (64),
+    float *bn_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // decoder net (64), pyramid-1 (32), pyramid-0 (16)
+    float *ie_w[3] = {nullptr, nullptr, nullptr}, *ie_b[3] = {nullptr, nullptr, nullptr};   // inf_encoder conv1d, [k][cin][128]
+    float *ie_gn_g = nullptr, *ie_gn_b = nullptr;
+    struct TrainWS {
+        int Bcap = 0;
+        float *y1 = nullptr, *y2 = nullptr, *enc_seq = nullptr, *h1 = nullptr, *h2 = nullptr, *inf_seq = nullptr;
+        double* stats = nullptr;                  // one zeroed block: st1 [3][32][2] | st2 [3][64][2] | gn [128][8][2] | d1 [64][2] | d2 | d3
+        int* tstep = nullptr;
+        unsigned char* keep = nullptr;
+        DevBuf x1, x2, x3;                        // raw / normalised decoder activations of all 255 nodes
+        float *pq[4] = {nullptr, nullptr, nullptr, nullptr};   // p_mu, p_ls, q_mu, q_ls [B][255][256]
+        float *nll_bt = nullptr, *kl_b = nullptr, *reg = nullptr, *inv_pred = nullptr, *cost_pred = nullptr, *exist_df = nullptr, *cost_tgt = nullptr;
+    } tw;
     // optional phase profiling (CUDA events on the caller's stream)
     bool profile = false;
     struct ProfSpan { int phase; cudaEvent_t a, b; };
@@ -352,20 +371,28 @@ static int fold_bn(const WStore& ws, const std::string& p, int C, BNFold* f) {
     return 0;
 }
 
-static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
+// Decoder layers 1-3 as dense matrices.  fold = true: eval-mode BatchNorm folded into rows / bias (rollout path);
+// fold = false: the raw convolutions (training path: batch statistics are applied by bn_stats / bn_apply kernels).
+static int pack_decoder_dense(gcpb200_ctx* c, const WStore& ws, bool fold, DevMat* d1, DevMat* d2x, DevMat* d2s, DevMat* d3) {
     const std::string p = "decoder.net.net.";
+    auto get_bn = [&](const std::string& name, int C, BNFold* f) -> int {
+        if (fold) return fold_bn(ws, name, C, f);
+        f->scale.assign(C, 1.0f);
+        f->shift.assign(C, 0.0f);
+        return 0;
+    };
     // ---- layer 1: ConvTranspose2d(128->64,k4) on a 1x1 map + BN + ReLU == Linear 128 -> 64*16
     const gcpb200_tensor* w1 = ws.get(p + "net.conv.weight", 4);
     if (!w1) return -1;
     BNFold bn1, bn2, bn3;
-    CHECK(fold_bn(ws, p + "net.norm", 64, &bn1));
-    CHECK(upload_mat(c, &c->dec1, 1024, 128,
+    CHECK(get_bn(p + "net.norm", 64, &bn1));
+    CHECK(upload_mat(c, d1, 1024, 128,
                      [&](int n, int k) { return w1->data[((size_t)k * 64 + n / 16) * 16 + n % 16] * bn1.scale[n / 16]; },
                      [&](int n) { return bn1.shift[n / 16]; }));
     // ---- layer 2: cat(x1 64ch, skip 64ch) 4x4 -> up -> pad -> conv(128->32) -> BN -> ReLU, as dense maps
     const gcpb200_tensor* w2 = ws.get(p + "pyramid-1.conv.weight", 4);
     if (!w2) return -1;
-    CHECK(fold_bn(ws, p + "pyramid-1.norm", 32, &bn2));
+    CHECK(get_bn(p + "pyramid-1.norm", 32, &bn2));
     {
         const std::vector<double> U = up_matrix(4);
         // output column order of layer 2 = K order of layer 3: n = iy*256 + co*8 + ix (row-major bands of the 8x8 map),
@@ -382,8 +409,8 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
                     for (int i = 0; i < 16; ++i)
                         dst[(size_t)col2(co, o) * 1024 + cil * 16 + i] = (float)(C[(size_t)o * 16 + i] * bn2.scale[co]);
             }
-        CHECK(upload_mat(c, &c->dec2x, 2048, 1024, [&](int n, int k) { return Wx[(size_t)n * 1024 + k]; }, nullptr));
-        CHECK(upload_mat(c, &c->dec2s, 2048, 1024, [&](int n, int k) { return Wsk[(size_t)n * 1024 + k]; },
+        CHECK(upload_mat(c, d2x, 2048, 1024, [&](int n, int k) { return Wx[(size_t)n * 1024 + k]; }, nullptr));
+        CHECK(upload_mat(c, d2s, 2048, 1024, [&](int n, int k) { return Wsk[(size_t)n * 1024 + k]; },
                          [&](int n) { return bn2.shift[(n & 255) >> 3]; }));
     }
     // ---- layer 3: 32ch 8x8 -> up -> pad -> conv(32->16) -> BN -> ReLU, as a banded dense map.  Output rows 2b, 2b+1
@@ -392,7 +419,7 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
     // Output columns are in the plane layout the tail kernel reads: n = ((co>>3)*256 + oy*16 + ox)*8 + (co&7).
     const gcpb200_tensor* w3 = ws.get(p + "pyramid-0.conv.weight", 4);
     if (!w3) return -1;
-    CHECK(fold_bn(ws, p + "pyramid-0.norm", 16, &bn3));
+    CHECK(get_bn(p + "pyramid-0.norm", 16, &bn3));
     {
         const std::vector<double> U = up_matrix(8);
         std::vector<float> W3((size_t)4096 * 1024, 0.f);
@@ -416,9 +443,15 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
             gcp_set_error("decoder layer 3: composite filter has weight outside its 4-row band (%g)", outside);
             return -1;
         }
-        CHECK(upload_mat(c, &c->dec3, 4096, 1024, [&](int n, int k) { return W3[(size_t)n * 1024 + k]; },
+        CHECK(upload_mat(c, d3, 4096, 1024, [&](int n, int k) { return W3[(size_t)n * 1024 + k]; },
                          [&](int n) { return bn3.shift[((n >> 3) / 256) * 8 + (n & 7)]; }));
     }
+    return 0;
+}
+
+static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
+    const std::string p = "decoder.net.net.";
+    CHECK(pack_decoder_dense(c, ws, true, &c->dec1, &c->dec2x, &c->dec2s, &c->dec3));
     // ---- layers 4, 5: packed for the implicit-GEMM kernel + plain copies for the verification kernel
     const gcpb200_tensor* w4 = ws.get(p + "additional_conv_layer.conv.weight", 4);
     const gcpb200_tensor* b4 = ws.get(p + "additional_conv_layer.conv.bias", 1);
@@ -561,6 +594,8 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
         return part * 256 + tile * 128 + chunk * 16 + u;
     };
     CHECK(pack_mlp(c, ws, tm + "prior", true, 2 * NZ_ENC, NZ_MID, 2 * NZ_VAE, 512, reparam_perm, &L.prior));
+    if (c->has_train)
+        CHECK(pack_mlp(c, ws, tm + "inference.q", true, 3 * NZ_ENC, NZ_MID, 2 * NZ_VAE, 512, reparam_perm, &L.q));
     if (l == 0)
         CHECK(pack_mlp(c, ws, tm + "lstm_initializer.net", true, 2 * NZ_ENC + NZ_VAE, INIT_MID, 2 * STATE, STATE, nullptr,
                        &L.init, &L.init_head_r, STATE));
@@ -593,6 +628,47 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     if (!wo || !bo) return -1;
     CHECK(upload_mat(c, &L.out, NZ_ENC, HID, [&](int n, int k) { return wo->data[(size_t)n * HID + k]; },
                      [&](int n) { return bo->data[n]; }));
+    return 0;
+}
+
+// Training-only tensors: BatchNorm affine terms (batch statistics are computed on the fly), the conv-1d inference
+// encoder (blox/torch/subnetworks.py:135-147), decoder layers 1-3 without BN folding.  The posterior MLPs are packed
+// per level in pack_level.
+static int pack_train(gcpb200_ctx* c, const WStore& ws) {
+    const char* bn_names[5] = {"encoder.net.net.pyramid-0.norm", "encoder.net.net.pyramid-1.norm", "decoder.net.net.net.norm",
+                               "decoder.net.net.pyramid-1.norm", "decoder.net.net.pyramid-0.norm"};
+    const int bn_c[5] = {32, 64, 64, 32, 16};
+    for (int i = 0; i < 5; ++i) {
+        const gcpb200_tensor *g = ws.get(std::string(bn_names[i]) + ".weight", 1), *b = ws.get(std::string(bn_names[i]) + ".bias", 1);
+        if (!g || !b) return -1;
+        CHECK(upload_f32(c, &c->bn_g[i], std::vector<float>(g->data, g->data + bn_c[i])));
+        CHECK(upload_f32(c, &c->bn_b[i], std::vector<float>(b->data, b->data + bn_c[i])));
+    }
+    const char* ie_names[3] = {"inf_encoder.net.input.conv", "inf_encoder.net.pyramid-0.conv", "inf_encoder.net.head.conv"};
+    for (int i = 0; i < 3; ++i) {
+        const gcpb200_tensor* w = ws.get(std::string(ie_names[i]) + ".weight", 3);
+        if (!w) return -1;
+        const int cin = (int)w->shape[1];
+        if (w->shape[0] != 128 || w->shape[2] != 3 || cin != (i == 0 ? 129 : 128)) {
+            gcp_set_error("%s.weight: unexpected shape", ie_names[i]);
+            return -1;
+        }
+        std::vector<float> wt((size_t)3 * cin * 128);
+        for (int k = 0; k < 3; ++k)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int co = 0; co < 128; ++co) wt[((size_t)k * cin + ci) * 128 + co] = w->data[((size_t)co * cin + ci) * 3 + k];
+        CHECK(upload_f32(c, &c->ie_w[i], wt));
+        if (i != 1) {
+            const gcpb200_tensor* b = ws.get(std::string(ie_names[i]) + ".bias", 1);
+            if (!b) return -1;
+            CHECK(upload_f32(c, &c->ie_b[i], std::vector<float>(b->data, b->data + 128)));
+        }
+    }
+    const gcpb200_tensor *gg = ws.get("inf_encoder.net.pyramid-0.norm.weight", 1), *gb = ws.get("inf_encoder.net.pyramid-0.norm.bias", 1);
+    if (!gg || !gb) return -1;
+    CHECK(upload_f32(c, &c->ie_gn_g, std::vector<float>(gg->data, gg->data + 128)));
+    CHECK(upload_f32(c, &c->ie_gn_b, std::vector<float>(gb->data, gb->data + 128)));
+    CHECK(pack_decoder_dense(c, ws, false, &c->dec1t, &c->dec2xt, &c->dec2st, &c->dec3t));
     return 0;
 }
 
@@ -883,6 +959,10 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
     for (int i = 0; i < n; ++i) ws.m[tensors[i].name] = &tensors[i];
     CHECK(pack_encoder(c, ws));
     CHECK(pack_decoder(c, ws));
+    // training-only tensors are optional: planner checkpoints stripped of them still load (forward_loss then refuses)
+    c->has_train = c->model == GCPB200_MODEL_TREE && ws.m.count("inf_encoder.net.input.conv.weight") != 0 &&
+                   ws.m.count("tree_module.tree_modules.0.inference.q.input.conv.weight") != 0;
+    if (c->has_train) CHECK(pack_train(c, ws));
     if (c->model == GCPB200_MODEL_SEQUENTIAL) {
         CHECK(pack_sequential(c, ws));
     } else {
@@ -1087,6 +1167,97 @@ static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const float* seq, con
     return 0;
 }
 
+// Posterior inputs of the training-phase tree (null = prior rollout)
+struct PosteriorArgs {
+    const float* inf_seq;   // [B][200][128] inference encoding of every frame
+    const int* tstep;       // [B][255] matched frame of every node (depth-first)
+    float *q_mu, *q_ls;     // [B][255][256]
+};
+
+// One level of SubgoalTreeLayer.produce_tree (gcp/prediction/utils/tree_utils.py:21-44) = TreeModule.produce_subgoal on all
+// B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
+static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
+                      const PosteriorArgs* post) {
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int goal_row0 = 256 * Bp;
+    const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
+    {
+        const LevelW& L = c->lvl[l];
+        const LevelGeom g = {Bp, l, DEPTH};
+        const int rows = Bp << l;
+        // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
+        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
+        // prior p(z | e_l, e_r) and reparametrisation
+        const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
+        CHECK(mlp_body(c, st, L.prior, rows, g, par));
+        {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.z = z; e.n_cand = B; e.nz = NZ_VAE;
+            e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
+            e.mu_out = mu_df; e.ls_out = ls_df;
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.prior.mid_k)}, L.prior.head, 256, EPI_REPARAM, e));
+        }
+        if (post != nullptr) {
+            // training phase: z ~ q(z | e_l, e_r, e_tilde), e_tilde = inference encoding of the frame the node is matched
+            // to (tree_module.py:86-95, tree/inference.py:16-36); the sample overwrites the prior's in c->zeta
+            const size_t n = (size_t)rows * 128;
+            gather_etilde_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(post->inf_seq, post->tstep, g, B, MAX_LEN, c->xb.p, HID);
+            LAUNCH_CHECK();
+            CHECK(mlp_body(c, st, L.q, rows, g, {par[0], par[1], seg(c->xb, 0, NZ_ENC)}));
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.z = z; e.n_cand = B; e.nz = NZ_VAE;
+            e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
+            e.mu_out = post->q_mu; e.ls_out = post->q_ls;
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.q.mid_k)}, L.q.head, 256, EPI_REPARAM, e));
+        }
+        const std::vector<Seg> par_z = {par[0], par[1], seg(c->zeta, 0, NZ_VAE)};
+        if (l == 0) {
+            // MLPLSTMCellInitializer: hidden states of the two root parents (slots 0 and 256)
+            CHECK(mlp_body(c, st, L.init, rows, g, par_z));
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 256, EPI_LINEAR,
+                       epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE)));
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 256, EPI_LINEAR,
+                       epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE)));
+        }
+        // split-linear projections of the parents' LSTM state
+        {
+            Seg a = seg(c->hid, 0, HID, ROW_LEFT), b = seg(c->hid, 0, HID, ROW_RIGHT);
+            const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
+            a.group_cols = b.group_cols = HID;
+            for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
+            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
+            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e));
+        }
+        // embed
+        {
+            EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
+            e.rowbias = c->ctxb;
+            e.rowbias_ld = HID;
+            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e));
+        }
+        // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
+        DevBuf* xin = &c->xa;
+        DevBuf* xout = &c->xb;
+        for (int i = 0; i < N_LSTM; ++i) {
+            EpiParams e;
+            memset(&e, 0, sizeof(e));
+            e.c_prev = c->sh.p; e.c_prev_ld = 6 * HID; e.c_prev_col0 = (3 + i) * HID;
+            e.out_bf16 = xout->p; e.out_bf16_ld = HID;
+            e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
+            e.write_hid = (l < DEPTH - 1);
+            CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e));
+            std::swap(xin, xout);
+        }
+        // output linear -> node latent e' (raw, no activation) at the node's slot
+        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF)));
+    }
+
+    return 0;
+}
+
 extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, void* stream) {
     if (!io) {
         gcp_set_error("null io");
@@ -1142,68 +1313,12 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     scope = new ProfScope(c, st, 1);
     // ---- 3. tree recursion, level by level (SubgoalTreeLayer.produce_tree)
     for (int l = 0; l < DEPTH; ++l) {
-        const LevelW& L = c->lvl[l];
-        const LevelGeom g = {Bp, l, DEPTH};
-        const int rows = Bp << l;
         if (io->z_host && (l == 0 || l >= 4)) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_copy[l == 0 ? 0 : l - 3], 0));
-        // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
-        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
-        // prior p(z | e_l, e_r) and reparametrisation
-        const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
-        CHECK(mlp_body(c, st, L.prior, rows, g, par));
-        {
-            EpiParams e;
-            memset(&e, 0, sizeof(e));
-            e.z = io->z; e.n_cand = B; e.nz = NZ_VAE;
-            e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
-            e.mu_out = io->mu_df; e.ls_out = io->log_sigma_df;
-            if ((e.mu_out == nullptr) != (e.ls_out == nullptr)) {
-                gcp_set_error("mu_df and log_sigma_df must be given together");
-                return -1;
-            }
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.prior.mid_k)}, L.prior.head, 256, EPI_REPARAM, e));
+        if ((io->mu_df == nullptr) != (io->log_sigma_df == nullptr)) {
+            gcp_set_error("mu_df and log_sigma_df must be given together");
+            return -1;
         }
-        const std::vector<Seg> par_z = {par[0], par[1], seg(c->zeta, 0, NZ_VAE)};
-        if (l == 0) {
-            // MLPLSTMCellInitializer: hidden states of the two root parents (slots 0 and 256)
-            CHECK(mlp_body(c, st, L.init, rows, g, par_z));
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 256, EPI_LINEAR,
-                       epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE)));
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 256, EPI_LINEAR,
-                       epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE)));
-        }
-        // split-linear projections of the parents' LSTM state
-        {
-            Seg a = seg(c->hid, 0, HID, ROW_LEFT), b = seg(c->hid, 0, HID, ROW_RIGHT);
-            const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
-            a.group_cols = b.group_cols = HID;
-            for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
-            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
-            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e));
-        }
-        // embed
-        {
-            EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
-            e.rowbias = c->ctxb;
-            e.rowbias_ld = HID;
-            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e));
-        }
-        // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
-        DevBuf* xin = &c->xa;
-        DevBuf* xout = &c->xb;
-        for (int i = 0; i < N_LSTM; ++i) {
-            EpiParams e;
-            memset(&e, 0, sizeof(e));
-            e.c_prev = c->sh.p; e.c_prev_ld = 6 * HID; e.c_prev_col0 = (3 + i) * HID;
-            e.out_bf16 = xout->p; e.out_bf16_ld = HID;
-            e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
-            e.write_hid = (l < DEPTH - 1);
-            CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e));
-            std::swap(xin, xout);
-        }
-        // output linear -> node latent e' (raw, no activation) at the node's slot
-        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR,
-                   epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF)));
+        CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr));
     }
 
     delete scope;
@@ -1262,6 +1377,264 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
                                                                            NZ_ENC / 4, seq);
         LAUNCH_CHECK();
         if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, c->end_ind, B, io->actions, io->regressed_state));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Training-phase forward + loss (BASELINE config 1)
+// ---------------------------------------------------------------------------------------------
+static int ensure_train_ws(gcpb200_ctx* c) {
+    gcpb200_ctx::TrainWS& w = c->tw;
+    if (w.Bcap > 0) return 0;
+    const size_t Bc = 128, n_img = Bc * (MAX_LEN + 2), rows = (size_t)N_NODES * Bc;
+    int rc = 0;
+    rc |= dalloc(c, &w.y1, n_img * 2048, false);
+    rc |= dalloc(c, &w.y2, n_img * 1024, false);
+    rc |= dalloc(c, &w.enc_seq, Bc * MAX_LEN * 128);
+    rc |= dalloc(c, &w.h1, Bc * MAX_LEN * 128);
+    rc |= dalloc(c, &w.h2, Bc * MAX_LEN * 128);
+    rc |= dalloc(c, &w.inf_seq, Bc * MAX_LEN * 128);
+    rc |= dalloc(c, &w.stats, 4096);
+    rc |= dalloc(c, &w.tstep, Bc * N_NODES);
+    rc |= dalloc(c, &w.keep, Bc * N_NODES);
+    rc |= make_buf(c, &w.x1, rows, 1024);
+    rc |= make_buf(c, &w.x2, rows, 2048);
+    rc |= make_buf(c, &w.x3, rows, 4096);
+    for (int i = 0; i < 4; ++i) rc |= dalloc(c, &w.pq[i], Bc * N_NODES * NZ_VAE);
+    rc |= dalloc(c, &w.nll_bt, Bc * MAX_LEN);
+    rc |= dalloc(c, &w.kl_b, Bc);
+    rc |= dalloc(c, &w.reg, Bc * MAX_LEN * 2 + 512);
+    rc |= dalloc(c, &w.inv_pred, 128 * 2);
+    rc |= dalloc(c, &w.cost_pred, 128);
+    rc |= dalloc(c, &w.exist_df, Bc * N_NODES);
+    rc |= dalloc(c, &w.cost_tgt, Bc);
+    if (rc) return -1;
+    cudaError_t e = cudaFuncSetAttribute(dec_tail_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES);
+    if (e != cudaSuccess) {
+        gcp_set_error("cudaFuncSetAttribute(dec_tail_nll_kernel) failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    w.Bcap = (int)Bc;
+    return 0;
+}
+
+// One decoder layer's batch-statistic BatchNorm + ReLU, in place on the raw bf16 GEMM output of all 255 * Bp node rows
+static int bn_layer(gcpb200_ctx* c, cudaStream_t st, DevBuf& x, int kind, int B, int Bp, double* stats, int bn_idx, int C,
+                    int spatial) {
+    const int rows = N_NODES * Bp;
+    bn_stats_kernel<<<dim3(x.ld / 256, (rows + 63) / 64), 256, 0, st>>>(x.p, rows, x.ld, Bp, B, kind, stats);
+    LAUNCH_CHECK();
+    const size_t n_vec = (size_t)rows * x.ld / 8;
+    bn_apply_relu_kernel<<<c->sms * 8, 256, 0, st>>>(x.p, n_vec, x.ld, kind, stats, (double)B * N_NODES * spatial, c->bn_g[bn_idx],
+                                                     c->bn_b[bn_idx], C);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, void* stream) {
+    if (!io) {
+        gcp_set_error("null io");
+        return -1;
+    }
+    CHECK(check_ready(c, io->B));
+    if (c->model != GCPB200_MODEL_TREE || !c->has_train || !c->has_cost || !c->has_inv || !c->has_state) {
+        gcp_set_error("gcpb200_forward_loss needs a GCPB200_MODEL_TREE context with attach_cost_mdl = 1 and a state dict that "
+                      "holds the training tensors (inf_encoder.*, inference.q.*, inv_mdl.*, state_regressor.*, cost_mdl.*)");
+        return -1;
+    }
+    if (io->B > 128) {
+        gcp_set_error("gcpb200_forward_loss: B = %d > 128 sequences per call", io->B);
+        return -1;
+    }
+    if (!io->traj_seq || !io->pad_mask || !io->end_ind || !io->I_0 || !io->I_g || !io->states || !io->actions || !io->eps ||
+        !io->inv_t0 || !io->inv_t1 || !io->cost_start || !io->cost_end || !io->losses) {
+        gcp_set_error("gcpb200_forward_loss: every input pointer except cost_target, and `losses`, are required");
+        return -1;
+    }
+    CHECK(ensure_train_ws(c));
+    gcpb200_ctx::TrainWS& w = c->tw;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int B = io->B, Bp = 128, T = MAX_LEN;
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    const int goal_row0 = 256 * Bp;
+    double* st1 = w.stats;                 // [3][32][2]
+    double* st2 = st1 + 3 * 32 * 2;        // [3][64][2]
+    double* gn = st2 + 3 * 64 * 2;         // [128][8][2]
+    double* sd1 = gn + 128 * 8 * 2;        // [64][2]
+    double* sd2 = sd1 + 64 * 2;            // [64][2] (32 used)
+    double* sd3 = sd2 + 64 * 2;            // [64][2] (16 used)
+    GCP_CUDA_CHECK(cudaMemsetAsync(w.stats, 0, 4096 * sizeof(double), st));
+    GCP_CUDA_CHECK(cudaMemcpyAsync(c->end_ind, io->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+
+    // ---- 1. encoders with batch statistics: all frames, start images, goal images (base_gcp.py:184-209)
+    {
+        EncTrainArgs a;
+        memset(&a, 0, sizeof(a));
+        a.img[0] = io->traj_seq; a.img[1] = io->I_0; a.img[2] = io->I_g;
+        a.n[0] = B * T; a.n[1] = B; a.n[2] = B;
+        a.W = c->enc;
+        a.g1 = c->bn_g[0]; a.b1 = c->bn_b[0]; a.g2 = c->bn_g[1]; a.b2 = c->bn_b[1];
+        a.y1 = w.y1; a.y2 = w.y2; a.st1 = st1; a.st2 = st2;
+        a.enc_seq = w.enc_seq; a.lat_f32 = c->lat_f32; a.lat_bf16 = c->lat.p; a.row0_a = 0; a.row0_b = goal_row0;
+        a.skip0 = c->s0; a.skip2 = c->s2; a.skip2_bf16 = c->s2b.p;
+        const int n_img = B * (T + 2);
+        enc_train_a_kernel<<<n_img, 256, 0, st>>>(a);
+        LAUNCH_CHECK();
+        enc_train_b_kernel<<<n_img, 256, 0, st>>>(a);
+        LAUNCH_CHECK();
+        enc_train_c_kernel<<<n_img, 256, 0, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    if (io->e_0) GCP_CUDA_CHECK(cudaMemcpyAsync(io->e_0, c->lat_f32, (size_t)B * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));
+    if (io->e_g)
+        GCP_CUDA_CHECK(cudaMemcpyAsync(io->e_g, c->lat_f32 + (size_t)goal_row0 * NZ_ENC, (size_t)B * NZ_ENC * 4,
+                                       cudaMemcpyDeviceToDevice, st));
+    if (io->enc_traj_seq)
+        GCP_CUDA_CHECK(cudaMemcpyAsync(io->enc_traj_seq, w.enc_seq, (size_t)B * T * 128 * 4, cudaMemcpyDeviceToDevice, st));
+    // ---- 2. inference encoder: three conv1d over time (subnetworks.py:120-147)
+    {
+        const dim3 grid((T + 7) / 8, B);
+        conv1d_k3_kernel<<<grid, 128, 0, st>>>(w.enc_seq, 128, 1, c->ie_w[0], c->ie_b[0], nullptr, nullptr, nullptr, ACT_LRELU, w.h1,
+                                               nullptr, T);
+        LAUNCH_CHECK();
+        conv1d_k3_kernel<<<grid, 128, 0, st>>>(w.h1, 128, 0, c->ie_w[1], nullptr, nullptr, nullptr, nullptr, ACT_NONE, w.h2, gn, T);
+        LAUNCH_CHECK();
+        conv1d_k3_kernel<<<grid, 128, 0, st>>>(w.h2, 128, 0, c->ie_w[2], c->ie_b[2], gn, c->ie_gn_g, c->ie_gn_b, ACT_NONE, w.inf_seq,
+                                               nullptr, T);
+        LAUNCH_CHECK();
+    }
+    if (io->inf_enc_seq)
+        GCP_CUDA_CHECK(cudaMemcpyAsync(io->inf_enc_seq, w.inf_seq, (size_t)B * T * 128 * 4, cudaMemcpyDeviceToDevice, st));
+    // ---- 3. length predictor logits (misc.py:38-51)
+    {
+        const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
+        CHECK(mlp_body(c, st, c->length_pred, Bp, flat, ctx_in));
+        CHECK(gemm(c, st, Bp, flat, {seg(c->tb, 0, c->length_pred.mid_k)}, c->length_pred.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->logits, 256, MAX_LEN)));
+        if (io->seq_len_logits)
+            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->seq_len_logits, MAX_LEN * 4, c->logits, 256 * 4, MAX_LEN * 4, B,
+                                             cudaMemcpyDeviceToDevice, st));
+    }
+    // ---- 4. frame <-> node matching (integer)
+    GCP_CUDA_CHECK(cudaMemsetAsync(c->frame_node, 0, (size_t)B * MAX_LEN * sizeof(int), st));
+    match_tables_kernel<<<(B * N_NODES + 255) / 256, 256, 0, st>>>(c->end_ind, B, DEPTH, MAX_LEN, c->frame_node, w.tstep, w.keep);
+    LAUNCH_CHECK();
+    if (io->match_timesteps)
+        GCP_CUDA_CHECK(cudaMemcpyAsync(io->match_timesteps, w.tstep, (size_t)B * N_NODES * 4, cudaMemcpyDeviceToDevice, st));
+    // ---- 5. tree with the approximate posterior
+    float* p_mu = io->p_mu ? io->p_mu : w.pq[0];
+    float* p_ls = io->p_log_sigma ? io->p_log_sigma : w.pq[1];
+    float* q_mu = io->q_mu ? io->q_mu : w.pq[2];
+    float* q_ls = io->q_log_sigma ? io->q_log_sigma : w.pq[3];
+    {
+        PosteriorArgs post = {w.inf_seq, w.tstep, q_mu, q_ls};
+        for (int l = 0; l < DEPTH; ++l) CHECK(tree_level(c, st, l, B, Bp, io->eps, p_mu, p_ls, &post));
+    }
+    float* e_df = io->e_df ? io->e_df : c->e_df;
+    {
+        const size_t n = (size_t)B * N_NODES * NZ_ENC;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, Bp, B, N_NODES, NZ_ENC, NZ_ENC, e_df);
+        LAUNCH_CHECK();
+    }
+    float* exist = io->existence ? io->existence : w.exist_df;
+    {
+        const int rows = N_NODES * Bp;
+        CHECK(mlp_body(c, st, c->existence, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, Bp)}));
+        CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->existence.mid_k)}, c->existence.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->exist_slot + Bp, 1, 1)));
+        const size_t n = (size_t)B * N_NODES;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->exist_slot, Bp, B, N_NODES, 1, 1, exist);
+        LAUNCH_CHECK();
+    }
+    // ---- 6. decoder over all nodes, BatchNorm with the statistics of this batch (tree_dense_rec.py:41-44)
+    {
+        const int rows = N_NODES * Bp;
+        skip_prep_kernel<<<B, 256, 0, st>>>(c->s0, c->skip_up, B);
+        LAUNCH_CHECK();
+        CHECK(gemm(c, st, Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2st, 256, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
+        CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, Bp)}, c->dec1t, 256, EPI_LINEAR,
+                   epi_linear(ACT_NONE, w.x1.p, 1024, nullptr, 0, 1024)));
+        CHECK(bn_layer(c, st, w.x1, 1, B, Bp, sd1, 2, 64, 16));
+        {
+            EpiParams e = epi_linear(ACT_NONE, w.x2.p, 2048, nullptr, 0, 2048);
+            e.rowbias = c->rowbias2;
+            e.rowbias_ld = 2048;
+            CHECK(gemm(c, st, rows, flat, {seg(w.x1, 0, 1024)}, c->dec2xt, 256, EPI_LINEAR, e));
+        }
+        CHECK(bn_layer(c, st, w.x2, 2, B, Bp, sd2, 3, 32, 64));
+        {
+            Seg a3 = seg(w.x2, 0, 1024);
+            a3.group_cols = 256;
+            for (int q = 0; q < 16; ++q) a3.group_col[q] = dec3_window_row0(q & 7) * 256;
+            CHECK(gemm(c, st, rows, flat, {a3}, c->dec3t, 256, EPI_LINEAR, epi_linear(ACT_NONE, w.x3.p, 4096, nullptr, 0, 4096)));
+        }
+        CHECK(bn_layer(c, st, w.x3, 3, B, Bp, sd3, 4, 16, 256));
+        if (io->images_df) {
+            // DLM mean image of every node with the rollout's tcgen05 tail kernel (tree.df.images; logging only)
+            skip_term3_kernel<<<dim3(8, B), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
+            LAUNCH_CHECK();
+            DecTail3Args a;
+            memset(&a, 0, sizeof(a));
+            a.x3 = w.x3.p; a.s4 = c->s4; a.s4_stride = 256 * 64;
+            a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
+            a.images = io->images_df; a.Bp = Bp; a.n_cand = B; a.slot0 = 1; a.n_slots = N_NODES; a.n_nodes = N_NODES;
+            const long long n_img = (long long)B * N_NODES;
+            dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+            LAUNCH_CHECK();
+        }
+    }
+    // ---- 7. matched latents + auxiliary heads (base_gcp.py:234-262,361-374)
+    float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
+    {
+        const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
+        gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
+                                                                           NZ_ENC / 4, seq);
+        LAUNCH_CHECK();
+        float* reg = io->regressed_state ? io->regressed_state : w.reg;
+        CHECK(run_pair_heads(c, st, seq, c->end_ind, B, nullptr, reg));
+        train_pairs_kernel<<<256, 256, 0, st>>>(w.enc_seq, seq, (const long long*)io->inv_t0, (const long long*)io->inv_t1,
+                                                (const long long*)io->cost_start, (const long long*)io->cost_end, B, T, c->pairs.p);
+        LAUNCH_CHECK();
+        CHECK(mlp_body(c, st, c->inv_mdl, 128, flat, {seg(c->pairs, 0, 256, ROW_LEVEL, 0)}));
+        CHECK(gemm(c, st, 128, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, w.inv_pred, 2, 2)));
+        CHECK(mlp_body(c, st, c->cost_mdl, 128, flat, {seg(c->pairs, 0, 256, ROW_LEVEL, 128)}));
+        CHECK(gemm(c, st, 128, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
+                   epi_linear(ACT_NONE, nullptr, 0, w.cost_pred, 1, 1)));
+        if (io->inv_actions) GCP_CUDA_CHECK(cudaMemcpyAsync(io->inv_actions, w.inv_pred, (size_t)B * 2 * 4, cudaMemcpyDeviceToDevice, st));
+        if (io->cost_pred) GCP_CUDA_CHECK(cudaMemcpyAsync(io->cost_pred, w.cost_pred, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+        // ---- 8. reconstruction NLL of every real frame under the node bound to it, KL, scalar losses
+        float* nll_bt = io->nll_per_frame ? io->nll_per_frame : w.nll_bt;
+        TailNllArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.x3 = w.x3.p; ta.skip_up = c->skip_up; ta.w4p = c->w4p; ta.w5p = c->w5p; ta.b4 = c->b4; ta.b5 = c->b5;
+        ta.traj = io->traj_seq; ta.pad_mask = io->pad_mask; ta.end_ind = c->end_ind; ta.frame_node = c->frame_node;
+        ta.Bp = Bp; ta.T = T; ta.lcap = MAX_LEN; ta.root_node = (1 << (DEPTH - 1)) - 1; ta.nll_bt = nll_bt;
+        dec_tail_nll_kernel<<<B * T, 256, TN_SMEM_BYTES, st>>>(ta);
+        LAUNCH_CHECK();
+        float* kl_b = io->kl_per_seq ? io->kl_per_seq : w.kl_b;
+        kl_seq_kernel<<<B, 256, 0, st>>>(q_mu, q_ls, p_mu, p_ls, N_NODES * NZ_VAE, kl_b);
+        LAUNCH_CHECK();
+        LossArgs la;
+        memset(&la, 0, sizeof(la));
+        la.B = B; la.T = T; la.n_nodes = N_NODES;
+        la.logits = c->logits; la.logits_ld = 256; la.end_ind = c->end_ind;
+        la.nll_bt = nll_bt; la.kl_b = kl_b; la.existence = exist; la.keep = w.keep;
+        la.reg = reg; la.states = io->states; la.pad_mask = io->pad_mask;
+        la.inv_pred = w.inv_pred; la.actions = io->actions; la.inv_t0 = (const long long*)io->inv_t0;
+        la.cost_pred = w.cost_pred; la.cost_target = io->cost_target;
+        if (!io->cost_target) {
+            path_length_kernel<<<B, 256, 0, st>>>(io->traj_seq, (const long long*)io->cost_start, (const long long*)io->cost_end, T,
+                                                  w.cost_tgt);
+            LAUNCH_CHECK();
+            la.cost_target = w.cost_tgt;
+        }
+        la.frame_elems = (double)T * 3072.0;
+        la.losses = io->losses;
+        loss_finalize_kernel<<<1, 256, 0, st>>>(la);
+        LAUNCH_CHECK();
     }
     return 0;
 }

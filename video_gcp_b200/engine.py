@@ -309,6 +309,53 @@ class Engine:
                                                        _stream()))
         return z
 
+    # ------------------------------------------------------------------------------------------
+    def forward_loss(self, traj_seq, pad_mask, end_ind, states, actions, eps, inv_t0, inv_t1, cost_start, cost_end,
+                     cost_target=None, I_0=None, I_g=None, want=("nll_per_frame", "kl_per_seq")):
+        """Training-phase forward + loss (gcpb200_forward_loss; reference: `model(inputs)` + `model.loss` +
+        `model.get_total_loss` in .train() mode, gcp/prediction/train.py:155-157,204-206).  Device tensors in; returns a
+        dict with `losses` ([9] device tensor, order _C.LOSS_NAMES) and the optional outputs named in `want`
+        (any field of gcpb200_train_io).  cost_target None: EuclideanPathLength of the ground-truth frames, on the device."""
+        dev = self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        i64 = dict(device=dev, dtype=torch.int64)
+        B, T = traj_seq.shape[:2]
+        assert T == MAX_LEN and tuple(traj_seq.shape[2:]) == (3, 32, 32)
+        traj_seq = traj_seq.to(**f32).contiguous()
+        end_ind = torch.as_tensor(end_ind).to(**i64).contiguous()
+        if I_0 is None:
+            I_0 = traj_seq[:, 0]
+        if I_g is None:
+            I_g = traj_seq[torch.arange(B, device=dev), end_ind]
+        ins = dict(traj_seq=traj_seq, pad_mask=pad_mask.to(**f32).contiguous(), end_ind=end_ind,
+                   I_0=I_0.to(**f32).contiguous(), I_g=I_g.to(**f32).contiguous(), states=states.to(**f32).contiguous(),
+                   actions=actions.to(**f32).contiguous(), eps=eps.to(**f32).contiguous(),
+                   inv_t0=torch.as_tensor(inv_t0).to(**i64).contiguous(), inv_t1=torch.as_tensor(inv_t1).to(**i64).contiguous(),
+                   cost_start=torch.as_tensor(cost_start).to(**i64).contiguous(),
+                   cost_end=torch.as_tensor(cost_end).to(**i64).contiguous(),
+                   cost_target=None if cost_target is None else torch.as_tensor(cost_target).to(**f32).reshape(-1).contiguous())
+        assert tuple(ins["eps"].shape) == (B, N_NODES, NZ_VAE)
+        assert ins["cost_target"] is None or ins["cost_target"].numel() == B
+        shapes = dict(nll_per_frame=(B, T), kl_per_seq=(B,), e_0=(B, NZ_ENC), e_g=(B, NZ_ENC), enc_traj_seq=(B, T, NZ_ENC),
+                      inf_enc_seq=(B, T, NZ_ENC), seq_len_logits=(B, T), e_df=(B, N_NODES, NZ_ENC),
+                      p_mu=(B, N_NODES, NZ_VAE), p_log_sigma=(B, N_NODES, NZ_VAE), q_mu=(B, N_NODES, NZ_VAE),
+                      q_log_sigma=(B, N_NODES, NZ_VAE), match_timesteps=(B, N_NODES), images_df=(B, N_NODES, 3, 32, 32),
+                      existence=(B, N_NODES), model_enc_seq=(B, T, NZ_ENC), regressed_state=(B, T, 2), inv_actions=(B, 2),
+                      cost_pred=(B,))
+        out = dict(losses=self._buf("train_losses", (len(_C.LOSS_NAMES),)))
+        for name in want:
+            out[name] = self._buf("train_" + name, shapes[name], torch.int32 if name == "match_timesteps" else torch.float32)
+        io = _C.TrainIO()
+        for k, v in ins.items():
+            setattr(io, k, _ptr(v))
+        io.B = B
+        for k, v in out.items():
+            setattr(io, k, _ptr(v))
+        self._train_refs = ins            # keep inputs alive until the (stream-ordered) call has run
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_forward_loss(self.h, C.byref(io), _stream()))
+        return out
+
     def launch_count(self):
         return int(self.lib.gcpb200_launch_count(self.h))
 
