@@ -11,6 +11,8 @@ function below against them.
 
 A plain torch-fp32 functional restatement; paths cite /root/reference.
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -20,6 +22,21 @@ from .gcp_oracle import (BN_EPS, DEPTH, GN_EPS, LRELU, N_NODES, _up_pad_conv, ba
 
 LOSS_NAMES = ("len_pred", "action_reconst", "cost_estimation", "state_regression", "dense_img_rec", "kl",
               "existence_predictor", "entropy", "total")
+
+
+@contextlib.contextmanager
+def bf16_operands():
+    """Error-envelope aid for the GPU parity tests: inside this context every F.linear of the oracle rounds its two
+    operands to bf16 (fp32 accumulation, fp32 bias), which is the arithmetic of the device's tensor-core GEMMs.  Running
+    the tree with and without it shows how much of a device-vs-fp32 difference is operand rounding amplified by the
+    network (random-init posteriors reach sigma = 17.8, and z = mu + sigma * eps multiplies log-sigma errors by that)."""
+    lin = F.linear
+    r = lambda t: t.bfloat16().float()
+    F.linear = lambda x, w, b=None: lin(r(x), r(w), b)
+    try:
+        yield
+    finally:
+        F.linear = lin
 
 
 def _bn_train(sd, name, x):
