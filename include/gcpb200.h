@@ -23,6 +23,8 @@
  *                          TreeModel.loss and get_total_loss, as train.py:155-157 / :204-206 call them
  *                          (gcp/prediction/models/base_gcp.py:140-304; tree/tree.py:42-79; tree/tree_module.py:67-157;
  *                           tree/inference.py:16-41; tree/frame_binding.py:42-100)
+ *   gcpb200_cdist_mean / gcpb200_soft_dtw / gcpb200_dtw / gcpb200_gather_rows
+ *                          the DTW family: AdaptiveBinding.get_w and DTWEvalBinding.get_single_matches (declared at the end)
  *   gcpb200_topk           CEMPlanner._get_best_rollouts argsort + slice (gcp/planning/cem/cem_planner.py:124-135)
  *   gcpb200_refit          FlatCEMSampler.fit (gcp/planning/cem/sampler.py:44-46)
  *   gcpb200_sample_noise   FlatCEMSampler.sample (gcp/planning/cem/sampler.py:40-42), on device
@@ -36,6 +38,7 @@
 #ifndef GCPB200_H
 #define GCPB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -277,6 +280,42 @@ int64_t gcpb200_launch_count(gcpb200_ctx* ctx);
 int gcpb200_profile_enable(gcpb200_ctx* ctx, int on);
 int gcpb200_profile_read(gcpb200_ctx* ctx, double* ms /* [GCPB200_N_PHASES] */, int64_t* tail_images,
                          int64_t* tail_launches);
+
+/* ---- DTW family.  No weights involved: any context of the device will do. ------------------------------
+ *
+ * gcpb200_cdist_mean   blox.torch.ops.batch_cdist(x, y, reduction='mean') (blox/torch/ops.py:62-91): the cost matrix of
+ *                      AdaptiveBinding.get_w (gcp/prediction/models/adaptive_binding/adaptive.py:41-47) and of
+ *                      DTWEvalBinding.get_single_matches (gcp/evaluation/evaluation_matching.py:138).
+ *                      x [B,n,dim], y [B,m,dim] -> out [B,n,m] = mean_d (x - y)^2, fp32 (dim % 4 == 0, 16-byte aligned).
+ * gcpb200_soft_dtw     soft_dtw(cost / temp, end_inds) (probabilistic_dtw.py:11-121; adaptive.py:51): float64 forward-backward
+ *                      of the 'nohor' alignment.  cost [B,r,c] fp32 (r nodes >= c frames), end_inds [B] int64 or NULL (= c-1).
+ *                      workspace: gcpb200_soft_dtw_workspace(B,r,c) bytes; on return it holds the forward table [B,r,c] then
+ *                      the backward table [B,r,c] (float64, un-flipped coordinates).
+ *                      w [B,r,c]: expected edge frequencies (the function's return value).
+ *                      w_bf [B,r,c] or NULL: depthfirst2breadthfirst(normalize(w, 1)) = AdaptiveBinding.get_w's result
+ *                      (adaptive.py:53-61; blox/torch/dist.py:22-24; gcp/prediction/utils/tree_utils.py:217-232), r = 2^d - 1.
+ *                      rowsum_max [1] or NULL: max over (b, node) of sum_t w -- the reference warns and stops when this is
+ *                      not within 1e-2 of 1 (probabilistic_dtw.py:115-117); the caller decides.
+ * gcpb200_dtw          c_dtw / basic_dtw / batched_dtw (gcp/evaluation/dtw_utils.py:77-130; gcp/evaluation/cutils.pyx:21-28)
+ *                      with _traceback / _batched_traceback (dtw_utils.py:201-241) and the per-frame best match of
+ *                      get_single_matches (evaluation_matching.py:142-146).  cost [B,r,c] fp32 (cost_is_f64 = 0) or float64;
+ *                      end_ind [B] int64 or NULL: column the path starts from (c-1).
+ *                      acc [B,r+1,c+1] float64: the padded accumulated-cost table; dist [B] = acc[r][end+1] / (r+end+1);
+ *                      path_p / path_q [B, r+c-1] int32: the warping path in start -> end order, RIGHT-aligned, the unused
+ *                      leading slots hold (0,0) (as _batched_traceback pads); path_len [B];
+ *                      match_inds [B,c] int32 or NULL: for every column the path row with the smallest accumulated cost
+ *                      (first minimum; 0 for columns the path does not visit).
+ * gcpb200_gather_rows  out[k] = src[idx[k]] for rows of row_floats floats (gen_images = estimates[inds],
+ *                      evaluation_matching.py:147).
+ */
+int gcpb200_cdist_mean(gcpb200_ctx* ctx, const float* x, const float* y, int B, int n, int m, int dim, float* out, void* stream);
+size_t gcpb200_soft_dtw_workspace(int B, int r, int c);
+int gcpb200_soft_dtw(gcpb200_ctx* ctx, const float* cost, float temp, const int64_t* end_inds, int B, int r, int c,
+                     void* workspace, float* w, float* w_bf, float* rowsum_max, void* stream);
+int gcpb200_dtw(gcpb200_ctx* ctx, const void* cost, int cost_is_f64, const int64_t* end_ind, int B, int r, int c, double* acc,
+                double* dist, int32_t* path_p, int32_t* path_q, int32_t* path_len, int32_t* match_inds, void* stream);
+int gcpb200_gather_rows(gcpb200_ctx* ctx, const float* src, const int32_t* idx, int n_out, int row_floats, float* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

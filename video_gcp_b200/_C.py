@@ -84,6 +84,14 @@ EXPORTS = {
                                        C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "gcpb200_sample_noise_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
                                            C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "gcpb200_cdist_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "gcpb200_soft_dtw_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gcpb200_soft_dtw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gcpb200_dtw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gcpb200_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gcpb200_launch_count": (C.c_int64, [C.c_void_p]),
     "gcpb200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gcpb200_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <string>
@@ -11,6 +12,7 @@
 
 #include "../../include/gcpb200.h"
 #include "dec_tail3.cuh"
+#include "dtw_kernels.cuh"
 #include "gemm_host.cuh"
 #include "kernels_misc.cuh"
 #include "train_kernels.cuh"
@@ -2008,6 +2010,114 @@ extern "C" int gcpb200_sample_noise_ids(gcpb200_ctx* c, const float* mean, const
     const size_t n = (size_t)B * (per / 4);
     sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mean, stdv, std_scalar, seed, 0ULL, ids, B, per, clip, z);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DTW family: no weights involved, so these only need a context (device + launch accounting)
+// ---------------------------------------------------------------------------------------------
+extern "C" int gcpb200_cdist_mean(gcpb200_ctx* c, const float* x, const float* y, int B, int n, int m, int dim, float* out,
+                                  void* stream) {
+    if (!c || !x || !y || !out || B <= 0 || n <= 0 || m <= 0 || dim <= 0 || B > 65535) {
+        gcp_set_error("gcpb200_cdist_mean: bad arguments (B=%d n=%d m=%d dim=%d)", B, n, m, dim);
+        return -1;
+    }
+    if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 != 0) {
+        gcp_set_error("gcpb200_cdist_mean: vectors must be 16-byte aligned with a length that is a multiple of 4 (dim=%d)", dim);
+        return -1;
+    }
+    dim3 grid((m + CD_T - 1) / CD_T, (n + CD_T - 1) / CD_T, B);
+    cdist_mean_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n, m, dim, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t gcpb200_soft_dtw_workspace(int B, int r, int c) {
+    return (B <= 0 || r <= 0 || c <= 0) ? 0 : (size_t)2 * B * r * c * sizeof(double);
+}
+
+extern "C" int gcpb200_soft_dtw(gcpb200_ctx* c, const float* cost, float temp, const int64_t* end_inds, int B, int r, int cols,
+                                void* workspace, float* w, float* w_bf, float* rowsum_max, void* stream) {
+    if (!c || !cost || !workspace || !w || B <= 0 || r <= 0 || cols <= 0 || B > 32767) {
+        gcp_set_error("gcpb200_soft_dtw: bad arguments (B=%d r=%d c=%d)", B, r, cols);
+        return -1;
+    }
+    if (r < cols) {      // probabilistic_dtw.py:35 `assert r >= c`
+        gcp_set_error("gcpb200_soft_dtw: needs at least as many nodes as frames (r=%d < c=%d)", r, cols);
+        return -1;
+    }
+    if (cols > 3072) {
+        gcp_set_error("gcpb200_soft_dtw: c=%d > 3072 frames", cols);
+        return -1;
+    }
+    if (!(temp != 0.f)) {
+        gcp_set_error("gcpb200_soft_dtw: temperature must be non-zero");
+        return -1;
+    }
+    int depth = 0;
+    if (w_bf) {
+        while ((1 << depth) - 1 < r) ++depth;
+        if ((1 << depth) - 1 != r) {
+            gcp_set_error("gcpb200_soft_dtw: breadth-first output needs r = 2^d - 1 tree nodes (r=%d)", r);
+            return -1;
+        }
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long* ei = reinterpret_cast<const long long*>(end_inds);
+    double* accum = reinterpret_cast<double*>(workspace);
+    const int threads = std::min(1024, (cols + 31) / 32 * 32);
+    soft_dtw_sweep_kernel<<<2 * B, threads, 2 * cols * sizeof(double), st>>>(cost, temp, ei, B, r, cols, accum);
+    LAUNCH_CHECK();
+    const size_t n = (size_t)B * r * cols;
+    soft_dtw_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cost, temp, ei, accum, B, r, cols, w);
+    LAUNCH_CHECK();
+    if (rowsum_max) {
+        GCP_CUDA_CHECK(cudaMemsetAsync(rowsum_max, 0, sizeof(float), st));
+        soft_dtw_rowsum_max_kernel<<<(B * r + 7) / 8, 256, 0, st>>>(w, B * r, cols, rowsum_max);
+        LAUNCH_CHECK();
+    }
+    if (w_bf) {
+        binding_normalize_kernel<<<dim3((cols + 127) / 128, B), 128, 0, st>>>(w, B, r, cols, depth, 1e-7f, w_bf);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int gcpb200_dtw(gcpb200_ctx* c, const void* cost, int cost_is_f64, const int64_t* end_ind, int B, int r, int cols,
+                           double* acc, double* dist, int32_t* path_p, int32_t* path_q, int32_t* path_len, int32_t* match_inds,
+                           void* stream) {
+    if (!c || !cost || !acc || !dist || !path_p || !path_q || !path_len || B <= 0 || r <= 0 || cols <= 0) {
+        gcp_set_error("gcpb200_dtw: bad arguments (B=%d r=%d c=%d)", B, r, cols);
+        return -1;
+    }
+    if (r > 2048) {
+        gcp_set_error("gcpb200_dtw: r=%d > 2048 rows", r);
+        return -1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long* ei = reinterpret_cast<const long long*>(end_ind);
+    const int threads = std::min(1024, (std::min(r, cols) + 31) / 32 * 32);
+    const size_t smem = (size_t)3 * r * sizeof(double);
+    if (cost_is_f64)
+        dtw_wavefront_kernel<double><<<B, threads, smem, st>>>(reinterpret_cast<const double*>(cost), ei, r, cols, acc, dist,
+                                                                path_p, path_q, path_len, match_inds);
+    else
+        dtw_wavefront_kernel<float><<<B, threads, smem, st>>>(reinterpret_cast<const float*>(cost), ei, r, cols, acc, dist,
+                                                               path_p, path_q, path_len, match_inds);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_gather_rows(gcpb200_ctx* c, const float* src, const int32_t* idx, int n_out, int row_floats, float* out,
+                                   void* stream) {
+    if (!c || !src || !idx || !out || n_out <= 0 || row_floats <= 0 || row_floats % 4 != 0) {
+        gcp_set_error("gcpb200_gather_rows: bad arguments (rows must be a multiple of 4 floats)");
+        return -1;
+    }
+    const size_t n = (size_t)n_out * (row_floats / 4);
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(src), idx, n_out, row_floats / 4, reinterpret_cast<float4*>(out));
     LAUNCH_CHECK();
     return 0;
 }

@@ -356,6 +356,71 @@ class Engine:
             _C.check(self.lib.gcpb200_forward_loss(self.h, C.byref(io), _stream()))
         return out
 
+    # ------------------------------------------------------------------------------------------
+    # DTW family.  Device tensors in / out; outputs are persistent buffers (valid until the next call).
+    def cdist_mean(self, x, y):
+        """batch_cdist(x, y, reduction='mean') (blox/torch/ops.py:62-91).  x [B,n,...], y [B,m,...] -> [B,n,m]."""
+        x = x.to(self.device, torch.float32).flatten(2).contiguous()
+        y = y.to(self.device, torch.float32).flatten(2).contiguous()
+        B, n, dim = x.shape
+        assert y.shape[0] == B and y.shape[2] == dim, (x.shape, y.shape)
+        out = self._buf("cdist", (B, n, y.shape[1]))
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_cdist_mean(self.h, _ptr(x), _ptr(y), B, n, y.shape[1], dim, _ptr(out), _stream()))
+        self._dtw_refs = (x, y)
+        return out
+
+    def soft_dtw(self, cost, temp=1.0, end_inds=None, want_bf=False, want_tables=False):
+        """soft_dtw(cost / temp, end_inds) (probabilistic_dtw.py:82-121).  Returns dict(w [B,r,c], rowsum_max [1],
+        optionally w_bf = depthfirst2breadthfirst(normalize(w, 1)) and the float64 forward / backward tables)."""
+        cost = cost.to(self.device, torch.float32).contiguous()
+        B, r, c = cost.shape
+        ei = None if end_inds is None else torch.as_tensor(end_inds).to(self.device, torch.int64).contiguous()
+        assert ei is None or tuple(ei.shape) == (B,)
+        ws = self._buf("soft_dtw_ws", (2, B, r, c), torch.float64)
+        assert ws.numel() * 8 == self.lib.gcpb200_soft_dtw_workspace(B, r, c)
+        out = dict(w=self._buf("soft_dtw_w", (B, r, c)), rowsum_max=self._buf("soft_dtw_rowsum", (1,)))
+        if want_bf:
+            out["w_bf"] = self._buf("soft_dtw_w_bf", (B, r, c))
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_soft_dtw(self.h, _ptr(cost), float(temp), _ptr(ei), B, r, c, _ptr(ws), _ptr(out["w"]),
+                                               _ptr(out.get("w_bf")), _ptr(out["rowsum_max"]), _stream()))
+        self._dtw_refs = (cost, ei)
+        if want_tables:
+            out["forward"], out["backward"] = ws[0], ws[1]
+        return out
+
+    def dtw(self, cost, end_ind=None, want_matches=True):
+        """c_dtw / batched_dtw (gcp/evaluation/dtw_utils.py:77-130,201-241).  cost [B,r,c] fp32 or float64.  Returns
+        dict(acc [B,r+1,c+1] f64 padded table, dist [B], path_p / path_q [B,r+c-1] right-aligned, path_len [B],
+        match_inds [B,c])."""
+        f64 = cost.dtype == torch.float64
+        cost = cost.to(self.device, torch.float64 if f64 else torch.float32).contiguous()
+        B, r, c = cost.shape
+        ei = None if end_ind is None else torch.as_tensor(end_ind).to(self.device, torch.int64).contiguous()
+        i32 = torch.int32
+        out = dict(acc=self._buf("dtw_acc", (B, r + 1, c + 1), torch.float64), dist=self._buf("dtw_dist", (B,), torch.float64),
+                   path_p=self._buf("dtw_p", (B, r + c - 1), i32), path_q=self._buf("dtw_q", (B, r + c - 1), i32),
+                   path_len=self._buf("dtw_len", (B,), i32))
+        if want_matches:
+            out["match_inds"] = self._buf("dtw_match", (B, c), i32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_dtw(self.h, _ptr(cost), int(f64), _ptr(ei), B, r, c, _ptr(out["acc"]), _ptr(out["dist"]),
+                                          _ptr(out["path_p"]), _ptr(out["path_q"]), _ptr(out["path_len"]),
+                                          _ptr(out.get("match_inds")), _stream()))
+        self._dtw_refs = (cost, ei)
+        return out
+
+    def gather_rows(self, src, idx):
+        """src[idx] for a device int32 index vector (rows of a multiple of 4 floats)."""
+        src = src.to(self.device, torch.float32).contiguous()
+        idx = idx.to(self.device, torch.int32).contiguous()
+        row = src[0].numel()
+        out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _C.check(self.lib.gcpb200_gather_rows(self.h, _ptr(src), _ptr(idx), idx.shape[0], row, _ptr(out), _stream()))
+        return out
+
     def launch_count(self):
         return int(self.lib.gcpb200_launch_count(self.h))
 
