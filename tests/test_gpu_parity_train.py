@@ -218,3 +218,45 @@ def test_rejects_bad_arguments(engine, dev):
     with pytest.raises(AssertionError):
         engine.forward_loss(batch["traj_seq"][:, :100].to(dev), batch["pad_mask"].to(dev), batch["end_ind"].to(dev),
                             batch["states"].to(dev), batch["actions"].to(dev), batch["eps"].to(dev), z, z, z, z)
+
+
+def test_model_drop_in_train_forward_and_loss(dev, sd, golden_dir):
+    """The module-level API train.py calls (train.py:155-157 and its validation pass :204-206): `model(inputs)` outside
+    val_mode, `model.loss`, `model.get_total_loss`.  With np.random seeded like the reference run the model draws the
+    same auxiliary pairs; with the fixture's posterior noise every loss must equal the unmodified reference's."""
+    from video_gcp_b200 import hparams
+    from video_gcp_b200.model import TreeModel
+    from video_gcp_b200.types import AttrDict
+    g = np.load(os.path.join(golden_dir, "train_losses_B16.npz"))
+    batch = synthetic_train_batch(16, seed=int(g["batch_seed"]))
+    model = TreeModel(hparams.gcp_tree_25room_config(batch_size=16, attach_cost_mdl=True), None, max_candidates=128)
+    model.load_state_dict(sd, strict=True)
+    model.device = dev
+    model.train()
+    d = lambda t: t.to(dev)
+    inputs = AttrDict(traj_seq=d(batch["traj_seq"]), traj_seq_images=d(batch["traj_seq"]), pad_mask=d(batch["pad_mask"]),
+                      end_ind=d(batch["end_ind"]), traj_seq_states=d(batch["states"]), actions=d(batch["actions"]),
+                      I_0=d(batch["I_0"]), I_g=d(batch["I_g"]), eps=d(batch["eps"]))
+    np.random.seed(int(g["np_seed"]))
+    out = model(inputs)
+    losses = model.loss(inputs, out)
+    losses.total = model.get_total_loss(inputs, losses)
+    torch.cuda.synchronize()
+    for k in ("inv_t0", "inv_t1", "cost_start", "cost_end"):
+        np.testing.assert_array_equal(out.aux_indices[k], g[k])
+    ref = dict(zip([str(n) for n in g["loss_names"]], g["loss_values"]))
+    assert set(losses.keys()) == set(ref.keys())
+    vec = torch.stack([losses[k].value for k in _C.LOSS_NAMES])
+    _check_losses(vec, ref, "drop-in losses B16 vs reference:")
+    assert rel(losses.kl.breakdown, g["kl_per_seq"]) < 5e-2
+    lmax = int(batch["end_ind"].max()) + 1
+    assert tuple(out.regressed_state.shape) == (16, lmax, 2) and tuple(inputs.model_enc_seq.shape) == (16, lmax, 128)
+    assert tuple(out.tree.bf.e_g_prime.shape) == (16, 255, 128, 1, 1) and tuple(out.tree.df.images.shape) == (16, 255, 3, 32, 32)
+    # without injected noise the model samples the posterior noise itself (device Philox): finite, different losses
+    del inputs["eps"]
+    kl1 = float(losses.kl.value)
+    out2 = model(inputs)
+    l2 = model.loss(inputs, out2)
+    assert torch.isfinite(torch.stack([l2[k].value for k in _C.LOSS_NAMES[:8]])).all()
+    assert float(l2.kl.value) != kl1 and float(losses.kl.value) == kl1
+    model.engine.close()

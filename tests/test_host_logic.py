@@ -101,3 +101,40 @@ def test_sharded_cost_gather_gloo_world2():
     assert [r[1:3] for r in res] == [(0, 32), (32, 64)]
     assert all(r[3] for r in res)                 # gathered vector == global cost vector on every rank
     assert res[0][4] == res[1][4]                 # identical elite ids everywhere
+
+
+def test_train_aux_indices_follow_reference_draws(golden_dir):
+    """TreeModel.sample_aux_indices makes the reference's np.random calls in the reference's order (inverse_mdl.py:88-98,
+    cost_mdl.py:105-106): seeded like the fixture run, it reproduces the pairs the unmodified reference drew."""
+    from video_gcp_b200.model import TreeModel
+    for name in ("train_forward_B2.npz", "train_losses_B16.npz"):
+        g = np.load(os.path.join(golden_dir, name))
+        np.random.seed(int(g["np_seed"]))
+        aux = TreeModel.sample_aux_indices(g["end_ind"])
+        for k in ("inv_t0", "inv_t1", "cost_start", "cost_end"):
+            np.testing.assert_array_equal(aux[k], g[k], err_msg="%s %s" % (name, k))
+
+
+def test_train_loss_surface_without_device():
+    """loss() / get_total_loss() hand out what the forward call reduced on the device: reference names and weights
+    (base_gcp.py:264-301), refusal of anything that did not come from a training-phase forward."""
+    from video_gcp_b200 import _C, hparams
+    from video_gcp_b200.model import TreeModel
+    from video_gcp_b200.types import AttrDict
+    m = TreeModel(hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True), None)
+    vec = torch.arange(9, dtype=torch.float32)
+    out = AttrDict({"_train_losses": vec, "_nll_per_frame": torch.zeros(2, 200), "_kl_per_seq": torch.zeros(2)})
+    losses = m.loss(AttrDict(), out)
+    assert list(losses.keys()) == list(_C.LOSS_NAMES[:8])
+    assert all(float(losses[k].value) == i for i, k in enumerate(_C.LOSS_NAMES[:8]))
+    assert losses.entropy.weight == 0.0 and all(losses[k].weight == 1.0 for k in _C.LOSS_NAMES[:7])
+    assert float(m.get_total_loss(AttrDict(), losses).value) == 8.0
+    losses.kl.weight = 0.5
+    with pytest.raises(NotImplementedError):
+        m.get_total_loss(AttrDict(), losses)
+    with pytest.raises(NotImplementedError):
+        m.loss(AttrDict(), AttrDict())
+    # a config the device call is not specialised to is refused before anything runs
+    m2 = TreeModel(hparams.gcp_tree_25room_config(batch_size=1), None)
+    with pytest.raises(NotImplementedError):
+        m2(AttrDict(traj_seq=torch.zeros(1, 200, 3, 32, 32)))

@@ -260,7 +260,140 @@ class TreeModel(_GCPModelBase):
         return TreeDenseRec(self)
 
     # ------------------------------------------------------------------------------------------
+    # Training-phase forward + loss (BASELINE config 1; train.py:155-157 and the validation pass train.py:204-206)
+    def _check_train_config(self):
+        hp = self._hp
+        if self.ENGINE_KIND != "tree":
+            raise NotImplementedError("the training-phase forward is implemented for the balanced 25-room GCP-tree only")
+        ok = (hp.attach_inv_mdl and hp.attach_state_regressor and hp.attach_cost_mdl and hp.get("run_cost_mdl", True)
+              and hp.regress_length and hp.get("seq_enc", "conv") == "conv"
+              and not hp.get("supervised_decoder", False) and not hp.get("train_inv_mdl_full_seq", False)
+              and hp.kl_weight == 1.0 and hp.length_pred_weight == 1.0 and hp.dense_img_rec_weight == 1.0
+              and hp.entropy_weight == 0.0 and not hp.get("kl_weight_burn_in", None) and hp.get("free_nats", 0) == 0)
+        if not ok:
+            raise NotImplementedError("gcpb200_forward_loss is specialised to the 25-room prediction config "
+                                      "(experiments/prediction/25room/gcp_tree/conf.py: inverse model, state regressor "
+                                      "and cost model attached, conv sequence encoder, unit loss weights)")
+
+    @staticmethod
+    def sample_aux_indices(end_ind, temp_dist=1):
+        """The auxiliary heads' frame pairs, drawn from `np.random` with the reference's calls in the reference's order
+        (run_auxilliary_models, base_gcp.py:250-260): inverse model first -- B scalar t0 draws, then one vector of B
+        offsets (inverse_mdl.py:88-98) -- then per sequence the cost model's start and end index (cost_mdl.py:105-106).
+        With the same `np.random.seed` the model therefore trains on the same pairs as the reference."""
+        import numpy as np
+        end_ind = np.asarray(end_ind).astype(np.int64)
+        B = end_ind.shape[0]
+        t0 = np.zeros(B, dtype=np.int64)
+        for b in range(B):
+            assert end_ind[b] >= temp_dist
+            t0[b] = np.random.randint(0, end_ind[b] - temp_dist + 1, 1)[0]
+        t1 = t0 + np.random.randint(1, temp_dist + 1, B)
+        cs, ce = np.zeros(B, dtype=np.int64), np.zeros(B, dtype=np.int64)
+        for b in range(B):
+            cs[b] = np.random.randint(0, end_ind[b], 1)[0]
+            ce[b] = np.random.randint(cs[b] + 1, end_ind[b] + 1, 1)[0]
+        return dict(inv_t0=t0, inv_t1=t1, cost_start=cs, cost_end=ce)
+
+    def _forward_train(self, inputs, phase):
+        """`model(inputs)` outside val_mode with a ground-truth sequence: BaseGCPModel.forward(phase='train')
+        (base_gcp.py:140-161) = run_encoder + length predictor + the tree under the approximate posterior + decoder +
+        matching + auxiliary heads, and -- because the device computes them in the same call -- every loss term.
+        One gcpb200_forward_loss call; `loss()` / `get_total_loss()` below only hand the results out.
+
+        Randomness: `inputs.eps` ([B,255,256], depth-first) replaces the posterior's N(0,1) draws if present, else the
+        device Philox stream (seed = self.seed); `inputs.aux_indices` (dict inv_t0, inv_t1, cost_start, cost_end)
+        replaces the np.random draws of `sample_aux_indices`; `inputs.cost_target` ([B,1]) replaces the device-side
+        EuclideanPathLength."""
+        self._check_train_config()
+        eng = self.engine
+        dev = eng.device
+        traj = inputs.traj_seq
+        B, T = traj.shape[:2]
+        if B > 128:
+            raise NotImplementedError("gcpb200_forward_loss takes at most 128 sequences per call")
+        outputs = AttrDict()
+        inputs.reference_tensor = traj
+        if "start_ind" not in inputs:
+            inputs.start_ind = torch.zeros(B, dtype=torch.long, device=dev)
+        end_ind = inputs.end_ind
+        aux = inputs.get("aux_indices", None)
+        if aux is None:
+            aux = self.sample_aux_indices(end_ind.detach().cpu().numpy())    # inverse_mdl.py:93 syncs the same way
+        if "eps" in inputs:
+            eps = inputs.eps
+        else:
+            eps = eng.sample_noise(B, std_scalar=1.0, seed=self.seed)
+            self.seed += 1
+        want = ["nll_per_frame", "kl_per_seq", "e_0", "e_g", "enc_traj_seq", "inf_enc_seq", "seq_len_logits", "e_df",
+                "p_mu", "p_log_sigma", "q_mu", "q_log_sigma", "match_timesteps", "existence", "model_enc_seq",
+                "regressed_state", "inv_actions", "cost_pred"]
+        if self.return_images:
+            want.append("images_df")
+        ct = inputs.get("cost_target", None)
+        res = eng.forward_loss(traj, inputs.pad_mask, end_ind, inputs.traj_seq_states, inputs.actions, eps,
+                               aux["inv_t0"], aux["inv_t1"], aux["cost_start"], aux["cost_end"], cost_target=ct,
+                               I_0=inputs.I_0, I_g=inputs.I_g, want=tuple(want))
+        lmax = int(end_ind.max()) + 1
+        sp = lambda t: t[..., None, None]
+        inputs.e_0, inputs.e_g = sp(res["e_0"]), sp(res["e_g"])
+        inputs.enc_traj_seq, inputs.inf_enc_seq = sp(res["enc_traj_seq"]), sp(res["inf_enc_seq"])
+        inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
+        outputs.seq_len_logits = res["seq_len_logits"]
+        outputs.end_ind = end_ind
+        fields = dict(e_g_prime=sp(res["e_df"]), p_z_mu=sp(res["p_mu"]), p_z_log_sigma=sp(res["p_log_sigma"]),
+                      q_z_mu=sp(res["q_mu"]), q_z_log_sigma=sp(res["q_log_sigma"]),
+                      match_timesteps=res["match_timesteps"])
+        if "images_df" in res:
+            fields["images"] = res["images_df"]
+        outputs.tree = TreeView(fields, self._hp.hierarchy_levels)
+        outputs.dense_rec = AttrDict()
+        outputs.existence_predictor = AttrDict(existence=res["existence"])
+        outputs.actions = res["inv_actions"]
+        outputs.regressed_state = res["regressed_state"][:, :lmax]
+        outputs.cost = res["cost_pred"][:, None]
+        outputs.aux_indices = aux
+        outputs.eps = eps
+        outputs["_train_losses"] = res["losses"].clone()      # the engine's buffer is overwritten by the next call
+        outputs["_nll_per_frame"], outputs["_kl_per_seq"] = res["nll_per_frame"], res["kl_per_seq"]
+        return outputs
+
+    def loss(self, inputs, outputs, log_error_arr=False):
+        """BaseGCPModel.loss + TreeModel.loss (base_gcp.py:264-288, tree.py:70-75, tree_module.py:116-130): the same
+        names, `.value` (0-dim device tensor) and `.weight` per term.  The values were reduced on the device by the
+        forward call; `breakdown` carries the per-frame NLL / per-sequence KL the reference exposes as error_mat sums."""
+        if "_train_losses" not in outputs:
+            raise NotImplementedError("loss() needs the outputs of a training-phase forward (model(inputs) outside "
+                                      "val_mode with inputs.traj_seq)")
+        from . import _C
+        vec = outputs["_train_losses"]
+        weights = dict(len_pred=self._hp.length_pred_weight, action_reconst=1.0, cost_estimation=1.0,
+                       state_regression=1.0, dense_img_rec=self._hp.dense_img_rec_weight, kl=self._hp.kl_weight,
+                       existence_predictor=1.0, entropy=self._hp.entropy_weight)
+        losses = AttrDict()
+        for i, name in enumerate(_C.LOSS_NAMES[:8]):
+            losses[name] = AttrDict(value=vec[i], weight=weights[name])
+        losses.dense_img_rec.breakdown = outputs["_nll_per_frame"]
+        losses.kl.breakdown = outputs["_kl_per_seq"]
+        self.__dict__["_last_train_total"] = (losses, {k: v.weight for k, v in losses.items()}, vec[8])
+        return losses
+
+    def get_total_loss(self, inputs, losses):
+        """base_gcp.py:290-301: sum of value * weight over the positively weighted terms, divided by the number of
+        elements of one sequence (T*3*32*32).  The device reduced it with the configuration's weights in the forward
+        call; changed weights are refused rather than silently ignored."""
+        last = self.__dict__.get("_last_train_total")
+        if last is None or last[0] is not losses or any(losses[k].weight != w for k, w in last[1].items()):
+            raise NotImplementedError("get_total_loss takes the unmodified result of loss() of the latest forward")
+        return AttrDict(value=last[2])
+
+    def step(self):
+        pass
+
+    # ------------------------------------------------------------------------------------------
     def forward(self, inputs, phase="train"):
+        if not self._val_mode and "traj_seq" in inputs:
+            return self._forward_train(inputs, phase)
         z, inject = self._rollout_args(inputs, N_NODES)
         eng = self.engine
         dev = eng.device
