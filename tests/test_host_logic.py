@@ -138,3 +138,43 @@ def test_train_loss_surface_without_device():
     m2 = TreeModel(hparams.gcp_tree_25room_config(batch_size=1), None)
     with pytest.raises(NotImplementedError):
         m2(AttrDict(traj_seq=torch.zeros(1, 200, 3, 32, 32)))
+
+
+def test_checkpoint_handler_reference_format(tmp_path):
+    """CheckpointHandler (checkpoint_handler.py:14-130): a checkpoint in the reference's format (train.py:113-122) loads
+    strictly into the drop-in model, `latest` / epoch / name resolution, sub-module filtering and the error cases."""
+    from video_gcp_b200 import hparams
+    from video_gcp_b200.checkpoint_handler import CheckpointHandler, NoCheckpointsException
+    from video_gcp_b200.model import TreeModel
+    from video_gcp_b200.synthetic import synthetic_state_dict
+    cfg = hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True)
+    src = TreeModel(cfg, None)
+    src.load_state_dict(synthetic_state_dict(src._hp, 3), strict=True)
+    folder = str(tmp_path / "weights")
+    with pytest.raises(NoCheckpointsException):
+        CheckpointHandler.get_epochs(str(tmp_path))
+    CheckpointHandler.save_checkpoint(folder, src, 2, global_step=10)
+    f9 = CheckpointHandler.save_checkpoint(folder, src, 9, global_step=77)
+    ck = torch.load(f9, map_location="cpu", weights_only=False)
+    assert set(ck.keys()) == {"epoch", "global_step", "state_dict", "optimizer"}
+    assert sorted(CheckpointHandler.get_epochs(folder)) == [2, 9]
+    assert CheckpointHandler.get_resume_ckpt_file("latest", folder) == f9
+    assert CheckpointHandler.get_resume_ckpt_file("2", folder).endswith("weights_ep2.pth")
+    assert CheckpointHandler.get_resume_ckpt_file("best", folder).endswith("best.pth")
+    dst = TreeModel(cfg, None)
+    assert CheckpointHandler.load_weights(f9, dst, strict=True) is True
+    a, b = src.state_dict(), dst.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert dst._dirty                           # the engine repacks on its next use
+    sub = CheckpointHandler.filter(ck["state_dict"], "cost_mdl")
+    assert sub and all(k.startswith("cost_pred.") for k in sub)
+    with pytest.raises(ValueError):
+        CheckpointHandler.filter(ck["state_dict"], "no_such_module")
+    with pytest.raises(ValueError):
+        CheckpointHandler.load_weights(os.path.join(folder, "missing.pth"), dst)
+
+    class Opt:
+        def load_state_dict(self, sd):
+            self.sd = sd
+    step, epoch, ok = CheckpointHandler.load_weights(f9, dst, load_step_and_opt=True, optimizer=Opt())
+    assert (step, epoch, ok) == (77, 10, True)

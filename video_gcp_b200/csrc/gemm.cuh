@@ -404,6 +404,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (C > 1) cluster_sync_all();             // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, cluster rendezvous) overlaps the tail of
+    // the previous kernel in the stream; nothing below may run before that kernel's writes are visible.
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {

@@ -1,6 +1,7 @@
 // Host-side helpers for the GEMM kernels: TMA tensor-map construction (driver entry point fetched at
 // run time, so the library has no link-time dependency on libcuda) and launchers.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
@@ -58,6 +59,22 @@ inline int gemm_cluster_size(int rows, int max_cluster) {
     return c < 1 ? 1 : c;
 }
 
+// Programmatic dependent launch of the GEMM chain (the kernel's prologue overlaps its predecessor's tail; see
+// pdl_wait() in common.cuh).  GCPB200_NO_PDL=1 turns it off for A/B measurements; gemm_pdl_suspend() is used around
+// stream capture.
+inline int& gemm_pdl_suspended() {
+    static int s = 0;
+    return s;
+}
+inline bool gemm_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GCPB200_NO_PDL");
+        on = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1 && gemm_pdl_suspended() == 0;
+}
+
 template <int BN, int EPI>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster) {
     using Cfg = GemmCfg<BN>;
@@ -77,13 +94,15 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster)
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = gemm_pdl_enabled() ? 2 : 1;
     if (max_clusters[cluster] == 0) {
         cfg.gridDim = dim3(num_sms / cluster * cluster);
         int n = 0;

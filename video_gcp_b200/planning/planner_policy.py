@@ -10,12 +10,10 @@ the CURRENT image and the next latent of the plan with the inverse model (:208-2
 Only what the reference's infrastructure (gcp/planning/infra) provides around the policy -- agent, environment,
 logging -- is left out; `log_outputs_stateful` just clears the planner logs.
 """
-import glob
-import os
-
 import numpy as np
 import torch
 
+from ..checkpoint_handler import CheckpointHandler
 from ..model import TreeModel
 from ..types import AttrDict
 from .cem_simulator import GCPImageSimulator
@@ -31,19 +29,7 @@ _DEFAULTS = dict(
 
 def resume_ckpt_file(resume, path):
     """CheckpointHandler.get_resume_ckpt_file (gcp/prediction/training/checkpoint_handler.py:31-43)."""
-    if resume == 'latest':
-        names = glob.glob(os.path.abspath(path) + "/*.pth")
-        epochs = []
-        for f in names:
-            s = os.path.basename(f).replace('weights_ep', '').replace('.pth', '')
-            if s.isdigit():
-                epochs.append(int(s))
-        if not epochs:
-            raise ValueError("No checkpoints found at {}!".format(path))
-        return os.path.join(path, 'weights_ep{}.pth'.format(max(epochs)))
-    if str(resume).isdigit():
-        return os.path.join(path, 'weights_ep{}.pth'.format(resume))
-    return os.path.join(path, resume if '.pth' in resume else resume + '.pth')
+    return CheckpointHandler.get_resume_ckpt_file(resume, path)
 
 
 class ImageCEMPolicy:
@@ -80,8 +66,9 @@ class ImageCEMPolicy:
         if hp.state_dict is not None:
             self.planner.load_state_dict(hp.state_dict, strict=False)
         else:
-            f = resume_ckpt_file('latest' if hp.load_epoch is None else hp.load_epoch, hp.checkpt_path)
-            self.planner.load_state_dict(torch.load(f, map_location='cpu')['state_dict'], strict=False)
+            # planner_policy.py:48-50
+            f = CheckpointHandler.get_resume_ckpt_file('latest' if hp.load_epoch is None else hp.load_epoch, hp.checkpt_path)
+            CheckpointHandler.load_weights(f, self.planner, strict=False)
         self.planner.eval()
 
         cem_params = AttrDict(hp.cem_params)
