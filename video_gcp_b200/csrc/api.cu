@@ -172,6 +172,46 @@ struct ProfScope {
     }
 };
 
+// GCPB200_TRACE=1: per-call timeline of the rollout on stderr (events on the rollout and the copy stream, relative to
+// the start of the call).  Diagnostic only: it synchronises the device at the end of every traced call.
+struct TraceMark {
+    const char* name;
+    cudaEvent_t ev;
+};
+static std::vector<TraceMark>& trace_marks() {
+    static std::vector<TraceMark> v;
+    return v;
+}
+static bool trace_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GCPB200_TRACE");
+        on = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+static void trace_mark(cudaStream_t st, const char* name) {
+    if (!trace_on()) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    trace_marks().push_back({name, ev});
+}
+static void trace_dump() {
+    if (!trace_on() || trace_marks().empty()) return;
+    cudaDeviceSynchronize();
+    auto& v = trace_marks();
+    fprintf(stderr, "[gcpb200 trace]");
+    for (size_t i = 0; i < v.size(); ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, v[0].ev, v[i].ev);
+        fprintf(stderr, " %s=%.2f", v[i].name, t);
+    }
+    fprintf(stderr, "\n");
+    for (auto& m : v) cudaEventDestroy(m.ev);
+    v.clear();
+}
+
 template <class T>
 static int dalloc(gcpb200_ctx* c, T** p, size_t n, bool zero = true) {
     void* q = nullptr;
@@ -890,8 +930,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     // An SM cannot hold CTAs of kernels that ask for different shared-memory carve-outs: without this the persistent
     // GEMM / decoder CTAs (200+ KB of shared memory) wait until every block of the upload kernel has left the SM and the
     // "overlapped" upload serialises with the rollout (measured: tree 6.2 -> 11.1 ms).  So the upload kernel asks for the
-    // same (maximum) carve-out as those kernels, and it only uses 32 blocks (enough for 51 GB/s over PCIe) so that the
-    // small kernels of the rollout that run with the default carve-out still find SMs they can be scheduled on.
+    // same (maximum) carve-out as those kernels, and it only uses 64 small blocks (see the launch-shape note in
+    // gcpb200_rollout) so that the small kernels of the rollout that run with the default carve-out still find SMs they
+    // can be scheduled on.
     cudaFuncSetAttribute(upload_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaFuncSetAttribute(dec_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
@@ -1077,9 +1118,9 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
 // Decoder over latent slots 1 .. n_dec (DecoderModule.decode_seq, blox/torch/encoder_decoder.py:358-372): three dense
 // composite layers as GEMMs + the implicit-GEMM tail kernel.  The image of (candidate c, slot s) goes to
 // images[(c * n_layout + s - 1) * 3072].
-static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int n_dec, float* images,
-                       int n_layout, const float* I_0 = nullptr, const float* I_g = nullptr) {
-    const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;   // pixel-copy head: needs the start / goal images
+// Per-call constants of the decoder: the up-sampled encoder skip, the skip half of the 32->16 tail conv in the quad
+// layout of dec_tail3, and the skip half of the 128->32 conv as a per-candidate row bias (the conv is linear in its input).
+static int decoder_prepare(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp) {
     const LevelGeom flat = {Bp, 0, DEPTH};
     const int n_skip = images_shared ? 1 : B;
     skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
@@ -1088,15 +1129,39 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
         skip_term3_kernel<<<dim3(8, n_skip), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
         LAUNCH_CHECK();
     }
-    // skip half of the 128->32 conv as a per-candidate additive term (the conv is linear in its input)
     CHECK(gemm(c, st, images_shared ? 128 : Bp, flat, {seg(c->s2b, 0, 1024)}, c->dec2s, 256, EPI_LINEAR,
                epi_linear(ACT_NONE, nullptr, 0, c->rowbias2, 2048, 2048)));
-    for (int s0 = 1; s0 <= n_dec; s0 += c->slot_chunk) {
+    return 0;
+}
+
+// Decodes the tree slots first, first + step, ..., `count` of them (step 1: a contiguous range; step 2 from slot 1: the
+// nodes of tree level 7; step 4 from slot 2: level 6; step 4 from slot 4: levels 0-5), slot_chunk slots per pass: three dense GEMM layers on
+// the slot-major latents, then the tail kernel writes image node = slot - 1 of every candidate.  step 2 needs the
+// tcgen05 tail kernel (the SIMT verification kernel only takes contiguous ranges).
+static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int first, int step, int count,
+                         float* images, int n_layout, const float* I_0, const float* I_g) {
+    const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;   // pixel-copy head: needs the start / goal images
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    if (step != 1 && ((step != 2 && step != 4) || c->use_ref)) {
+        gcp_set_error("decoder_slots: unsupported slot step %d", step);
+        return -1;
+    }
+    for (int k0 = 0; k0 < count; k0 += c->slot_chunk) {
         ProfScope* dsc = new ProfScope(c, st, 2);
-        const int ns = (s0 + c->slot_chunk <= n_dec + 1) ? c->slot_chunk : n_dec + 1 - s0;
+        const int ns = (k0 + c->slot_chunk <= count) ? c->slot_chunk : count - k0;
+        const int s0 = first + k0 * step;
         const int rows = ns * Bp;
-        CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 256, EPI_LINEAR,
-                   epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
+        if (step == 1) {
+            CHECK(gemm(c, st, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, s0 * Bp)}, c->dec1, 256, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
+        } else {
+            // row block j of the A operand = slot s0 + step * j: the geometry of tree level 7 (step 2) / 6 (step 4) maps
+            // j to slot (2j + 1) * step / 2 (ROW_SELF); row_base shifts that to s0
+            const int half = step / 2;
+            const LevelGeom gl = {Bp, step == 2 ? DEPTH - 1 : DEPTH - 2, DEPTH};
+            CHECK(gemm(c, st, rows, gl, {seg(c->lat, 0, NZ_ENC, ROW_SELF, (s0 - half) * Bp)}, c->dec1, 256, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
+        }
         {
             EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
             e.rowbias = c->rowbias2;
@@ -1130,6 +1195,7 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
             a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = images_shared ? 0 : 256 * 64;
             a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
             a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
+            a.slot_extra = step - 1;
             // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
             const long long n_img = (long long)B * ns;
             a.src0 = I_0; a.srcg = I_g; a.src_stride = images_shared ? 0 : 3072;
@@ -1139,6 +1205,12 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
         LAUNCH_CHECK();
     }
     return 0;
+}
+
+static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int n_dec, float* images,
+                       int n_layout, const float* I_0 = nullptr, const float* I_g = nullptr) {
+    CHECK(decoder_prepare(c, st, images_shared, B, Bp));
+    return decoder_slots(c, st, images_shared, B, Bp, 1, 1, n_dec, images, n_layout, I_0, I_g);
 }
 
 // Inverse model on consecutive rows of the zero-padded latent sequence seq [B][200][128] and state regressor on every
@@ -1292,15 +1364,33 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     if (io->z_host) {
         // Noise upload, overlapped: the copy stream gathers the rows of levels 0-3, then levels 4, 5, 6, 7 one by one
         // from pinned host memory; the rollout stream waits for each set just before the level that consumes it.
+        trace_mark(st, "start");
         GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy_start, st));       // earlier users of the staging buffer are done
         GCP_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy_start, 0));
         const int sets[5][3] = {{16, 15, 15}, {16, 7, 16}, {8, 3, 32}, {4, 1, 64}, {2, 0, 128}};   // node = a*k + b, k < cnt
+        // Launch shape (measured with GCPB200_TRACE=1, profiles/r1j_upload_interference.txt): PCIe saturates at about
+        // 8 k outstanding 16-byte reads.  Reads beyond that queue inside the GPU's memory system and slow the tensor-core
+        // kernels of the rollout stream (12-16 k outstanding: GEMMs and decoder 1.5x slower; 19 k: they stall until the
+        // upload ends), fewer leave PCIe idle.  64 blocks x 32 threads x 4 reads in flight = 8192.
+        static int up_grid = 0, up_block = 0;
+        if (up_grid == 0) {
+            const char* eg = getenv("GCPB200_UPLOAD_GRID");
+            const char* eb = getenv("GCPB200_UPLOAD_BLOCK");
+            up_grid = eg ? atoi(eg) : 64;
+            up_block = eb ? atoi(eb) : 32;
+            if (up_grid < 1 || up_block < 32 || up_block > 128 || (up_block & 31)) {
+                up_grid = 64;
+                up_block = 32;
+            }
+        }
         for (int i = 0; i < 5; ++i) {
-            upload_rows_kernel<<<32, 128, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
+            upload_rows_kernel<<<up_grid, up_block, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
                                                                       reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
                                                                       N_NODES, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
             LAUNCH_CHECK();
             GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy[i], c->copy_stream));
+            static const char* names[5] = {"up_l0-3", "up_l4", "up_l5", "up_l6", "up_l7"};
+            trace_mark(c->copy_stream, names[i]);
         }
     }
     ProfScope* scope = new ProfScope(c, st, 0);
@@ -1314,7 +1404,25 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = new ProfScope(c, st, 1);
     // ---- 3. tree recursion, level by level (SubgoalTreeLayer.produce_tree)
+    // Level-ordered decoding: a node can be decoded as soon as its level is done, so the decoder runs in three parts --
+    // levels 0-5 (63 nodes) before tree level 6, level 6 (64 nodes) before tree level 7, level 7 (128 nodes) after it.
+    // Same work in total; with host-resident noise it puts 2 ms of tensor-bound work in front of each of the two big
+    // uploads (level 6: 67 MB, level 7: 133 MB at 1024 candidates) instead of stalling the recursion on PCIe.
+    const bool level_ordered = io->images_df != nullptr && !c->use_ref;
     for (int l = 0; l < DEPTH; ++l) {
+        if (level_ordered && l >= DEPTH - 2) {
+            trace_mark(st, l == DEPTH - 2 ? "tree_l5_end" : "tree_l6_end");
+            delete scope;
+            scope = nullptr;
+            if (l == DEPTH - 2) {
+                CHECK(decoder_prepare(c, st, io->images_shared, B, Bp));
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, 63, io->images_df, N_NODES, io->I_0, io->I_g));
+            } else {
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 64, io->images_df, N_NODES, io->I_0, io->I_g));
+            }
+            scope = new ProfScope(c, st, 1);
+            trace_mark(st, l == DEPTH - 2 ? "dec_l0-5_end" : "dec_l6_end");
+        }
         if (io->z_host && (l == 0 || l >= 4)) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_copy[l == 0 ? 0 : l - 3], 0));
         if ((io->mu_df == nullptr) != (io->log_sigma_df == nullptr)) {
             gcp_set_error("mu_df and log_sigma_df must be given together");
@@ -1323,6 +1431,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr));
     }
 
+    trace_mark(st, "tree_l7_end");
     delete scope;
     scope = new ProfScope(c, st, 4);
     // ---- 4. depth-first latents, existence predictor
@@ -1345,7 +1454,10 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = nullptr;
     // ---- 5. decoder over all 255 node latents
-    if (io->images_df) CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES, io->I_0, io->I_g));
+    if (level_ordered)      // level 7 = the odd slots
+        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, N_NODES / 2 + 1, io->images_df, N_NODES, io->I_0, io->I_g));
+    else if (io->images_df)
+        CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES, io->I_0, io->I_g));
     if (adaptive && (io->distances || io->pruned_nodes || io->pruned_len)) {
         // AdaptiveBinding.prune_sequence: distance predictor on consecutive depth-first latents, then compaction
         ProfScope dsc(c, st, 4);
@@ -1380,6 +1492,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         LAUNCH_CHECK();
         if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, c->end_ind, B, io->actions, io->regressed_state));
     }
+    trace_mark(st, "end");
+    trace_dump();
     return 0;
 }
 

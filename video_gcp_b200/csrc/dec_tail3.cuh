@@ -60,6 +60,8 @@ struct DecTail3Args {
     const float* b5h;      // [16] 0.5 * bias of those channels (entry 15 = 0)
     float* images;         // [B][n_nodes][3][32][32]
     int Bp, n_cand, slot0, n_slots, n_nodes;
+    int slot_extra;        // x3 row block sl holds tree slot slot0 + sl * (1 + slot_extra); node = slot - 1, and a block
+                           // whose node is -1 (slot 0 = the start frame) is computed but not stored
     unsigned long long* prof;   // optional [16]: per-role wait / work cycles
     // pixel-copy head (dec_tail3_pc_kernel; PixelCopyDecoder, blox/torch/encoder_decoder.py:235-259): w5 holds gen_head
     // (channels 0-2, unscaled) and mask_head (3-5), b5h their biases
@@ -389,8 +391,8 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
         for (int n = 0; n < n_img; ++n) {
             const int img = img0 + n;
             const int cand = img / a.n_slots, sl = img - cand * a.n_slots;
-            const int node = a.slot0 + sl - 1;
-            float* out = a.images + ((size_t)cand * a.n_nodes + node) * 3072;
+            const int node = a.slot0 + sl * (1 + a.slot_extra) - 1;
+            float* out = a.images + ((size_t)cand * a.n_nodes + max(node, 0)) * 3072;
             const float* src0 = HEAD == 1 ? a.src0 + (size_t)cand * a.src_stride : nullptr;
             const float* srcg = HEAD == 1 ? a.srcg + (size_t)cand * a.src_stride : nullptr;
             for (int T = 0; T < 2; ++T, ++n5) {
@@ -445,9 +447,11 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
                         rgb[k][3] += mk[0][3] * p0.w + mk[1][3] * pg.w;
                     }
                 }
+                if (node >= 0) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    *reinterpret_cast<float4*>(out + k * 1024 + oy * 32 + 4 * c) = make_float4(rgb[k][0], rgb[k][1], rgb[k][2], rgb[k][3]);
+                    for (int k = 0; k < 3; ++k)
+                        *reinterpret_cast<float4*>(out + k * 1024 + oy * 32 + 4 * c) = make_float4(rgb[k][0], rgb[k][1], rgb[k][2], rgb[k][3]);
+                }
                 pc[1] += D3_T() - w1;
             }
         }
