@@ -103,6 +103,7 @@ struct gcpb200_ctx {
     bool has_cost = false, has_inv = false, has_state = false;
     int pair_rows = 0;       // rows of the `pairs` / `rowcost` scratch arrays
     EncoderWeights enc;
+    const float *enc_w1t = nullptr, *enc_w2t = nullptr, *enc_w3t = nullptr;   // k-major copies for the batch-stat encoder
     DevMat dec1, dec2x, dec2s, dec3;
     bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *z4 = nullptr, *z5 = nullptr, *s4 = nullptr;
     float *b4 = nullptr, *b5 = nullptr, *b5h = nullptr;
@@ -594,6 +595,19 @@ static int pack_encoder(gcpb200_ctx* c, const WStore& ws) {
     CHECK(up(p + "pyramid-1.conv.weight", 4, &c->enc.w2));
     CHECK(up(p + "head.weight", 4, &c->enc.w3));
     CHECK(up(p + "head.bias", 1, &c->enc.b3));
+    {   // k-major (k = ci*16 + ky*4 + kx) copies of the three strided convolutions for enc_train_*_kernel
+        auto upT = [&](const std::string& k, int CO, int K, const float** d) -> int {
+            const gcpb200_tensor* t = ws.get(k, 4);
+            if (!t) return -1;
+            std::vector<float> h((size_t)CO * K);
+            for (int co = 0; co < CO; ++co)
+                for (int kk = 0; kk < K; ++kk) h[(size_t)kk * CO + co] = t->data[(size_t)co * K + kk];
+            return upload_f32(c, d, h);
+        };
+        CHECK(upT(p + "pyramid-0.conv.weight", 32, 256, &c->enc_w1t));
+        CHECK(upT(p + "pyramid-1.conv.weight", 64, 512, &c->enc_w2t));
+        CHECK(upT(p + "head.weight", 128, 1024, &c->enc_w3t));
+    }
     BNFold f1, f2;
     CHECK(fold_bn(ws, p + "pyramid-0.norm", 32, &f1));
     CHECK(fold_bn(ws, p + "pyramid-1.norm", 64, &f2));
@@ -935,6 +949,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     // can be scheduled on.
     cudaFuncSetAttribute(upload_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaFuncSetAttribute(dec_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_train_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCA_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_train_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_train_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCC_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail3_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
@@ -1594,12 +1611,15 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
         a.y1 = w.y1; a.y2 = w.y2; a.st1 = st1; a.st2 = st2;
         a.enc_seq = w.enc_seq; a.lat_f32 = c->lat_f32; a.lat_bf16 = c->lat.p; a.row0_a = 0; a.row0_b = goal_row0;
         a.skip0 = c->s0; a.skip2 = c->s2; a.skip2_bf16 = c->s2b.p;
+        a.w1t = c->enc_w1t; a.w2t = c->enc_w2t; a.w3t = c->enc_w3t;
         const int n_img = B * (T + 2);
-        enc_train_a_kernel<<<n_img, 256, 0, st>>>(a);
+        const int n_quads = (n_img + ENCB_IMGS - 1) / ENCB_IMGS, n_blk = (n_img + ENCC_IMGS - 1) / ENCC_IMGS;
+        // persistent over images: 3 / 2 / 3 CTAs per SM fit the shared memory of the three passes
+        enc_train_a_kernel<<<std::min(n_img, 3 * c->sms), ENC_T, ENCA_SMEM, st>>>(a);
         LAUNCH_CHECK();
-        enc_train_b_kernel<<<n_img, 256, 0, st>>>(a);
+        enc_train_b_kernel<<<std::min(n_quads, 2 * c->sms), ENC_T, ENCB_SMEM, st>>>(a);
         LAUNCH_CHECK();
-        enc_train_c_kernel<<<n_img, 256, 0, st>>>(a);
+        enc_train_c_kernel<<<std::min(n_blk, 3 * c->sms), ENC_T, ENCC_SMEM, st>>>(a);
         LAUNCH_CHECK();
     }
     if (io->e_0) GCP_CUDA_CHECK(cudaMemcpyAsync(io->e_0, c->lat_f32, (size_t)B * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));

@@ -42,11 +42,17 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh /*[32]*/) {
 // Pass A: conv0 + LReLU (skip s0 of the start images), conv1 raw + channel sums.   y1 [n][32*8*8]
 // Pass B: BN(stats1) + LReLU, conv2 raw + channel sums.                             y2 [n][64*4*4]
 // Pass C: BN(stats2) + LReLU (skip s2 of the start images), 4x4 head -> latent.
+// fp32 SIMT direct convolutions (the latents feed every later stage, so they keep the reference's fp32 arithmetic),
+// register-tiled: a thread owns 8-16 output channels of one output pixel, input maps sit zero-bordered in shared
+// memory (no bounds tests in the inner loops), weights are staged k-major so that one broadcast LDS.128 feeds four
+// FMAs; CTAs are persistent over images so the weight staging is paid once.  B = 16 (3232 images): 3.4 ms -> see
+// profiles/r1k_train_forward.txt.
 // ---------------------------------------------------------------------------------------------
 struct EncTrainArgs {
     const float* img[3];    // group 0: frames [n0][3,32,32]; 1: I_0 [n1]; 2: I_g [n2]
     int n[3];
     EncoderWeights W;       // sc*/sh* unused
+    const float *w1t, *w2t, *w3t;     // k-major copies: [16*16][32], [32*16][64], [64*16][128]  (k = ci*16 + ky*4 + kx)
     const float *g1, *b1, *g2, *b2;   // BatchNorm affine of pyramid-0 (32) / pyramid-1 (64)
     float *y1, *y2;
     double *st1, *st2;      // [3][32][2], [3][64][2]  (sum, sum of squares), zeroed by the caller
@@ -62,61 +68,6 @@ __device__ __forceinline__ void enc_group(const EncTrainArgs& a, int i, int& g, 
     else if (i < a.n[0] + a.n[1]) { g = 1; li = i - a.n[0]; }
     else { g = 2; li = i - a.n[0] - a.n[1]; }
 }
-template <int CI, int CO, int HIN>
-__device__ __forceinline__ float conv_s2_at(const float* in, const float* w, int o) {
-    constexpr int HO = HIN / 2;
-    const int co = o / (HO * HO), oy = (o / HO) % HO, ox = o % HO;
-    float s = 0.f;
-    for (int ci = 0; ci < CI; ++ci) {
-        const float* wp = w + ((size_t)co * CI + ci) * 16;
-        const float* ip = in + ci * HIN * HIN;
-#pragma unroll
-        for (int ky = 0; ky < 4; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy >= HIN) continue;
-#pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-                const int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix >= HIN) continue;
-                s = fmaf(ip[iy * HIN + ix], __ldg(wp + ky * 4 + kx), s);
-            }
-        }
-    }
-    return s;
-}
-
-__global__ void __launch_bounds__(256) enc_train_a_kernel(const EncTrainArgs a) {
-    __shared__ float a0[3 * 32 * 32];
-    __shared__ float a1[16 * 16 * 16];
-    __shared__ double ssum[32], ssq[32];
-    const int tid = threadIdx.x;
-    int g, li;
-    enc_group(a, blockIdx.x, g, li);
-    const float* img = a.img[g] + (size_t)li * 3072;
-    for (int k = tid; k < 3072; k += 256) a0[k] = img[k];
-    if (tid < 32) ssum[tid] = ssq[tid] = 0.0;
-    __syncthreads();
-    enc_conv_s2<3, 16, 32>(a0, a1, a.W.w0, nullptr, nullptr, a.W.b0, tid, 256);
-    __syncthreads();
-    if (g == 1)
-        for (int k = tid; k < 4096; k += 256) a.skip0[(size_t)li * 4096 + k] = a1[k];
-    float* y = a.y1 + (size_t)blockIdx.x * 2048;
-    for (int o = tid; o < 2048; o += 256) {       // a warp's 32 outputs share one channel (64 outputs per channel)
-        const float v = conv_s2_at<16, 32, 16>(a1, a.W.w1, o);
-        y[o] = v;
-        const float s = warp_sum(v), q = warp_sum(v * v);
-        if ((tid & 31) == 0) {
-            atomicAdd(&ssum[o >> 6], (double)s);
-            atomicAdd(&ssq[o >> 6], (double)q);
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {
-        atomicAdd(a.st1 + (g * 32 + tid) * 2, ssum[tid]);
-        atomicAdd(a.st1 + (g * 32 + tid) * 2 + 1, ssq[tid]);
-    }
-}
-
 // scale / shift of a training-mode BatchNorm channel from (sum, sumsq) over `count` values
 __device__ __forceinline__ void bn_coef(const double* st, double count, float gamma, float beta, float& sc, float& sh) {
     const double mean = st[0] / count;
@@ -126,73 +77,253 @@ __device__ __forceinline__ void bn_coef(const double* st, double count, float ga
     sc = (float)s;
     sh = (float)((double)beta - mean * s);
 }
+__device__ __forceinline__ void fma4x(float (&acc)[16], int j0, float v, const float4 w) {
+    acc[j0 + 0] = fmaf(v, w.x, acc[j0 + 0]);
+    acc[j0 + 1] = fmaf(v, w.y, acc[j0 + 1]);
+    acc[j0 + 2] = fmaf(v, w.z, acc[j0 + 2]);
+    acc[j0 + 3] = fmaf(v, w.w, acc[j0 + 3]);
+}
 
-__global__ void __launch_bounds__(256) enc_train_b_kernel(const EncTrainArgs a) {
-    __shared__ float a2[32 * 8 * 8];
-    __shared__ float sc[32], sh[32];
-    __shared__ double ssum[64], ssq[64];
+constexpr int ENC_T = 128;                                   // threads of the three passes
+constexpr int ENCA_IMG = 3 * 34 * 34, ENCA_A1 = 16 * 18 * 18, ENCA_W0 = 48 * 16, ENCA_W1 = 256 * 32;
+constexpr int ENCA_SMEM = (ENCA_IMG + ENCA_A1 + ENCA_W0 + ENCA_W1) * 4;           // 70 448 B
+__global__ void __launch_bounds__(ENC_T) enc_train_a_kernel(const EncTrainArgs a) {
+    extern __shared__ float enc_sm[];
+    float* img = enc_sm;               // [3][34][34]  zero border
+    float* a1 = img + ENCA_IMG;        // [16][18][18] zero border
+    float* w0s = a1 + ENCA_A1;         // [k 48][co 16]
+    float* w1s = w0s + ENCA_W0;        // [k 256][co 32]
+    __shared__ double ssum[3][32], ssq[3][32];
     const int tid = threadIdx.x;
-    int g, li;
-    enc_group(a, blockIdx.x, g, li);
-    if (tid < 32) bn_coef(a.st1 + (g * 32 + tid) * 2, (double)a.n[g] * 64.0, a.g1[tid], a.b1[tid], sc[tid], sh[tid]);
-    if (tid < 64) ssum[tid] = ssq[tid] = 0.0;
-    __syncthreads();
-    const float* y1 = a.y1 + (size_t)blockIdx.x * 2048;
-    for (int k = tid; k < 2048; k += 256) a2[k] = lrelu_(y1[k] * sc[k >> 6] + sh[k >> 6]);
-    __syncthreads();
-    float* y = a.y2 + (size_t)blockIdx.x * 1024;
-    for (int o = tid; o < 1024; o += 256) {       // 16 consecutive outputs share one channel
-        const float v = conv_s2_at<32, 64, 8>(a2, a.W.w2, o);
-        y[o] = v;
-        float s = v, q = v * v;
+    for (int i = tid; i < ENCA_IMG + ENCA_A1; i += ENC_T) enc_sm[i] = 0.f;
+    for (int i = tid; i < ENCA_W0; i += ENC_T) w0s[(i % 48) * 16 + i / 48] = a.W.w0[i];
+    for (int i = tid; i < ENCA_W1; i += ENC_T) w1s[i] = a.w1t[i];
+    if (tid < 96) (&ssum[0][0])[tid] = (&ssq[0][0])[tid] = 0.0;
+    const int n_total = a.n[0] + a.n[1] + a.n[2];
+    for (int im = blockIdx.x; im < n_total; im += gridDim.x) {
+        int g, li;
+        enc_group(a, im, g, li);
+        __syncthreads();               // staging done / previous image consumed
+        const float* src = a.img[g] + (size_t)li * 3072;
+        for (int k = tid; k < 3072; k += ENC_T) img[(k >> 10) * 1156 + (((k >> 5) & 31) + 1) * 34 + (k & 31) + 1] = src[k];
+        __syncthreads();
+        // conv0 3 -> 16, 32x32 -> 16x16, + bias, LReLU: thread = output pixels (oy, ox) and (oy + 8, ox), 16 channels
+        {
+            const int oy = tid >> 4, ox = tid & 15;
+            float acc0[16], acc1[16];
 #pragma unroll
-        for (int d = 8; d > 0; d >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, d);
-            q += __shfl_xor_sync(0xffffffffu, q, d);
+            for (int j = 0; j < 16; ++j) acc0[j] = acc1[j] = __ldg(a.W.b0 + j);
+#pragma unroll 1
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int ky = t >> 2, kx = t & 3;
+                    const float v0 = img[ci * 1156 + (2 * oy + ky) * 34 + 2 * ox + kx];
+                    const float v1 = img[ci * 1156 + (2 * oy + 16 + ky) * 34 + 2 * ox + kx];
+                    const float4* w = reinterpret_cast<const float4*>(w0s + (ci * 16 + t) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 ww = w[q];
+                        fma4x(acc0, 4 * q, v0, ww);
+                        fma4x(acc1, 4 * q, v1, ww);
+                    }
+                }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float r0 = lrelu_(acc0[j]), r1 = lrelu_(acc1[j]);
+                a1[j * 324 + (oy + 1) * 18 + ox + 1] = r0;
+                a1[j * 324 + (oy + 9) * 18 + ox + 1] = r1;
+                if (g == 1) {
+                    a.skip0[(size_t)li * 4096 + j * 256 + oy * 16 + ox] = r0;
+                    a.skip0[(size_t)li * 4096 + j * 256 + (oy + 8) * 16 + ox] = r1;
+                }
+            }
         }
-        if ((tid & 15) == 0) {
-            atomicAdd(&ssum[o >> 4], (double)s);
-            atomicAdd(&ssq[o >> 4], (double)q);
+        __syncthreads();
+        // conv1 16 -> 32, 16x16 -> 8x8, raw: thread = output pixel p (64) x channel group cg (2 x 16)
+        {
+            const int p = tid & 63, cg = tid >> 6, oy = p >> 3, ox = p & 7;
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float v = a1[ci * 324 + (2 * oy + (t >> 2)) * 18 + 2 * ox + (t & 3)];
+                    const float4* w = reinterpret_cast<const float4*>(w1s + (ci * 16 + t) * 32 + cg * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) fma4x(acc, 4 * q, v, w[q]);
+                }
+            float* y = a.y1 + (size_t)im * 2048 + cg * 16 * 64 + p;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                y[j * 64] = acc[j];
+                const float s = warp_sum(acc[j]), q = warp_sum(acc[j] * acc[j]);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&ssum[g][cg * 16 + j], (double)s);
+                    atomicAdd(&ssq[g][cg * 16 + j], (double)q);
+                }
+            }
         }
     }
     __syncthreads();
-    if (tid < 64) {
-        atomicAdd(a.st2 + (g * 64 + tid) * 2, ssum[tid]);
-        atomicAdd(a.st2 + (g * 64 + tid) * 2 + 1, ssq[tid]);
+    if (tid < 96 && ((&ssum[0][0])[tid] != 0.0 || (&ssq[0][0])[tid] != 0.0)) {
+        atomicAdd(a.st1 + tid * 2, (&ssum[0][0])[tid]);
+        atomicAdd(a.st1 + tid * 2 + 1, (&ssq[0][0])[tid]);
     }
 }
 
-__global__ void __launch_bounds__(256) enc_train_c_kernel(const EncTrainArgs a) {
-    __shared__ float a3[64 * 4 * 4];
-    __shared__ float sc[64], sh[64];
+constexpr int ENCB_IMGS = 4;                                  // images per CTA pass (register-blocked together)
+constexpr int ENCB_A2 = 32 * 10 * 10, ENCB_W = 128 * 64;     // one image's padded input; one 8-input-channel weight chunk
+constexpr int ENCB_SMEM = (ENCB_IMGS * ENCB_A2 + ENCB_W) * 4;                     // 83 968 B
+__global__ void __launch_bounds__(ENC_T) enc_train_b_kernel(const EncTrainArgs a) {
+    extern __shared__ float enc_sm[];
+    float* a2 = enc_sm;                        // [img 4][32][10][10] zero border
+    float* w2s = a2 + ENCB_IMGS * ENCB_A2;     // [k 128][co 64] of the current input-channel chunk
+    __shared__ float sc[3][32], sh[3][32];
+    __shared__ double ssum[3][64], ssq[3][64];
     const int tid = threadIdx.x;
-    int g, li;
-    enc_group(a, blockIdx.x, g, li);
-    if (tid < 64) bn_coef(a.st2 + (g * 64 + tid) * 2, (double)a.n[g] * 16.0, a.g2[tid], a.b2[tid], sc[tid], sh[tid]);
-    __syncthreads();
-    const float* y2 = a.y2 + (size_t)blockIdx.x * 1024;
-    for (int k = tid; k < 1024; k += 256) a3[k] = lrelu_(y2[k] * sc[k >> 4] + sh[k >> 4]);
-    __syncthreads();
-    if (g == 1)
-        for (int k = tid; k < 1024; k += 256) {
-            a.skip2[(size_t)li * 1024 + k] = a3[k];
-            a.skip2_bf16[(size_t)li * 1024 + k] = __float2bfloat16_rn(a3[k]);
+    if (tid < 96) {
+        const int g = tid >> 5, ch = tid & 31;
+        bn_coef(a.st1 + tid * 2, (double)a.n[g] * 64.0, a.g1[ch], a.b1[ch], sc[g][ch], sh[g][ch]);
+    }
+    for (int i = tid; i < ENCB_IMGS * ENCB_A2; i += ENC_T) a2[i] = 0.f;
+    for (int i = tid; i < 192; i += ENC_T) (&ssum[0][0])[i] = (&ssq[0][0])[i] = 0.0;
+    const int n_total = a.n[0] + a.n[1] + a.n[2];
+    const int n_quads = (n_total + ENCB_IMGS - 1) / ENCB_IMGS;
+    const int p = tid & 15, cg = tid >> 4, oy = p >> 2, ox = p & 3;      // output pixel (16) x channel group (8 x 8)
+    for (int quad = blockIdx.x; quad < n_quads; quad += gridDim.x) {
+        const int im0 = quad * ENCB_IMGS, nimg = min(ENCB_IMGS, n_total - im0);
+        __syncthreads();                       // coefficients ready / previous quad consumed
+        for (int k = tid; k < nimg * 2048; k += ENC_T) {
+            const int i = k >> 11, r = k & 2047, ch = r >> 6;
+            int g, li;
+            enc_group(a, im0 + i, g, li);
+            a2[i * ENCB_A2 + ch * 100 + (((r >> 3) & 7) + 1) * 10 + (r & 7) + 1] =
+                lrelu_(a.y1[(size_t)(im0 + i) * 2048 + r] * sc[g][ch] + sh[g][ch]);
         }
-    // head: 1024 -> 128, two threads per output
-    const int o = tid >> 1, part = tid & 1;
-    const float* wp = a.W.w3 + (size_t)o * 1024 + part * 512;
-    const float* ap = a3 + part * 512;
-    float s = 0.f;
-    for (int k = 0; k < 512; ++k) s = fmaf(ap[k], __ldg(wp + k), s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (part == 0) {
-        s += __ldg(a.W.b3 + o);
-        if (g == 0) {
-            a.enc_seq[(size_t)li * 128 + o] = s;
-        } else {
-            const size_t r = (size_t)(g == 1 ? a.row0_a : a.row0_b) + li;
-            a.lat_f32[r * 128 + o] = s;
-            a.lat_bf16[r * 128 + o] = __float2bfloat16_rn(s);
+        float acc[ENCB_IMGS][8];
+#pragma unroll
+        for (int i = 0; i < ENCB_IMGS; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 4; ++c8) {
+            __syncthreads();                   // a2 staged / previous weight chunk consumed
+            for (int i = tid; i < ENCB_W; i += ENC_T) w2s[i] = a.w2t[c8 * ENCB_W + i];
+            __syncthreads();
+#pragma unroll 1
+            for (int cl = 0; cl < 8; ++cl)
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int off = (c8 * 8 + cl) * 100 + (2 * oy + (t >> 2)) * 10 + 2 * ox + (t & 3);
+                    const float4* w = reinterpret_cast<const float4*>(w2s + (cl * 16 + t) * 64 + cg * 8);
+                    const float4 wa = w[0], wb = w[1];
+#pragma unroll
+                    for (int i = 0; i < ENCB_IMGS; ++i) {
+                        const float v = a2[i * ENCB_A2 + off];
+                        acc[i][0] = fmaf(v, wa.x, acc[i][0]); acc[i][1] = fmaf(v, wa.y, acc[i][1]);
+                        acc[i][2] = fmaf(v, wa.z, acc[i][2]); acc[i][3] = fmaf(v, wa.w, acc[i][3]);
+                        acc[i][4] = fmaf(v, wb.x, acc[i][4]); acc[i][5] = fmaf(v, wb.y, acc[i][5]);
+                        acc[i][6] = fmaf(v, wb.z, acc[i][6]); acc[i][7] = fmaf(v, wb.w, acc[i][7]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < ENCB_IMGS; ++i) {
+            if (i < nimg) {                    // uniform per CTA
+                int g, li;
+                enc_group(a, im0 + i, g, li);
+                float* y = a.y2 + (size_t)(im0 + i) * 1024 + cg * 8 * 16 + p;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    y[j * 16] = acc[i][j];
+                    float s = acc[i][j], q = acc[i][j] * acc[i][j];
+#pragma unroll
+                    for (int d = 8; d > 0; d >>= 1) {      // the 16 pixels of a channel sit in one half-warp
+                        s += __shfl_xor_sync(0xffffffffu, s, d);
+                        q += __shfl_xor_sync(0xffffffffu, q, d);
+                    }
+                    if (p == 0) {
+                        atomicAdd(&ssum[g][cg * 8 + j], (double)s);
+                        atomicAdd(&ssq[g][cg * 8 + j], (double)q);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 192; i += ENC_T)
+        if ((&ssum[0][0])[i] != 0.0 || (&ssq[0][0])[i] != 0.0) {
+            atomicAdd(a.st2 + i * 2, (&ssum[0][0])[i]);
+            atomicAdd(a.st2 + i * 2 + 1, (&ssq[0][0])[i]);
+        }
+}
+
+constexpr int ENCC_IMGS = 16;
+constexpr int ENCC_SMEM = ENCC_IMGS * 1024 * 4;                                   // 65 536 B
+__global__ void __launch_bounds__(ENC_T) enc_train_c_kernel(const EncTrainArgs a) {
+    extern __shared__ float enc_sm[];          // a3 [img 16][k 1024], k = ch*16 + y*4 + x
+    __shared__ float sc[3][64], sh[3][64];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 192; i += ENC_T) {
+        const int g = i >> 6, ch = i & 63;
+        bn_coef(a.st2 + i * 2, (double)a.n[g] * 16.0, a.g2[ch], a.b2[ch], sc[g][ch], sh[g][ch]);
+    }
+    const int n_total = a.n[0] + a.n[1] + a.n[2];
+    const int n_blk = (n_total + ENCC_IMGS - 1) / ENCC_IMGS;
+    for (int blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const int im0 = blk * ENCC_IMGS, nimg = min(ENCC_IMGS, n_total - im0);
+        __syncthreads();
+        for (int k = tid; k < ENCC_IMGS * 1024; k += ENC_T) {
+            const int i = k >> 10, r = k & 1023;
+            float v = 0.f;
+            if (i < nimg) {
+                int g, li;
+                enc_group(a, im0 + i, g, li);
+                v = lrelu_(a.y2[(size_t)(im0 + i) * 1024 + r] * sc[g][r >> 4] + sh[g][r >> 4]);
+                if (g == 1) {
+                    a.skip2[(size_t)li * 1024 + r] = v;
+                    a.skip2_bf16[(size_t)li * 1024 + r] = __float2bfloat16_rn(v);
+                }
+            }
+            enc_sm[k] = v;
+        }
+        __syncthreads();
+        // head: 1024 -> 128 for 16 images; thread = output channel, 16 accumulators
+        float acc[ENCC_IMGS];
+#pragma unroll
+        for (int i = 0; i < ENCC_IMGS; ++i) acc[i] = 0.f;
+        const float* wp = a.w3t + tid;
+#pragma unroll 1
+        for (int k = 0; k < 1024; k += 4) {
+            const float w0 = __ldg(wp + (size_t)k * 128), w1 = __ldg(wp + (size_t)(k + 1) * 128);
+            const float w2 = __ldg(wp + (size_t)(k + 2) * 128), w3 = __ldg(wp + (size_t)(k + 3) * 128);
+#pragma unroll
+            for (int i = 0; i < ENCC_IMGS; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(enc_sm + i * 1024 + k);
+                acc[i] = fmaf(v.x, w0, acc[i]);
+                acc[i] = fmaf(v.y, w1, acc[i]);
+                acc[i] = fmaf(v.z, w2, acc[i]);
+                acc[i] = fmaf(v.w, w3, acc[i]);
+            }
+        }
+        const float b = __ldg(a.W.b3 + tid);
+#pragma unroll
+        for (int i = 0; i < ENCC_IMGS; ++i) {
+            if (i < nimg) {
+                int g, li;
+                enc_group(a, im0 + i, g, li);
+                const float s = acc[i] + b;
+                if (g == 0) {
+                    a.enc_seq[(size_t)li * 128 + tid] = s;
+                } else {
+                    const size_t r = (size_t)(g == 1 ? a.row0_a : a.row0_b) + li;
+                    a.lat_f32[r * 128 + tid] = s;
+                    a.lat_bf16[r * 128 + tid] = __float2bfloat16_rn(s);
+                }
+            }
         }
     }
 }
