@@ -107,6 +107,8 @@ struct gcpb200_ctx {
     DevMat dec1, dec2x, dec2s, dec3;
     bf16 *w4 = nullptr, *w5 = nullptr, *w4p = nullptr, *w5p = nullptr, *z4 = nullptr, *z5 = nullptr, *s4 = nullptr;
     float *b4 = nullptr, *b5 = nullptr, *b5h = nullptr;
+    bf16 *z5m = nullptr, *z5s = nullptr;      // training NLL: unscaled Toeplitz arrays of the 15 mean / 15 log-scale channels
+    float *b5m = nullptr, *b5s = nullptr;
     // workspace
     float* lat_f32 = nullptr;
     DevBuf lat, hid, xa, xb, zeta, sh, ta, tb, s2b, x1, x2, x3, pairs;
@@ -135,6 +137,7 @@ struct gcpb200_ctx {
         unsigned char* keep = nullptr;
         DevBuf x1, x2, x3;                        // raw / normalised decoder activations of all 255 nodes
         float *pq[4] = {nullptr, nullptr, nullptr, nullptr};   // p_mu, p_ls, q_mu, q_ls [B][255][256]
+        float *raw_mu = nullptr, *raw_ls = nullptr;   // raw head outputs of one 64-node chunk [128][64][1024][16]
         float *nll_bt = nullptr, *kl_b = nullptr, *reg = nullptr, *inv_pred = nullptr, *cost_pred = nullptr, *exist_df = nullptr, *cost_tgt = nullptr;
     } tw;
     // optional phase profiling (CUDA events on the caller's stream)
@@ -564,6 +567,31 @@ static int pack_decoder(gcpb200_ctx* c, const WStore& ws) {
         std::vector<float> hb5h(16, 0.f);
         for (int i = 0; i < (pc ? 6 : 15); ++i) hb5h[i] = (pc ? 1.0f : 0.5f) * head_b(i);
         CHECK(upload_f32(c, &c->b5h, hb5h));
+        if (!pc && n_head >= 30) {
+            // raw-head variants for the training-phase NLL (dec_tail3_raw_kernel): channels 0-14 and 15-29, unscaled
+            std::vector<bf16> zm(D3_W_BYTES / 2, __float2bfloat16(0.f)), zs(D3_W_BYTES / 2, __float2bfloat16(0.f));
+            for (int ky = 0; ky < 4; ++ky)
+                for (int h = 0; h < 2; ++h)
+                    for (int b = 3; b < 7; ++b)
+                        for (int co = 0; co < 15; ++co)
+                            for (int e = 0; e < 8; ++e) {
+                                const size_t o = (size_t)ky * (D3_Z_KY / 2) + h * (D3_Z_CHUNK / 2) + (16 * b + co) * 8 + e;
+                                const int ci = 8 * h + e, tap = ky * 4 + (b - 3);
+                                zm[o] = __float2bfloat16(head_w(co, ci, tap));
+                                zs[o] = __float2bfloat16(head_w(15 + co, ci, tap));
+                            }
+            CHECK(dalloc(c, &c->z5m, zm.size(), false));
+            CHECK(dalloc(c, &c->z5s, zs.size(), false));
+            GCP_CUDA_CHECK(cudaMemcpy(c->z5m, zm.data(), zm.size() * 2, cudaMemcpyHostToDevice));
+            GCP_CUDA_CHECK(cudaMemcpy(c->z5s, zs.data(), zs.size() * 2, cudaMemcpyHostToDevice));
+            std::vector<float> hbm(16, 0.f), hbs(16, 0.f);
+            for (int i = 0; i < 15; ++i) {
+                hbm[i] = head_b(i);
+                hbs[i] = head_b(15 + i);
+            }
+            CHECK(upload_f32(c, &c->b5m, hbm));
+            CHECK(upload_f32(c, &c->b5s, hbs));
+        }
         CHECK(dalloc(c, &c->w4, h4.size(), false));
         CHECK(dalloc(c, &c->w5, h5.size(), false));
         CHECK(dalloc(c, &c->w4p, p4.size(), false));
@@ -954,6 +982,8 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_train_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCC_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail3_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dec_tail3_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
     if (e != cudaSuccess) {
@@ -1535,6 +1565,8 @@ static int ensure_train_ws(gcpb200_ctx* c) {
     rc |= make_buf(c, &w.x2, rows, 2048);
     rc |= make_buf(c, &w.x3, rows, 4096);
     for (int i = 0; i < 4; ++i) rc |= dalloc(c, &w.pq[i], Bc * N_NODES * NZ_VAE);
+    rc |= dalloc(c, &w.raw_mu, Bc * 64 * 1024 * 16, false);
+    rc |= dalloc(c, &w.raw_ls, Bc * 64 * 1024 * 16, false);
     rc |= dalloc(c, &w.nll_bt, Bc * MAX_LEN);
     rc |= dalloc(c, &w.kl_b, Bc);
     rc |= dalloc(c, &w.reg, Bc * MAX_LEN * 2 + 512);
@@ -1707,10 +1739,11 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
             CHECK(gemm(c, st, rows, flat, {a3}, c->dec3t, 256, EPI_LINEAR, epi_linear(ACT_NONE, w.x3.p, 4096, nullptr, 0, 4096)));
         }
         CHECK(bn_layer(c, st, w.x3, 3, B, Bp, sd3, 4, 16, 256));
+        // skip half of the 32->16 tail conv per sequence, quad layout of the tcgen05 tail kernel
+        skip_term3_kernel<<<dim3(8, B), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
+        LAUNCH_CHECK();
         if (io->images_df) {
             // DLM mean image of every node with the rollout's tcgen05 tail kernel (tree.df.images; logging only)
-            skip_term3_kernel<<<dim3(8, B), 128, 0, st>>>(c->skip_up, c->w4p, c->b4, c->s4);
-            LAUNCH_CHECK();
             DecTail3Args a;
             memset(&a, 0, sizeof(a));
             a.x3 = w.x3.p; a.s4 = c->s4; a.s4_stride = 256 * 64;
@@ -1743,13 +1776,42 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
         if (io->cost_pred) GCP_CUDA_CHECK(cudaMemcpyAsync(io->cost_pred, w.cost_pred, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         // ---- 8. reconstruction NLL of every real frame under the node bound to it, KL, scalar losses
         float* nll_bt = io->nll_per_frame ? io->nll_per_frame : w.nll_bt;
-        TailNllArgs ta;
-        memset(&ta, 0, sizeof(ta));
-        ta.x3 = w.x3.p; ta.skip_up = c->skip_up; ta.w4p = c->w4p; ta.w5p = c->w5p; ta.b4 = c->b4; ta.b5 = c->b5;
-        ta.traj = io->traj_seq; ta.pad_mask = io->pad_mask; ta.end_ind = c->end_ind; ta.frame_node = c->frame_node;
-        ta.Bp = Bp; ta.T = T; ta.lcap = MAX_LEN; ta.root_node = (1 << (DEPTH - 1)) - 1; ta.nll_bt = nll_bt;
-        dec_tail_nll_kernel<<<B * T, 256, TN_SMEM_BYTES, st>>>(ta);
-        LAUNCH_CHECK();
+        if (c->use_ref || c->z5m == nullptr) {
+            // SIMT path (verification mode): decoder tail + NLL of one frame per block
+            TailNllArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.x3 = w.x3.p; ta.skip_up = c->skip_up; ta.w4p = c->w4p; ta.w5p = c->w5p; ta.b4 = c->b4; ta.b5 = c->b5;
+            ta.traj = io->traj_seq; ta.pad_mask = io->pad_mask; ta.end_ind = c->end_ind; ta.frame_node = c->frame_node;
+            ta.Bp = Bp; ta.T = T; ta.lcap = MAX_LEN; ta.root_node = (1 << (DEPTH - 1)) - 1; ta.nll_bt = nll_bt;
+            dec_tail_nll_kernel<<<B * T, 256, TN_SMEM_BYTES, st>>>(ta);
+            LAUNCH_CHECK();
+        } else {
+            // tcgen05 path: per 64-node chunk the tail kernel runs twice with the raw head (15 mixture-mean logits, 15
+            // log-scales; fp32 [seq][node][pixel][16]), then one block per frame evaluates the mixture NLL of the frame
+            // under the node bound to it.  All 255 nodes are decoded (half of them are bound to a frame); at 21 ns per
+            // node image that is cheaper than gathering the bound ones.
+            for (int n0 = 0; n0 < N_NODES; n0 += 64) {
+                const int nc = std::min(64, N_NODES - n0);
+                for (int half = 0; half < 2; ++half) {
+                    DecTail3Args a;
+                    memset(&a, 0, sizeof(a));
+                    a.x3 = w.x3.p + (size_t)n0 * Bp * 4096; a.s4 = c->s4; a.s4_stride = 256 * 64;
+                    a.w4 = c->z4; a.w5 = half ? c->z5s : c->z5m; a.b5h = half ? c->b5s : c->b5m;
+                    a.raw = half ? w.raw_ls : w.raw_mu;
+                    a.Bp = Bp; a.n_cand = B; a.slot0 = 1 + n0; a.n_slots = nc; a.n_nodes = N_NODES;
+                    const long long n_img = (long long)B * nc;
+                    dec_tail3_raw_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+                    LAUNCH_CHECK();
+                }
+                RawNllArgs ra;
+                memset(&ra, 0, sizeof(ra));
+                ra.raw_mu = w.raw_mu; ra.raw_ls = w.raw_ls; ra.traj = io->traj_seq; ra.pad_mask = io->pad_mask;
+                ra.end_ind = c->end_ind; ra.frame_node = c->frame_node; ra.T = T; ra.lcap = MAX_LEN;
+                ra.root_node = (1 << (DEPTH - 1)) - 1; ra.node0 = n0; ra.n_chunk = nc; ra.nll_bt = nll_bt;
+                dlm_nll_raw_kernel<<<B * T, 256, 0, st>>>(ra);
+                LAUNCH_CHECK();
+            }
+        }
         float* kl_b = io->kl_per_seq ? io->kl_per_seq : w.kl_b;
         kl_seq_kernel<<<B, 256, 0, st>>>(q_mu, q_ls, p_mu, p_ls, N_NODES * NZ_VAE, kl_b);
         LAUNCH_CHECK();

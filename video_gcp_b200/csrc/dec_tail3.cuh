@@ -65,6 +65,9 @@ struct DecTail3Args {
     unsigned long long* prof;   // optional [16]: per-role wait / work cycles
     // pixel-copy head (dec_tail3_pc_kernel; PixelCopyDecoder, blox/torch/encoder_decoder.py:235-259): w5 holds gen_head
     // (channels 0-2, unscaled) and mask_head (3-5), b5h their biases
+    // raw head (dec_tail3_raw_kernel): w5 / b5h hold 15 head channels + one zero slot, unscaled; the pre-activation
+    // outputs go to raw [n_cand][n_slots][1024 px][16] fp32 (block sl = slot slot0 + sl) for the training-phase NLL
+    float* raw;
     const float* src0;     // [n_cand or 1][3][32][32] start image
     const float* srcg;     // goal image
     int src_stride;        // elements between candidates (0: shared)
@@ -113,7 +116,8 @@ __device__ __forceinline__ void d3_conv_tile(uint32_t a_lo, uint32_t a_hi, uint3
 
 #define D3_T() (prof_on ? clock64() : 0ll)
 
-// HEAD 0: discrete-logistic-mixture mean (15 channels); HEAD 1: pixel-copy head (3 generated + 3 mask channels)
+// HEAD 0: discrete-logistic-mixture mean (15 channels); HEAD 1: pixel-copy head (3 generated + 3 mask channels);
+// HEAD 2: raw pre-activation output of 16 head channels
 template <int HEAD>
 __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
     extern __shared__ uint8_t smem_raw[];
@@ -384,7 +388,7 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
         const int q = warp - 4;
         const int m = q * 32 + lane;
         uint32_t n5 = 0;
-        constexpr int NCH = HEAD == 0 ? 15 : 6;
+        constexpr int NCH = HEAD == 0 ? 15 : (HEAD == 1 ? 6 : 16);
         float bh[NCH];
 #pragma unroll
         for (int i = 0; i < NCH; ++i) bh[i] = bias5[i];
@@ -416,7 +420,16 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
                     }
 #pragma unroll
                     for (int j2 = 0; j2 < 2; ++j2) {
-                        if (HEAD == 0) {
+                        if (HEAD == 2) {
+                            // pixel 4c + px of image row oy; 16 channels = 64 contiguous bytes
+                            const int px = 3 - (2 * half + j2);
+                            float4* rp = reinterpret_cast<float4*>(
+                                a.raw + ((((size_t)cand * a.n_slots + sl) * 1024) + (16 * T + (m >> 3)) * 32 + 4 * (m & 7) + px) * 16);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                rp[v] = make_float4(d[16 * j2 + 4 * v] + bh[4 * v], d[16 * j2 + 4 * v + 1] + bh[4 * v + 1],
+                                                    d[16 * j2 + 4 * v + 2] + bh[4 * v + 2], d[16 * j2 + 4 * v + 3] + bh[4 * v + 3]);
+                        } else if (HEAD == 0) {
                             float s[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                             for (int ch = 0; ch < 15; ++ch) s[ch % 3] += tanh_approx(d[16 * j2 + ch] + bh[ch]);
@@ -434,6 +447,10 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
                             for (int k = 0; k < 3; ++k) rgb[k][px] = e2 * inv * tanh_approx(d[16 * j2 + k] + bh[k]);
                         }
                     }
+                }
+                if (HEAD == 2) {
+                    pc[1] += D3_T() - w1;
+                    continue;
                 }
                 const int oy = 16 * T + (m >> 3), c = m & 7;
                 if (HEAD == 1) {
@@ -471,6 +488,9 @@ __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_kernel(const __grid_c
 }
 __global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_pc_kernel(const __grid_constant__ DecTail3Args a) {
     dec_tail3_body<1>(a);
+}
+__global__ void __launch_bounds__(D3_THREADS, 1) dec_tail3_raw_kernel(const __grid_constant__ DecTail3Args a) {
+    dec_tail3_body<2>(a);
 }
 
 // per-candidate skip term of the 32->16 conv in the quad layout of dec_tail3:

@@ -697,6 +697,65 @@ __global__ void __launch_bounds__(256) dec_tail_nll_kernel(const __grid_constant
     if (tid == 0) a.nll_bt[blockIdx.x] = (float)(s * (double)pad);
 }
 
+// Reconstruction NLL from the raw head outputs of the tcgen05 tail kernel (dec_tail3_raw_kernel run twice: mixture
+// means, log-scales): the same arithmetic as the second half of dec_tail_nll_kernel.  One block per (sequence, frame);
+// frames whose node is outside [node0, node0 + n_chunk) are left to the launch of their node chunk.
+struct RawNllArgs {
+    const float* raw_mu;     // [B][n_chunk][1024][16]: channel k*3 + colour = mean logit of mixture k
+    const float* raw_ls;     // same layout: log-scales
+    const float* traj;       // [B][T][3][32][32]
+    const float* pad_mask;   // [B][T]
+    const long long* end_ind;
+    const int* frame_node;   // [B][lcap]
+    int T, lcap, root_node, node0, n_chunk;
+    float* nll_bt;           // [B][T]  (multiplied by pad_mask)
+};
+__global__ void __launch_bounds__(256) dlm_nll_raw_kernel(const RawNllArgs a) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / a.T, t = blockIdx.x - b * a.T;
+    const float pad = a.pad_mask[blockIdx.x];
+    if (pad == 0.f) {                      // uniform per block
+        if (tid == 0 && a.node0 == 0) a.nll_bt[blockIdx.x] = 0.f;
+        return;
+    }
+    const int node = t <= (int)a.end_ind[b] ? a.frame_node[b * a.lcap + t] : a.root_node;
+    if (node < a.node0 || node >= a.node0 + a.n_chunk) return;
+    const size_t base = (((size_t)b * a.n_chunk + (node - a.node0)) * 1024) * 16;
+    const float* tgt = a.traj + (size_t)blockIdx.x * 3072;
+    double nll_sum = 0.0;
+    for (int p = tid; p < 1024; p += 256) {
+        float m[16], ls[16];
+        const float4* m4 = reinterpret_cast<const float4*>(a.raw_mu + base + (size_t)p * 16);
+        const float4* s4 = reinterpret_cast<const float4*>(a.raw_ls + base + (size_t)p * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 x = __ldg(m4 + v), y = __ldg(s4 + v);
+            m[4 * v] = x.x; m[4 * v + 1] = x.y; m[4 * v + 2] = x.z; m[4 * v + 3] = x.w;
+            ls[4 * v] = y.x; ls[4 * v + 1] = y.y; ls[4 * v + 2] = y.z; ls[4 * v + 3] = y.w;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float x01 = (tgt[ch * 1024 + p] + 1.0f) * 0.5f;
+            const float xb = floorf(x01 * 256.0f) * (1.0f / 256.0f);
+            float pm = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float inv = expf(-ls[k * 3 + ch]);                 // 1 / scale
+                const float xs = (xb - sigmoid_acc(m[k * 3 + ch])) * inv;
+                const float hi = sigmoid_acc(xs + (1.0f / 256.0f) * inv), lo = sigmoid_acc(xs);
+                float pr = hi - lo;
+                if (x01 == 0.f) pr = hi;
+                if (x01 == 1.f) pr = 1.0f - lo;
+                pm += pr;
+            }
+            nll_sum -= (double)logf(pm * 0.2f + 1e-7f);
+        }
+    }
+    const double s = block_sum_d(nll_sum, red);
+    if (tid == 0) a.nll_bt[blockIdx.x] = (float)(s * (double)pad);
+}
+
 // ---------------------------------------------------------------------------------------------
 // KL(q || p) of diagonal Gaussians summed over the 255 nodes x 256 dims of one sequence
 // (Gaussian.kl_divergence, blox/torch/dist.py:249-252; KLDivLoss2, blox/torch/losses.py:75-109).  grid B.
