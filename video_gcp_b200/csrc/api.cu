@@ -102,6 +102,7 @@ struct gcpb200_ctx {
     Mlp length_pred, existence, inv_mdl, state_reg, cost_mdl, distance_pred;
     bool has_cost = false, has_inv = false, has_state = false;
     int pair_rows = 0;       // rows of the `pairs` / `rowcost` scratch arrays
+    DevBuf seqb;             // bf16 copy of the pruned latent sequences, [cand][MAX_LEN + 1][128] (last row zero)
     EncoderWeights enc;
     const float *enc_w1t = nullptr, *enc_w2t = nullptr, *enc_w3t = nullptr;   // k-major copies for the batch-stat encoder
     DevMat dec1, dec2x, dec2s, dec3;
@@ -934,8 +935,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= make_buf(c, &c->x1, (size_t)c->slot_chunk * Bp, 1024);
     rc |= make_buf(c, &c->x2, (size_t)c->slot_chunk * Bp, 2048);
     rc |= make_buf(c, &c->x3, (size_t)c->slot_chunk * Bp, 4096);
-    c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? N_NODES : MAX_LEN) * Bp + 256);
+    c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? N_NODES : MAX_LEN + 1) * Bp + 256);
     rc |= make_buf(c, &c->pairs, (size_t)c->pair_rows, 256);
+    rc |= make_buf(c, &c->seqb, (size_t)(MAX_LEN + 1) * Bp + 256, NZ_ENC);
     rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
@@ -1262,28 +1264,35 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
 
 // Inverse model on consecutive rows of the zero-padded latent sequence seq [B][200][128] and state regressor on every
 // row (InverseModel.full_seq_forward, inverse_mdl.py:110-134; base_gcp.py:252-256).
-static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const float* seq, const long long* end_ind, int B, float* actions,
+static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const long long* end_ind, int B, float* actions,
                           float* regressed_state) {
+    // c->seqb holds the sequences as bf16 rows (cand, t), MAX_LEN + 1 rows per candidate (gather_frames_kernel): the
+    // pair [frame t | frame t + 1] is two row-shifted K segments of the same array, no pair matrix is materialised.
     const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
-    const int rows = (B * MAX_LEN + 127) / 128 * 128;
-    const size_t np = (size_t)rows * 256;
+    const int L1 = MAX_LEN + 1;
+    const int rows = (B * L1 + 127) / 128 * 128;
+    (void)end_ind;
     if ((actions && !c->has_inv) || (regressed_state && !c->has_state)) {
         gcp_set_error("actions / regressed_state requested but the loaded state dict has no inv_mdl / state_regressor weights");
         return -1;
     }
-    make_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(seq, end_ind, nullptr, B, MAX_LEN, rows, c->pairs.p);
-    LAUNCH_CHECK();
+    if (rows > c->pair_rows) {
+        gcp_set_error("run_pair_heads: %d rows exceed the scratch capacity %d", rows, c->pair_rows);
+        return -1;
+    }
     if (actions) {
-        CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
+        CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->seqb, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->seqb, 0, NZ_ENC, ROW_LEVEL, 1)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-        GCP_CUDA_CHECK(cudaMemcpyAsync(actions, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
+        GCP_CUDA_CHECK(cudaMemcpy2DAsync(actions, (size_t)MAX_LEN * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4, (size_t)MAX_LEN * 2 * 4, B,
+                                         cudaMemcpyDeviceToDevice, st));
     }
     if (regressed_state) {
-        CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->pairs, 0, 128)}));
+        CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->seqb, 0, NZ_ENC)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->state_reg.mid_k)}, c->state_reg.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-        GCP_CUDA_CHECK(cudaMemcpyAsync(regressed_state, c->rowcost, (size_t)B * MAX_LEN * 2 * 4, cudaMemcpyDeviceToDevice, st));
+        GCP_CUDA_CHECK(cudaMemcpy2DAsync(regressed_state, (size_t)MAX_LEN * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4,
+                                         (size_t)MAX_LEN * 2 * 4, B, cudaMemcpyDeviceToDevice, st));
     }
     return 0;
 }
@@ -1298,7 +1307,7 @@ struct PosteriorArgs {
 // One level of SubgoalTreeLayer.produce_tree (gcp/prediction/utils/tree_utils.py:21-44) = TreeModule.produce_subgoal on all
 // B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
 static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
-                      const PosteriorArgs* post) {
+                      const PosteriorArgs* post, float* e_df = nullptr) {
     const LevelGeom flat = {Bp, 0, DEPTH};
     const int goal_row0 = 256 * Bp;
     const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
@@ -1372,8 +1381,14 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             std::swap(xin, xout);
         }
         // output linear -> node latent e' (raw, no activation) at the node's slot
-        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR,
-                   epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF)));
+        // (fp32 copy: slot-major, or -- e_df given -- straight into the caller's depth-first [B][255][128] output)
+        EpiParams eo = epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF);
+        if (e_df != nullptr) {
+            eo.out_f32 = e_df;
+            eo.out_f32_df = N_NODES;
+            eo.n_cand = B;
+        }
+        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR, eo));
     }
 
     return 0;
@@ -1456,6 +1471,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     // Same work in total; with host-resident noise it puts 2 ms of tensor-bound work in front of each of the two big
     // uploads (level 6: 67 MB, level 7: 133 MB at 1024 candidates) instead of stalling the recursion on PCIe.
     const bool level_ordered = io->images_df != nullptr && !c->use_ref;
+    float* e_df = io->e_df ? io->e_df : c->e_df;
     for (int l = 0; l < DEPTH; ++l) {
         if (level_ordered && l >= DEPTH - 2) {
             trace_mark(st, l == DEPTH - 2 ? "tree_l5_end" : "tree_l6_end");
@@ -1475,19 +1491,13 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             gcp_set_error("mu_df and log_sigma_df must be given together");
             return -1;
         }
-        CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr));
+        CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr, e_df));
     }
 
     trace_mark(st, "tree_l7_end");
     delete scope;
     scope = new ProfScope(c, st, 4);
-    // ---- 4. depth-first latents, existence predictor
-    float* e_df = io->e_df ? io->e_df : c->e_df;
-    {
-        const size_t n = (size_t)B * N_NODES * NZ_ENC;
-        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, Bp, B, N_NODES, NZ_ENC, NZ_ENC, e_df);
-        LAUNCH_CHECK();
-    }
+    // ---- 4. existence predictor (the depth-first fp32 latents were written by the output GEMM of every level)
     if (io->existence) {
         const int rows = N_NODES * Bp;
         CHECK(mlp_body(c, st, c->existence, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, Bp)}));
@@ -1535,9 +1545,9 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
         const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
         gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
-                                                                           NZ_ENC / 4, seq);
+                                                                           NZ_ENC / 4, seq, c->seqb.p);
         LAUNCH_CHECK();
-        if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, c->end_ind, B, io->actions, io->regressed_state));
+        if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, c->end_ind, B, io->actions, io->regressed_state));
     }
     trace_mark(st, "end");
     trace_dump();
@@ -1759,10 +1769,10 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
     {
         const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
         gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
-                                                                           NZ_ENC / 4, seq);
+                                                                           NZ_ENC / 4, seq, c->seqb.p);
         LAUNCH_CHECK();
         float* reg = io->regressed_state ? io->regressed_state : w.reg;
-        CHECK(run_pair_heads(c, st, seq, c->end_ind, B, nullptr, reg));
+        CHECK(run_pair_heads(c, st, c->end_ind, B, nullptr, reg));
         train_pairs_kernel<<<256, 256, 0, st>>>(w.enc_seq, seq, (const long long*)io->inv_t0, (const long long*)io->inv_t1,
                                                 (const long long*)io->cost_start, (const long long*)io->cost_end, B, T, c->pairs.p);
         LAUNCH_CHECK();
@@ -1988,7 +1998,12 @@ extern "C" int gcpb200_seq_rollout(gcpb200_ctx* c, const gcpb200_seq_io* io, voi
         const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
         seq_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, given, Bp, B, MAX_LEN, seq);
         LAUNCH_CHECK();
-        if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, seq, given, B, io->actions, io->regressed_state));
+        if (io->actions || io->regressed_state) {
+            const size_t nq = (size_t)B * MAX_LEN * (NZ_ENC / 4);
+            seq_to_b16_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(seq, B, MAX_LEN, NZ_ENC / 4, c->seqb.p);
+            LAUNCH_CHECK();
+            CHECK(run_pair_heads(c, st, given, B, io->actions, io->regressed_state));
+        }
     }
     return 0;
 }

@@ -58,6 +58,8 @@ struct EpiParams {
     int out_bf16_ld, out_bf16_mode;
     float* out_f32;
     int out_f32_ld, out_f32_mode;
+    int out_f32_df;         // >0 (= n_nodes): out_f32 is candidate-major depth-first [n_cand][n_nodes][ld]; a row of tree
+                            // level g.level goes to (cand, node = slot - 1), padded candidates are dropped
     int split_col;          // >0: columns < split go to out_bf16, the rest to out_f32 (col - split)
     int n_valid;            // columns >= n_valid are dropped
     // EPI_REPARAM: zeta = exp(log_sigma) * eps + mu (blox/torch/dist.py:285-287)
@@ -254,8 +256,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
                     store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
             }
             if (p.out_f32 != nullptr) {
-                const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
-                store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
+                if (p.out_f32_df > 0) {
+                    if (cand < p.n_cand) {
+                        const size_t r = (size_t)cand * p.out_f32_df + slot_of(g, row / g.Bp, ROW_SELF) - 1;
+                        store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
+                    }
+                } else {
+                    const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
+                    store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
+                }
             }
         }
     } else if (EPI == EPI_REPARAM) {

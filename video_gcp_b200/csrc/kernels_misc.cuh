@@ -167,10 +167,13 @@ __global__ void prune_map_kernel(const long long* __restrict__ end_ind, int n_ca
     if (t != l && t != r && t >= 0 && t < lcap) frame_node[c * lcap + t] = node;
 }
 
-// dst[c][t][:] = src[c][frame_node[c][t]][:] for t <= end_ind[c], zeros after (pad_sequence)
+// dst[c][t][:] = src[c][frame_node[c][t]][:] for t <= end_ind[c], zeros after (pad_sequence).  dst_b16 (optional): the
+// same sequence as bf16 rows [c][lcap + 1][4 * d4] -- one extra, always-zero row per candidate, so that the GEMM A operand
+// "row r | row r + 1" is the consecutive-frame pair of the inverse model without crossing into the next candidate.
 __global__ void gather_frames_kernel(const float* __restrict__ src, const int* __restrict__ frame_node,
                                      const long long* __restrict__ end_ind, int n_cand, int n_nodes, int lcap,
-                                     int d4 /* row length in float4 */, float* __restrict__ dst) {
+                                     int d4 /* row length in float4 */, float* __restrict__ dst,
+                                     bf16* __restrict__ dst_b16 = nullptr) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n_cand * lcap * d4;
     if (idx >= total) return;
@@ -183,6 +186,26 @@ __global__ void gather_frames_kernel(const float* __restrict__ src, const int* _
         v = __ldg(reinterpret_cast<const float4*>(src) + ((size_t)c * n_nodes + node) * d4 + k);
     }
     reinterpret_cast<float4*>(dst)[idx] = v;
+    if (dst_b16 != nullptr) {
+        uint2 u;
+        u.x = pack_bf16x2(v.x, v.y);
+        u.y = pack_bf16x2(v.z, v.w);
+        reinterpret_cast<uint2*>(dst_b16)[((size_t)c * (lcap + 1) + t) * d4 + k] = u;
+    }
+}
+
+// fp32 sequences [c][lcap][4 * d4] -> bf16 rows [c][lcap + 1][4 * d4] (the layout gather_frames_kernel's dst_b16 has)
+__global__ void seq_to_b16_rows_kernel(const float* __restrict__ seq, int n_cand, int lcap, int d4, bf16* __restrict__ dst) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * lcap * d4) return;
+    const int k = idx % d4;
+    const int t = (idx / d4) % lcap;
+    const int c = idx / ((size_t)d4 * lcap);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(seq) + idx);
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[((size_t)c * (lcap + 1) + t) * d4 + k] = u;
 }
 
 // pair rows for the inverse model / learned cost: row (c,t) = [seq[c][t] | seq[c][t+1]] as bf16,
