@@ -201,9 +201,39 @@ __device__ __forceinline__ void group_norm_chunk(const EpiParams& p, int col0, f
     }
 }
 
+// GroupNorm over groups of 16 channels with the affine parameters staged in shared memory (gam / bet point at the
+// chunk's first column; all lanes read the same address -> broadcast LDS.128) and pairwise sums: the tcgen05 kernel's
+// row-MLP epilogue is latency-bound (8 warps per SM), so it is the dependent-chain length and the instruction count per
+// element that matter (profiles/r1h_gemm_ncu_full.txt: 548 instructions per 32-column chunk before, 6.6 cycles each).
+__device__ __forceinline__ void group_norm16_chunk_smem(const float* gam, const float* bet, float (&acc)[32]) {
+#pragma unroll
+    for (int g0 = 0; g0 < 32; g0 += 16) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = acc[g0 + 2 * i] + acc[g0 + 2 * i + 1];
+        const float mean = (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) * (1.0f / 16.0f);
+        float d[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = acc[g0 + i] - mean;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = fmaf(d[2 * i + 1], d[2 * i + 1], d[2 * i] * d[2 * i]);
+        const float var = (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) * (1.0f / 16.0f);
+        const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 ga = *reinterpret_cast<const float4*>(gam + g0 + 4 * q);
+            const float4 be = *reinterpret_cast<const float4*>(bet + g0 + 4 * q);
+            acc[g0 + 4 * q + 0] = fmaf(d[4 * q + 0] * rstd, ga.x, be.x);
+            acc[g0 + 4 * q + 1] = fmaf(d[4 * q + 1] * rstd, ga.y, be.y);
+            acc[g0 + 4 * q + 2] = fmaf(d[4 * q + 2] * rstd, ga.z, be.z);
+            acc[g0 + 4 * q + 3] = fmaf(d[4 * q + 3] * rstd, ga.w, be.w);
+        }
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int col0,
-                                               float (&acc)[32], uint4* stage = nullptr) {
+                                               float (&acc)[32], uint4* stage = nullptr, const float* gn_sm = nullptr) {
     const int cand = row % g.Bp;
     if (p.bias != nullptr) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -226,8 +256,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         }
         if (EPI == EPI_GN) {
             // torch GroupNorm: biased variance over the channels of one group, eps 1e-5
-            if (p.gn_group == 16) group_norm_chunk<16>(p, col0, acc);
-            else group_norm_chunk<4>(p, col0, acc);
+            if (p.gn_group == 16) {
+                if (gn_sm != nullptr) group_norm16_chunk_smem(gn_sm + col0, gn_sm + 256 + col0, acc);
+                else group_norm_chunk<16>(p, col0, acc);
+            } else {
+                group_norm_chunk<4>(p, col0, acc);
+            }
         }
         if (p.act == ACT_LRELU) {
 #pragma unroll
@@ -380,6 +414,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     uint4* store_stage = reinterpret_cast<uint4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
+    // EPI_GN: GroupNorm scale / shift of all N <= 256 columns (weights, so reading them before pdl_wait() is safe)
+    __shared__ __align__(16) float gn_sm[EPI == EPI_GN ? 512 : 4];
+    if (EPI == EPI_GN && args.N <= 256) {
+        for (int i = threadIdx.x; i < args.N; i += GEMM_THREADS) {
+            gn_sm[i] = __ldg(args.epi.gn_gamma + i);
+            gn_sm[256 + i] = __ldg(args.epi.gn_beta + i);
+        }
+    }
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_n = args.N / BN;
@@ -496,7 +538,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 float acc[32];
                 __syncwarp();
                 tmem_ld32(t0 + ch * 32, acc);
-                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128);
+                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128,
+                                    (EPI == EPI_GN && args.N <= 256) ? gn_sm : nullptr);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
