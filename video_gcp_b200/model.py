@@ -173,6 +173,10 @@ class _GCPModelBase(nn.Module):
         self.return_prior = False       # also return p_z (mu / log_sigma) per node
         self.return_images = True
         self.inject_end_ind = None      # parity harness: replaces the sampled rollout length
+        # True (set by the device-resident simulator around its call): the rollout outputs that the reference pads to
+        # the longest sequence of the batch keep their full [B,200] buffers instead, which saves the host
+        # synchronisation on `end_ind.max()` in the middle of a CEM step
+        self.defer_length_sync = False
         self.seed = 0
         self.__dict__["dense_rec_impl"] = self._make_dense_rec()
 
@@ -432,7 +436,8 @@ class TreeModel(_GCPModelBase):
                 outputs.pruned_prediction = _LazyNodePruned(self, outputs, res["images_df"])
             return outputs
         outputs.existence_predictor = AttrDict(existence=res["existence"])
-        lmax = int(res["end_ind"].max()) + 1
+        outputs["_lmax"] = lambda e=res["end_ind"]: int(e.max()) + 1      # length the reference pads to (host sync)
+        lmax = MAX_LEN if self.defer_length_sync else outputs["_lmax"]()
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
         outputs.actions = res["actions"][:, :lmax - 1]
         outputs.regressed_state = res["regressed_state"][:, :lmax]
@@ -513,7 +518,8 @@ class SequentialModel(_GCPModelBase):
         outputs.dense_rec = dr
         if phase != "train":
             raise NotImplementedError("only the simulator's default phase='train' aux path is implemented")
-        lmax = int(given.max()) + 1 if given is not None else MAX_LEN
+        outputs["_lmax"] = (lambda e=given: int(e.max()) + 1) if given is not None else (lambda: MAX_LEN)
+        lmax = MAX_LEN if self.defer_length_sync else outputs["_lmax"]()
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
         outputs.actions = res["actions"][:, :lmax - 1]
         outputs.regressed_state = res["regressed_state"][:, :lmax]

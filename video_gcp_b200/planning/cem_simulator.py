@@ -47,8 +47,11 @@ class DeviceRollouts:
         if append_latent:
             img = torch.cat([img, lat], -1)
         img, lat = img.cpu().numpy(), lat.cpu().numpy()
-        act = self.outputs.actions[sel_t].cpu().numpy()
-        sta = self.outputs.regressed_state[sel_t].cpu().numpy()
+        # the reference pads these two to the longest sequence of the batch (pad_sequence, base_gcp.py:242): actions
+        # [B, lmax - 1], states [B, lmax]; the device buffers are full length when the length sync was deferred
+        lmax = self.outputs["_lmax"]()
+        act = self.outputs.actions[sel_t][:, :lmax - 1].cpu().numpy()
+        sta = self.outputs.regressed_state[sel_t][:, :lmax].cpu().numpy()
         out = AttrDict(predictions=[], actions=[], states=[], latents=[])
         for n, i in enumerate(sel):
             L = ends[i] + 1
@@ -91,8 +94,14 @@ class GCPSimulator:
         input_dict = self._postprocess_inputs(input_dict)
         input_dict.I_0 = input_dict.I_0.to(dev, non_blocking=True)
         input_dict.I_g = input_dict.I_g.to(dev, non_blocking=True)
-        with self._model.val_mode():
-            out = self._model(input_dict)
+        # device-resident path: nothing on the host needs the batch's longest length, so the model skips that sync
+        defer = getattr(self._model, "defer_length_sync", False)
+        self._model.defer_length_sync = True
+        try:
+            with self._model.val_mode():
+                out = self._model(input_dict)
+        finally:
+            self._model.defer_length_sync = defer
         return DeviceRollouts(self._model, input_dict, out, input_dict.I_g[0])
 
     def rollout(self, state, goal_state, samples, rollout_len, prune=False):
