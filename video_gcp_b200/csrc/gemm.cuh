@@ -231,6 +231,29 @@ __device__ __forceinline__ void group_norm16_chunk_smem(const float* gam, const 
     }
 }
 
+// Fast path of the 128-wide row-MLP layers (EPI_LINEAR / EPI_GN, all columns valid, bf16 output only, no row bias): the
+// arithmetic of one chunk without any store, so that the kernel can run the two chunks of a thread as two independent
+// instruction streams (the layer is bound by the latency of the epilogue, not by its instruction count).
+template <int EPI>
+__device__ __forceinline__ void epilogue_math_fast(const EpiParams& p, int col0, float (&acc)[32], const float* gn_sm) {
+    if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+        }
+    }
+    if (EPI == EPI_GN) group_norm16_chunk_smem(gn_sm + col0, gn_sm + 256 + col0, acc);
+    if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = lrelu_(acc[i]);
+    } else if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int col0,
                                                float (&acc)[32], uint4* stage = nullptr, const float* gn_sm = nullptr) {
@@ -523,6 +546,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp drains
         constexpr int CH_PER_WARP = BN / 32 / (GEMM_EPI_WARPS / 4);
+        constexpr bool kPair = (BN == 128) && (EPI == EPI_LINEAR || EPI == EPI_GN);
+        const bool pair_fast = kPair && args.epi.rowbias == nullptr && args.epi.split_col == 0 && args.epi.out_f32 == nullptr &&
+                               args.epi.out_bf16 != nullptr && args.epi.n_valid >= args.N &&
+                               (EPI != EPI_GN || (args.epi.gn_group == 16 && args.N <= 256));
         const int row_in_tile = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
@@ -533,6 +560,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tc_fence_after();
             const int row = tile_m * GEMM_BM + row_in_tile;
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+            if (kPair && pair_fast) {
+                // both chunks of this thread at once; the accumulator buffer is released as soon as they are in registers
+                float a0[32], a1[32];
+                const int ch0 = half * 2;
+                __syncwarp();
+                tmem_ld32_pair(t0 + ch0 * 32, t0 + (ch0 + 1) * 32, a0, a1);
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[as]);
+                const int c0 = tile_n * BN + ch0 * 32;
+                epilogue_math_fast<EPI>(args.epi, c0, a0, gn_sm);
+                epilogue_math_fast<EPI>(args.epi, c0 + 32, a1, gn_sm);
+                const size_t r = (size_t)map_row(args.g, args.epi.out_bf16_mode, row);
+                bf16* orow = args.epi.out_bf16 + (r - lane) * args.epi.out_bf16_ld + c0;
+                uint4* stg = store_stage + (warp - 2) * 128;
+                store_bf16x32_staged(stg, orow, args.epi.out_bf16_ld, a0);
+                store_bf16x32_staged(stg, orow + 32, args.epi.out_bf16_ld, a1);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                continue;
+            }
 #pragma unroll 1
             for (int ch = half * CH_PER_WARP; ch < (half + 1) * CH_PER_WARP; ++ch) {
                 float acc[32];
