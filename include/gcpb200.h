@@ -81,8 +81,10 @@ typedef struct {
     const float* z;          /* [B,255,256] noise, depth-first node order (device) */
     const float* z_host;     /* optional PINNED HOST copy of the noise: if non-NULL, `z` is only the device staging
                                 buffer; the library uploads z_host -> z level by level on its own copy stream,
-                                overlapped with the encoder and the upper tree levels (cem_simulator.py:19-26 does
-                                this copy up front with torch.tensor(..., device)) */
+                                overlapped with the encoder, the tree and the decoder of the finished tree levels
+                                (the decoder runs level-ordered: levels 0-5, then 6, then 7), so a host-noise call
+                                takes the same time as a device-noise call (cem_simulator.py:19-26 does this copy up
+                                front with torch.tensor(..., device)) */
     const int64_t* end_ind;  /* [B] injected rollout length, or NULL: sample from the length predictor */
     uint64_t seed;           /* RNG seed for length sampling */
     int B;
