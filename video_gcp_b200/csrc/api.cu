@@ -15,6 +15,7 @@
 #include "dtw_kernels.cuh"
 #include "gemm_host.cuh"
 #include "kernels_misc.cuh"
+#include "mlp_fused.cuh"
 #include "train_kernels.cuh"
 
 using namespace gcp;
@@ -862,8 +863,79 @@ static EpiParams epi_linear(int act, bf16* ob, int ob_ld, float* of, int of_ld, 
     return e;
 }
 
+// The whole body (in + 3 GroupNorm layers) as one mlp_fused_kernel launch; result in c->tb like the unfused path.
+// GCPB200_NO_FUSED_MLP=1 keeps the four-launch path (A/B measurements).
+static bool fused_mlp_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GCPB200_NO_FUSED_MLP");
+        on = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+}
+static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
+    static bool configured = false;
+    if (!configured) {
+        GCP_CUDA_CHECK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLPF_SMEM_BYTES));
+        configured = true;
+    }
+    MlpFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    GemmArgs& ia = a.in;
+    ia.n_seg = (int)in.size();
+    int K = 0;
+    for (int i = 0; i < ia.n_seg; ++i) {
+        const Seg& s = in[i];
+        ia.a_map[i] = s.buf->map;
+        ia.seg[i].ptr = s.buf->p;
+        ia.seg[i].ld = s.buf->ld;
+        ia.seg[i].col0 = s.col0;
+        ia.seg[i].k_len = s.k_len;
+        ia.seg[i].row_mode = s.mode;
+        ia.seg[i].row_base = s.row_base;
+        K += s.k_len;
+    }
+    if (K != m.in.K || rows % GEMM_BM || K % GEMM_BK) {
+        gcp_set_error("fused mlp: bad shape rows %d K %d (weights K %d)", rows, K, m.in.K);
+        return -1;
+    }
+    ia.w_map = m.in.map_box[3];
+    ia.rows = rows;
+    ia.N = 128;
+    ia.K = K;
+    ia.g = g;
+    for (int l = 0; l < 3; ++l) {
+        a.w_mid[l] = m.mid[l].map_box[3];
+        a.gam[l] = m.gam[l];
+        a.bet[l] = m.bet[l];
+    }
+    a.bias_in = m.in.bias;
+    a.out = c->tb.p;
+    a.out_ld = c->tb.ld;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const int tiles = rows / GEMM_BM;
+    cfg.gridDim = dim3(tiles < c->sms ? tiles : c->sms);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = MLPF_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gemm_pdl_enabled() ? 1 : 0;
+    ++c->launches;
+    GCP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, a));
+    return 0;
+}
+
 // runs in -> mid x3; the last activation ends in c->tb (K = m.mid_k columns valid)
 static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
+    bool plain = in.size() <= GEMM_MAX_SEGS;
+    for (const Seg& s : in) plain = plain && s.group_cols == 0 && s.k_len % GEMM_BK == 0;
+    if (!c->use_ref && fused_mlp_enabled() && plain && m.n_mid == 3 && m.mid_valid == 128 && m.mid_k == 128 &&
+        m.gn_group == 16 && m.in.N == 128 && c->tb.ld == 128)
+        return mlp_body_fused(c, st, m, rows, g, in);
     CHECK(gemm(c, st, rows, g, in, m.in, 128, EPI_LINEAR, epi_linear(ACT_LRELU, c->ta.p, c->ta.ld, nullptr, 0, m.mid_valid)));
     DevBuf* src = &c->ta;
     DevBuf* dst = &c->tb;
