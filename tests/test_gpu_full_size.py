@@ -103,3 +103,39 @@ def test_adaptive_rollout_4096_candidates(dev):
     keep = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=dev), ~(a["distances"] > 0.0)], 1)
     assert torch.equal(keep.sum(1), n)
     eng.close()
+
+
+def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
+    """mlp_fused_kernel keeps the rounding points of the four-launch row-MLP body (bf16 activations between layers), so a
+    rollout with GCPB200_NO_FUSED_MLP=1 (read once per process, hence the subprocesses) must give the same bits; the same
+    holds for programmatic dependent launch (GCPB200_NO_PDL=1), which only changes when kernels start."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from video_gcp_b200 import hparams\n"
+        "from video_gcp_b200.engine import Engine\n"
+        "from video_gcp_b200.synthetic import synthetic_rollout_inputs, synthetic_state_dict\n"
+        "dev = torch.device('cuda:0')\n"
+        "hp = hparams.build_hparams(hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True))\n"
+        "eng = Engine(dev, max_candidates=384, attach_cost_mdl=True); eng.load_weights(synthetic_state_dict(hp, 1))\n"
+        "inp = synthetic_rollout_inputs(300, seed=5, shared_images=True)\n"
+        "out = eng.rollout(inp['I_0'][:1].to(dev), inp['I_g'][:1].to(dev), inp['z'].to(dev), end_ind=inp['end_ind'].to(dev),\n"
+        "                  images_shared=True, want_prior=True)\n"
+        "torch.cuda.synchronize()\n"
+        "h = hashlib.sha256()\n"
+        "for k in ('e_df', 'mu_df', 'log_sigma_df', 'images_df', 'existence', 'actions', 'regressed_state', 'seq_len_logits'):\n"
+        "    h.update(out[k].cpu().numpy().tobytes())\n"
+        "print('HASH', h.hexdigest(), eng.launch_count())\n" % root)
+    res = {}
+    for name, env in (("fused", {}), ("layerwise", {"GCPB200_NO_FUSED_MLP": "1"}), ("no_pdl", {"GCPB200_NO_PDL": "1"})):
+        p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("HASH")][0].split()
+        res[name] = (line[1], int(line[2]))
+    assert res["fused"][0] == res["layerwise"][0] == res["no_pdl"][0], res
+    assert res["fused"][1] < res["layerwise"][1]            # and it really is the fused path that ran
