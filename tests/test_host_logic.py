@@ -122,6 +122,7 @@ def test_train_loss_surface_without_device():
     from video_gcp_b200.model import TreeModel
     from video_gcp_b200.types import AttrDict
     m = TreeModel(hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True), None)
+    assert m.defer_length_sync is False        # a direct model(inputs) call keeps the reference's padded shapes
     vec = torch.arange(9, dtype=torch.float32)
     out = AttrDict({"_train_losses": vec, "_nll_per_frame": torch.zeros(2, 200), "_kl_per_seq": torch.zeros(2)})
     losses = m.loss(AttrDict(), out)
