@@ -217,12 +217,14 @@ def forward_loss(sd, batch, aux):
     out["model_enc_seq"] = seq
     ar = torch.arange(B)
     t0, t1 = torch.as_tensor(aux["inv_t0"]), torch.as_tensor(aux["inv_t1"])
-    inv = mlp(sd, "inv_mdl.action_pred", torch.cat([enc_seq[ar, t0], seq[ar, t1]], 1), conv=False)       # inverse_mdl.py:139-170
+    # the three auxiliary heads train on DETACHED latents (inverse_mdl.py:30,161-163; base_gcp.py:252-256;
+    # cost_mdl.py:53,91-92): no effect on the forward values, decisive for loss_gradients() below
+    inv = mlp(sd, "inv_mdl.action_pred", torch.cat([enc_seq[ar, t0].detach(), seq[ar, t1].detach()], 1), conv=False)  # inverse_mdl.py:139-170
     out["inv_actions"] = inv
-    reg = mlp(sd, "state_regressor", seq.reshape(-1, 128), conv=False).reshape(B, Lmax, 2)
+    reg = mlp(sd, "state_regressor", seq.detach().reshape(-1, 128), conv=False).reshape(B, Lmax, 2)
     out["regressed_state"] = reg
     cs, ce = torch.as_tensor(aux["cost_start"]), torch.as_tensor(aux["cost_end"])
-    cost = mlp(sd, "cost_mdl.cost_pred", torch.cat([seq[ar, cs], seq[ar, ce]], 1), conv=False)           # cost_mdl.py:55-67
+    cost = mlp(sd, "cost_mdl.cost_pred", torch.cat([seq[ar, cs].detach(), seq[ar, ce].detach()], 1), conv=False)   # cost_mdl.py:55-67
     out["cost_pred"] = cost
     # ---- losses
     L = {}
@@ -248,3 +250,26 @@ def forward_loss(sd, batch, aux):
     L["total"] = total
     out["losses"] = L
     return out
+
+
+def loss_gradients(sd, batch, aux):
+    """d total / d parameter for every floating-point tensor of the state dict the training-phase forward uses: what
+    `losses.total.value.backward()` leaves in `.grad` in the reference's training step (train.py:155-160).  Groundwork
+    for the backward pass: it pins this restatement's autograd graph -- in particular
+    the reference's three detach points -- against gradients recorded from the unmodified reference
+    (tests/golden/train_grads_B2.npz, oracle/make_golden_train_grad.py).  Returns (losses, {key: grad})."""
+    leaf = {}
+    uniq = {}
+    for k, v in sd.items():
+        if not torch.is_floating_point(v) or k.endswith(("running_mean", "running_var")):
+            leaf[k] = v
+            continue
+        # aliased entries (the decoder is registered under three names) must share one leaf
+        key = (v.data_ptr(), tuple(v.shape))
+        if key not in uniq:
+            uniq[key] = v.detach().clone().requires_grad_(True)
+        leaf[k] = uniq[key]
+    out = forward_loss(leaf, batch, aux)
+    out["losses"]["total"].backward()
+    grads = {k: v.grad for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return out["losses"], grads

@@ -111,3 +111,35 @@ def test_losses_config1_B16(golden_dir, sd):
     _check_losses(g, out["losses"])
     _close(out["kl_per_node"].sum(1), g["kl_per_seq"], 0, 1e-3)
     _close(out["nll_per_frame"].sum(1), g["nll_per_seq"], 0, 1e-4)
+
+
+def test_oracle_gradients_match_the_reference(sd, golden_dir):
+    """Groundwork for the backward pass: autograd through the oracle (with the reference's three detach points) gives the
+    gradients `losses.total.value.backward()` left in the UNMODIFIED reference (train_grads_B2.npz,
+    oracle/make_golden_train_grad.py) for every one of its 540 parameters: L2 norm, sum and leading entries."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import train_oracle as TO
+    from video_gcp_b200.synthetic import synthetic_train_batch
+    g = np.load(os.path.join(golden_dir, "train_grads_B2.npz"))
+    batch = synthetic_train_batch(2, seed=int(g["batch_seed"]), end_ind=g["end_ind"])
+    aux = dict(inv_t0=g["inv_t0"], inv_t1=g["inv_t1"], cost_start=g["cost_start"], cost_end=g["cost_end"],
+               cost_target=g["cost_target"])
+    torch.set_num_threads(os.cpu_count())
+    losses, grads = TO.loss_gradients(sd, batch, aux)
+    assert abs(float(losses["total"]) - float(g["total"])) < 1e-4 * abs(float(g["total"]))
+    names = [str(n) for n in g["names"]]
+    assert len(names) == 540 and all(n in grads for n in names)
+    worst_norm = worst_head = 0.0
+    for i, n in enumerate(names):
+        gr = grads[n].double().reshape(-1)
+        ref = float(g["norm"][i])
+        worst_norm = max(worst_norm, abs(float(gr.norm()) - ref) / max(ref, 1e-12))
+        h = np.zeros(8)
+        h[:min(8, gr.numel())] = gr[:8].numpy()
+        # leading entries against the scale of the whole gradient (single entries can be arbitrarily small)
+        scale = max(float(gr.abs().max()), 1e-12)
+        worst_head = max(worst_head, float(np.abs(h - g["head"][i]).max()) / scale)
+    print("gradient norms max rel err %.2e, leading entries max err / |grad|_inf %.2e" % (worst_norm, worst_head))
+    assert worst_norm < 1e-3 and worst_head < 1e-3
