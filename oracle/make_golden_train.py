@@ -182,6 +182,26 @@ def main():
         ref_cpu_seconds=dt, ref_cpu_threads=torch.get_num_threads(),
     )
 
+    # ---------------------------------------------------------------- case C: the extreme sequence lengths (end_ind = 1 is the
+    # shortest the inverse / cost models accept, 199 the longest the data format holds): losses + per-sequence reductions
+    B = 3
+    model = build_train_model(B)
+    model.load_state_dict(sd, strict=True)
+    batch = synthetic_train_batch(B, seed=9, end_ind=[1, 199, 100])
+    inputs, out, losses, draws = run_reference(model, batch)
+    t0, t1, cs, ce = parse_draws(draws, B)
+    L = loss_dict(losses)
+    print("case C (end_ind 1 / 199 / 100) losses", L)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "train_losses_edge_B3.npz"),
+        weight_seed=WEIGHT_SEED, batch_seed=9, end_ind=batch["end_ind"].numpy(), np_seed=int(batch["np_seed"]),
+        inv_t0=t0, inv_t1=t1, cost_start=cs, cost_end=ce, cost_target=out.cost_target.numpy(),
+        loss_names=np.array(sorted(L.keys())), loss_values=np.array([L[k] for k in sorted(L.keys())]),
+        kl_per_seq=losses.kl.error_mat.reshape(B, -1).sum(1).numpy(),
+        nll_per_frame=losses.dense_img_rec.error_mat.sum((2, 3, 4)).numpy(),
+        match_node=out.tree.bf.match_dist.argmax(1).numpy(),
+    )
+
 
 if __name__ == "__main__":
     main()

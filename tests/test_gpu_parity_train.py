@@ -192,6 +192,17 @@ def test_losses_config1_B16(engine, dev, sd, golden_dir):
     assert rel(out["nll_per_frame"].sum(1), g["nll_per_seq"]) < 2e-2
 
 
+def test_losses_extreme_lengths_B3(engine, dev, golden_dir):
+    """end_ind = 1 (two frames), 199 (the whole buffer) and 100 in one batch, against the reference's own values."""
+    g = np.load(os.path.join(golden_dir, "train_losses_edge_B3.npz"))
+    batch = synthetic_train_batch(3, seed=int(g["batch_seed"]), end_ind=g["end_ind"])
+    out = _run(engine, dev, batch, _aux(g), want=("nll_per_frame", "kl_per_seq"))
+    _check_losses(out["losses"], dict(zip([str(n) for n in g["loss_names"]], g["loss_values"])), "losses edge B3 vs reference:")
+    assert rel(out["kl_per_seq"], g["kl_per_seq"]) < 5e-2
+    assert rel(out["nll_per_frame"], g["nll_per_frame"]) < 2e-2
+    assert float(out["nll_per_frame"][0, 2:].abs().max()) == 0.0
+
+
 def test_device_cost_target_matches_reference(engine, dev, golden_dir):
     """cost_target = NULL: EuclideanPathLength of the ground-truth frames is computed on the device (cost_fcn.py:39-59);
     the cost-estimation loss must equal the one obtained with the reference's recorded target."""

@@ -113,6 +113,19 @@ def test_losses_config1_B16(golden_dir, sd):
     _close(out["nll_per_frame"].sum(1), g["nll_per_seq"], 0, 1e-4)
 
 
+def test_losses_extreme_lengths_B3(golden_dir, sd):
+    """Sequence lengths at the extremes (end_ind = 1: two frames, the shortest the inverse / cost models accept; 199: the
+    whole buffer): every loss term, the per-frame NLL and the frame -> node matching of the reference."""
+    g = np.load(os.path.join(golden_dir, "train_losses_edge_B3.npz"))
+    batch = synthetic_train_batch(3, seed=int(g["batch_seed"]), end_ind=g["end_ind"])
+    with torch.no_grad():
+        out = TO.forward_loss(sd, batch, _aux(g))
+    _check_losses(g, out["losses"])
+    _close(out["kl_per_node"].sum(1), g["kl_per_seq"], 0, 1e-3)
+    _close(out["nll_per_frame"], g["nll_per_frame"], 0, 1e-4)
+    assert float(out["nll_per_frame"][0, 2:].abs().max()) == 0.0          # frames past end_ind = 1 carry no loss
+
+
 def test_oracle_gradients_match_the_reference(sd, golden_dir):
     """Groundwork for the backward pass: autograd through the oracle (with the reference's three detach points) gives the
     gradients `losses.total.value.backward()` left in the UNMODIFIED reference (train_grads_B2.npz,
