@@ -874,10 +874,13 @@ static bool fused_mlp_enabled() {
     return on == 1;
 }
 static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured_dev[64] = {false};     // function attributes are per device
+    int dev = 0;
+    GCP_CUDA_CHECK(cudaGetDevice(&dev));
+    dev &= 63;
+    if (!configured_dev[dev]) {
         GCP_CUDA_CHECK(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLPF_SMEM_BYTES));
-        configured = true;
+        configured_dev[dev] = true;
     }
     MlpFusedArgs a;
     memset(&a, 0, sizeof(a));

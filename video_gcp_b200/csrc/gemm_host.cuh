@@ -78,12 +78,18 @@ inline bool gemm_pdl_enabled() {
 template <int BN, int EPI>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster) {
     using Cfg = GemmCfg<BN>;
-    static bool configured = false;
-    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // co-resident clusters per cluster size
-    if (!configured) {
+    // function attributes and occupancy are per device: one slot per device ordinal (a process normally drives one GPU,
+    // but nothing here should break when it owns several contexts)
+    static bool configured_dev[64] = {false};
+    static int max_clusters_dev[64][9] = {{0}};   // co-resident clusters per cluster size
+    int dev = 0;
+    GCP_CUDA_CHECK(cudaGetDevice(&dev));
+    dev &= 63;
+    int* max_clusters = max_clusters_dev[dev];
+    if (!configured_dev[dev]) {
         GCP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES));
-        configured = true;
+        configured_dev[dev] = true;
     }
     if (a.rows % GEMM_BM || a.N % BN || a.K % GEMM_BK || (a.rows / GEMM_BM) % cluster) {
         gcp_set_error("gemm: bad shape rows %d N %d K %d (BN %d, cluster %d)", a.rows, a.N, a.K, BN, cluster);
