@@ -319,6 +319,25 @@ int gcpb200_dtw(gcpb200_ctx* ctx, const void* cost, int cost_is_f64, const int64
 int gcpb200_gather_rows(gcpb200_ctx* ctx, const float* src, const int32_t* idx, int n_out, int row_floats, float* out,
                         void* stream);
 
+/* ---- optimiser step (the `self.optimizer.step()` of train.py:162) -------------------------------------
+ * The reference trains with RAdam (gcp_builder.py:174-186,259; blox/torch/radam.py:17-80) or torch.optim.Adam, wrapped in
+ * ClipGradOptimizer (blox/torch/training.py:146-161: torch.nn.utils.clip_grad_norm_ over all parameters, then the step).
+ *
+ * gcpb200_sq_norm     *acc += sum(x[i]^2) in float64 (device scalar, zeroed by the caller): called once per gradient tensor,
+ *                     it yields the total gradient norm the clipping needs without any host round trip.
+ * gcpb200_optim_step  one in-place step over a flat fp32 parameter array p with gradient g and moments m, v (all [n]).
+ *                     kind GCPB200_OPT_ADAM / GCPB200_OPT_RADAM; `step` is the 1-based step count of this update;
+ *                     hyper-parameters are doubles (Python floats) and rounded to fp32 where torch rounds them.
+ *                     grad_sq_norm (device float64 scalar or NULL) + max_norm > 0: gradients are scaled by
+ *                     min(1, max_norm / (sqrt(*grad_sq_norm) + 1e-6)) as clip_grad_norm_ does.  HBM-bound: 16 B read and
+ *                     12 B written per parameter. */
+#define GCPB200_OPT_ADAM 0
+#define GCPB200_OPT_RADAM 1
+int gcpb200_sq_norm(gcpb200_ctx* ctx, const float* x, int64_t n, double* acc, void* stream);
+int gcpb200_optim_step(gcpb200_ctx* ctx, int kind, float* p, const float* g, float* m, float* v, int64_t n, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                       const double* grad_sq_norm, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

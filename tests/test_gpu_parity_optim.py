@@ -1,0 +1,88 @@
+"""GPU parity of the optimiser step (gcpb200_sq_norm / gcpb200_optim_step through video_gcp_b200.optim) against the
+trajectories of the unmodified reference optimisers (tests/golden/optim_steps.npz) and the CPU oracle; fp32 elementwise
+arithmetic: 5e-6 relative (FMA contraction on the device vs separate roundings in torch)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import optim_oracle as OO
+from oracle.make_golden_optim_data import CASES, data
+
+# not yet run on the B200 box (the pod was draining when it was written): opt in with GCPB200_TEST_OPTIM=1 until verified
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GCPB200_TEST_OPTIM") != "1",
+                                                   reason="optimiser step not yet verified on the GPU box")]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    assert torch.cuda.is_available(), "GPU tests need the B200 box"
+    from video_gcp_b200.engine import Engine
+    eng = Engine(torch.device("cuda:0"), max_candidates=128)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_trajectory_matches_reference(engine, golden_dir, name):
+    from video_gcp_b200.optim import get_clipped_optimizer
+    g = np.load(os.path.join(golden_dir, "optim_steps.npz"))
+    c = CASES[name]
+    params, grads = data()
+    dev = engine.device
+    ps = [torch.nn.Parameter(torch.tensor(p, device=dev)) for p in params]
+    opt = get_clipped_optimizer(ps, engine, optimizer_type=c["kind"], lr=c["lr"], betas=c["betas"],
+                                weight_decay=c["weight_decay"], gradient_clip=c["clip"])
+    for step_grads in grads:
+        for p, gr in zip(ps, step_grads):
+            p.grad = torch.tensor(gr, device=dev)
+        opt.step()
+    torch.cuda.synchronize()
+    for i, p in enumerate(ps):
+        st = opt.state[p]
+        for tag, got in (("p", p.data), ("m", st["exp_avg"]), ("v", st["exp_avg_sq"])):
+            ref = g["%s_%s%d" % (name, tag, i)]
+            err = np.abs(got.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+            assert err < 5e-6, (name, tag, i, err)
+    # checkpoint round trip in torch.optim's format, then one more step equals the oracle's 13th step
+    sd = opt.state_dict()
+    opt2 = get_clipped_optimizer(ps, engine, optimizer_type=c["kind"], gradient_clip=c["clip"])
+    opt2.load_state_dict(sd)
+    assert opt2.param_groups[0]["lr"] == c["lr"] and opt2.state[ps[2]]["step"] == len(grads)
+    before = [p.detach().cpu().numpy().copy() for p in ps]
+    ms = [opt2.state[p]["exp_avg"].cpu().numpy().copy() for p in ps]
+    vs = [opt2.state[p]["exp_avg_sq"].cpu().numpy().copy() for p in ps]
+    for p, gr in zip(ps, grads[0]):
+        p.grad = torch.tensor(gr, device=dev)
+    opt2.step()
+    torch.cuda.synchronize()
+    s = OO.clip_scale(grads[0], c["clip"])
+    fn = OO.radam_step if c["kind"] == "radam" else OO.adam_step
+    for i, p in enumerate(ps):
+        want, _, _ = fn(before[i], (grads[0][i] * s).astype(np.float32), ms[i], vs[i], len(grads) + 1, c["lr"], c["betas"], 1e-8,
+                        c["weight_decay"])
+        assert np.abs(p.detach().cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-12) < 5e-6
+
+
+def test_full_model_step_bandwidth(engine):
+    """One RAdam step over a 124.24 M-parameter flat array (the 25-room GCP-tree): algorithmic 28 B per parameter."""
+    from video_gcp_b200.optim import get_clipped_optimizer
+    dev = engine.device
+    n = 124_240_000
+    p = torch.nn.Parameter(torch.randn(n, device=dev))
+    opt = get_clipped_optimizer([p], engine, optimizer_type="radam", gradient_clip=1.0)
+    p.grad = torch.randn(n, device=dev)
+    for _ in range(3):
+        opt.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gbs = n * (28 + 4) / ms / 1e6          # + 4 B: the gradient is read once more for the norm
+    print("RAdam + clipping over %d parameters: %.3f ms per step = %.0f GB/s algorithmic" % (n, ms, gbs))
+    assert torch.isfinite(p).all() and gbs > 2000

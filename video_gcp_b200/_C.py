@@ -92,6 +92,10 @@ EXPORTS = {
     "gcpb200_dtw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gcpb200_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gcpb200_sq_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "gcpb200_optim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_float,
+                                     C.c_void_p]),
     "gcpb200_launch_count": (C.c_int64, [C.c_void_p]),
     "gcpb200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gcpb200_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -2407,3 +2407,67 @@ extern "C" int gcpb200_gather_rows(gcpb200_ctx* c, const float* src, const int32
     LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Optimiser step (RAdam / Adam + gradient-norm clipping)
+// ---------------------------------------------------------------------------------------------
+extern "C" int gcpb200_sq_norm(gcpb200_ctx* c, const float* x, int64_t n, double* acc, void* stream) {
+    if (!c || !x || !acc || n < 0) {
+        gcp_set_error("gcpb200_sq_norm: bad arguments");
+        return -1;
+    }
+    if (n == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    sq_norm_kernel<<<(unsigned)(blocks < 4LL * c->sms ? blocks : 4LL * c->sms), 256, 0, st>>>(x, (long long)n, acc);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gcpb200_optim_step(gcpb200_ctx* c, int kind, float* p, const float* g, float* m, float* v, int64_t n, double lr,
+                                  double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                                  const double* grad_sq_norm, float max_norm, void* stream) {
+    if (!c || !p || !g || !m || !v || n < 0 || step < 1 || (kind != GCPB200_OPT_ADAM && kind != GCPB200_OPT_RADAM)) {
+        gcp_set_error("gcpb200_optim_step: bad arguments (kind %d, n %lld, step %lld)", kind, (long long)n, (long long)step);
+        return -1;
+    }
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) {
+        gcp_set_error("gcpb200_optim_step: p, g, m, v must be 16-byte aligned");
+        return -1;
+    }
+    if (n == 0) return 0;
+    OptimArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = p; a.g = g; a.m = m; a.v = v; a.n = (long long)n;
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+    a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+    a.grad_sq_norm = grad_sq_norm; a.max_norm = max_norm;
+    // per-step scalars in double, as the Python floats of the reference
+    const double b1 = beta1, b2 = beta2, t = (double)step;
+    if (kind == GCPB200_OPT_RADAM) {
+        // blox/torch/radam.py:56-68
+        const double beta2_t = pow(b2, t);
+        const double n_sma_max = 2.0 / (1.0 - b2) - 1.0;
+        const double n_sma = n_sma_max - 2.0 * t * beta2_t / (1.0 - beta2_t);
+        double step_size;
+        if (n_sma >= 5.0)
+            step_size = sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_sma_max - 4.0) * (n_sma - 2.0) / n_sma * n_sma_max /
+                             (n_sma_max - 2.0)) / (1.0 - pow(b1, t));
+        else
+            step_size = 1.0 / (1.0 - pow(b1, t));
+        a.radam = 1;
+        a.rectified = n_sma >= 5.0;
+        a.step_size = (float)(step_size * lr);
+        a.decay = (float)(weight_decay * lr);
+    } else {
+        a.step_size = (float)(lr / (1.0 - pow(b1, t)));
+        a.sqrt_bc2 = (float)sqrt(1.0 - pow(b2, t));
+        a.decay = (float)weight_decay;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long blocks = (n / 4 + 255) / 256 + 1;
+    optim_step_kernel<<<(unsigned)(blocks < 8LL * c->sms ? blocks : 8LL * c->sms), 256, 0, st>>>(a);
+    LAUNCH_CHECK();
+    return 0;
+}
+
