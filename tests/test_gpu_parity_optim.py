@@ -10,9 +10,7 @@ import torch
 from oracle import optim_oracle as OO
 from oracle.make_golden_optim_data import CASES, data
 
-# not yet run on the B200 box (the pod was draining when it was written): opt in with GCPB200_TEST_OPTIM=1 until verified
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GCPB200_TEST_OPTIM") != "1",
-                                                   reason="optimiser step not yet verified on the GPU box")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
