@@ -270,6 +270,16 @@ def loss_gradients(sd, batch, aux):
             uniq[key] = v.detach().clone().requires_grad_(True)
         leaf[k] = uniq[key]
     out = forward_loss(leaf, batch, aux)
+    # stage targets for a device backward pass: d total / d (intermediate) of the tensors a staged implementation hands
+    # from one kernel group to the next (node latents, posterior / prior parameters, DLM head outputs, encoder outputs)
+    stages = dict(e_df=out["tree"]["e"], q_mu=out["tree"]["q_mu"], q_log_sigma=out["tree"]["q_ls"], p_mu=out["tree"]["p_mu"],
+                  p_log_sigma=out["tree"]["p_ls"], distr_mu=out["distr_mu"], distr_log_sigma=out["distr_ls"],
+                  enc_traj_seq=out["enc_traj_seq"], inf_enc_seq=out["inf_enc_seq"], e_0=out["e0"], e_g=out["eg"],
+                  skip0=out["s0"], skip2=out["s2"], seq_len_logits=out["seq_len_logits"], existence=out["existence"])
+    for t in stages.values():
+        if t.requires_grad:
+            t.retain_grad()
     out["losses"]["total"].backward()
     grads = {k: v.grad for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    grads["__stages__"] = {k: (t.grad if t.grad is not None else torch.zeros_like(t)) for k, t in stages.items()}
     return out["losses"], grads

@@ -144,6 +144,15 @@ def test_oracle_gradients_match_the_reference(sd, golden_dir):
     assert abs(float(losses["total"].detach()) - float(g["total"])) < 1e-4 * abs(float(g["total"]))
     names = [str(n) for n in g["names"]]
     assert len(names) == 540 and all(n in grads for n in names)
+    # stage targets (gradients of the intermediates a staged device backward hands over): shapes, finiteness, and the one
+    # closed form among them -- d total / d q_mu of KL + reconstruction is non-zero exactly on ... every node (KL touches all)
+    st = grads["__stages__"]
+    assert tuple(st["e_df"].shape) == (2, 255, 128) and tuple(st["distr_mu"].shape) == (2, 255, 5, 3, 32, 32)
+    assert all(bool(torch.isfinite(t).all()) for t in st.values())
+    bound = torch.as_tensor(TO.match_tables(g["end_ind"])[0])                      # [B,255] nodes bound to a frame
+    per_node = st["distr_mu"].abs().sum((2, 3, 4, 5))
+    assert bool((per_node[~bound] == 0).all()) and bool((per_node[bound] > 0).all())   # only bound nodes are reconstructed
+    assert float(st["q_mu"].abs().sum((2,)).min()) > 0.0
     worst_norm = worst_head = 0.0
     for i, n in enumerate(names):
         gr = grads[n].double().reshape(-1)
