@@ -51,7 +51,8 @@ typedef struct {
     int device;          /* CUDA device ordinal */
     int max_candidates;  /* largest B of one rollout call (workspace is sized for it, rounded up to 128) */
     int attach_cost_mdl; /* 1: expect cost_mdl.cost_pred.* weights (learned cost available) */
-    int use_ref_kernels; /* 1: verification mode, SIMT kernels instead of tcgen05 (tests only) */
+    int reserved0;       /* must be 0 (the separately built verification library of tests/cuda uses it to select its
+                            SIMT cross-check kernels; the shipped library has one code path and rejects non-zero) */
     int decoder_slot_chunk; /* decoder processes this many tree slots per pass (0 = default 64) */
     int model;           /* GCPB200_MODEL_TREE (0), _SEQUENTIAL (1) or _TREE_ADAPTIVE (2): which reference model the context
                             holds (TreeModel, gcp/prediction/models/tree/tree.py:14; SequentialModel,

@@ -41,7 +41,9 @@ def main():
     outs = {}
     for mode in ("ref", "tc"):
         print("== %s kernels ==" % mode)
-        eng = Engine(dev, max_candidates=128, attach_cost_mdl=True, use_ref_kernels=(mode == "ref"))
+        from tests.verify_lib import verify_engine
+        eng = verify_engine(dev, max_candidates=128, attach_cost_mdl=True) if mode == "ref" else \
+            Engine(dev, max_candidates=128, attach_cost_mdl=True)
         eng.load_weights(sd)
         out = eng.rollout(inp["I_0"].to(dev), inp["I_g"].to(dev), inp["z"].to(dev), end_ind=inp["end_ind"].to(dev),
                           want_prior=True)

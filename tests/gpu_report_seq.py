@@ -37,7 +37,9 @@ def main():
     print("oracle (CPU, %d threads) B=%d: %.2f s" % (torch.get_num_threads(), B, time.time() - t0))
     dev = torch.device("cuda:0")
     for use_ref in (True, False):
-        eng = Engine(dev, max_candidates=max(B, 128), use_ref_kernels=use_ref, model="sequential")
+        from tests.verify_lib import verify_engine
+        eng = verify_engine(dev, max_candidates=max(B, 128), model="sequential") if use_ref else \
+            Engine(dev, max_candidates=max(B, 128), model="sequential")
         eng.load_weights(sd)
         out = eng.seq_rollout(inp["I_0"].to(dev), inp["I_g"].to(dev), inp["z"].to(dev), end_ind=inp["end_ind"].to(dev),
                               want_prior=True)

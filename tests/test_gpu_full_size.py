@@ -108,7 +108,8 @@ def test_adaptive_rollout_4096_candidates(dev):
 def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
     """mlp_fused_kernel keeps the rounding points of the four-launch row-MLP body (bf16 activations between layers), so a
     rollout with GCPB200_NO_FUSED_MLP=1 (read once per process, hence the subprocesses) must give the same bits; the same
-    holds for programmatic dependent launch (GCPB200_NO_PDL=1), which only changes when kernels start."""
+    holds for programmatic dependent launch (GCPB200_NO_PDL=1), which only changes when kernels start.  The switches exist
+    in the verification build of the library only (tests/verify_lib.py); the shipped library's result must equal them."""
     import hashlib
     import os
     import subprocess
@@ -119,10 +120,13 @@ def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
         "sys.path.insert(0, %r)\n"
         "from video_gcp_b200 import hparams\n"
         "from video_gcp_b200.engine import Engine\n"
+        "from tests.verify_lib import verify_engine\n"
         "from video_gcp_b200.synthetic import synthetic_rollout_inputs, synthetic_state_dict\n"
         "dev = torch.device('cuda:0')\n"
         "hp = hparams.build_hparams(hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True))\n"
-        "eng = Engine(dev, max_candidates=384, attach_cost_mdl=True); eng.load_weights(synthetic_state_dict(hp, 1))\n"
+        "eng = Engine(dev, max_candidates=384, attach_cost_mdl=True) if sys.argv[1] == 'shipped' else \\\n"
+        "    verify_engine(dev, simt=False, max_candidates=384, attach_cost_mdl=True)\n"
+        "eng.load_weights(synthetic_state_dict(hp, 1))\n"
         "inp = synthetic_rollout_inputs(300, seed=5, shared_images=True)\n"
         "out = eng.rollout(inp['I_0'][:1].to(dev), inp['I_g'][:1].to(dev), inp['z'].to(dev), end_ind=inp['end_ind'].to(dev),\n"
         "                  images_shared=True, want_prior=True)\n"
@@ -132,10 +136,10 @@ def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
         "    h.update(out[k].cpu().numpy().tobytes())\n"
         "print('HASH', h.hexdigest(), eng.launch_count())\n" % root)
     res = {}
-    for name, env in (("fused", {}), ("layerwise", {"GCPB200_NO_FUSED_MLP": "1"}), ("no_pdl", {"GCPB200_NO_PDL": "1"})):
-        p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    for name, env in (("shipped", {}), ("fused", {}), ("layerwise", {"GCPB200_NO_FUSED_MLP": "1"}), ("no_pdl", {"GCPB200_NO_PDL": "1"})):
+        p = subprocess.run([sys.executable, "-c", code, name], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, p.stderr[-2000:]
         line = [l for l in p.stdout.splitlines() if l.startswith("HASH")][0].split()
         res[name] = (line[1], int(line[2]))
-    assert res["fused"][0] == res["layerwise"][0] == res["no_pdl"][0], res
+    assert res["shipped"][0] == res["fused"][0] == res["layerwise"][0] == res["no_pdl"][0], res
     assert res["fused"][1] < res["layerwise"][1]            # and it really is the fused path that ran

@@ -133,8 +133,10 @@ def test_adaptive_tc_kernels_match_simt_verification_kernels(dev, ada_sd):
     from video_gcp_b200.engine import Engine
     inp = synthetic_rollout_inputs(4, seed=37, shared_images=True)
     outs = []
+    from tests.verify_lib import verify_engine
     for use_ref in (True, False):
-        eng = Engine(dev, max_candidates=128, use_ref_kernels=use_ref, model="tree_adaptive")
+        eng = verify_engine(dev, max_candidates=128, model="tree_adaptive") if use_ref else \
+            Engine(dev, max_candidates=128, model="tree_adaptive")
         eng.load_weights(ada_sd)
         outs.append(eng.rollout(inp["I_0"][:1].to(dev), inp["I_g"][:1].to(dev), inp["z"].to(dev), images_shared=True, fresh=True))
         torch.cuda.synchronize()

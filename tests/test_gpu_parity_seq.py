@@ -128,8 +128,10 @@ def test_seq_tc_kernels_match_simt_verification_kernels(dev, seq_sd):
     from video_gcp_b200.engine import Engine
     inp = synthetic_seq_inputs(3, seed=35, shared_images=True)
     outs = []
+    from tests.verify_lib import verify_engine
     for use_ref in (True, False):
-        eng = Engine(dev, max_candidates=128, use_ref_kernels=use_ref, model="sequential")
+        eng = verify_engine(dev, max_candidates=128, model="sequential") if use_ref else \
+            Engine(dev, max_candidates=128, model="sequential")
         eng.load_weights(seq_sd)
         outs.append(eng.seq_rollout(inp["I_0"][:1].to(dev), inp["I_g"][:1].to(dev), inp["z"].to(dev),
                                     end_ind=inp["end_ind"].to(dev), images_shared=True, fresh=True))

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgcpb200.
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("max_candidates", C.c_int), ("attach_cost_mdl", C.c_int),
-                ("use_ref_kernels", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int)]
+                ("reserved0", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int)]
 
 
 MODEL_TREE, MODEL_SEQUENTIAL, MODEL_TREE_ADAPTIVE = 0, 1, 2
@@ -106,8 +106,18 @@ class GcpB200Error(RuntimeError):
     pass
 
 
+def bind(path):
+    """dlopen a build of the library and set the prototypes of every exported symbol."""
+    lib = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)            # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
 def load():
-    """dlopen the library and set the prototypes of every exported symbol."""
+    """The shipped library (one code path, no environment switches).  Raises when it has not been built."""
     global _LIB
     if _LIB is not None:
         return _LIB
@@ -115,15 +125,10 @@ def load():
         raise GcpB200Error(
             "libgcpb200.so not found at %s -- build it first (`make -C video_gcp_b200/csrc` or "
             "`__graft_entry__.build()`); this package has no CPU or PyTorch fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in EXPORTS.items():
-        fn = getattr(lib, name)            # AttributeError if a declared symbol is not exported
-        fn.restype = res
-        fn.argtypes = args
-    _LIB = lib
-    return lib
+    _LIB = bind(LIB_PATH)
+    return _LIB
 
 
-def check(rc):
+def check(rc, lib=None):
     if rc != 0:
-        raise GcpB200Error(load().gcpb200_last_error().decode())
+        raise GcpB200Error((lib if lib is not None else load()).gcpb200_last_error().decode())

@@ -10,6 +10,15 @@
 #include <string>
 #include <vector>
 
+// GCPB200_VERIFY (tests/cuda/libgcpb200_verify.so only, never the shipped library): compiles the SIMT verification
+// kernels (gemm_ref_kernel, dec_tail_ref_kernel, dec_tail_nll_kernel) and the GCPB200_* environment switches used for
+// A/B measurements.  Without it the library has one code path and reads no environment variable.
+#ifdef GCPB200_VERIFY
+#define GCP_VERIFY 1
+#else
+#define GCP_VERIFY 0
+#endif
+
 #include "../../include/gcpb200.h"
 #include "dec_tail3.cuh"
 #include "dtw_kernels.cuh"
@@ -42,6 +51,7 @@ extern "C" const char* gcpb200_version(void) { return "gcpb200 0.1.0 (sm_100a)";
 static const int DEPTH = 8, N_NODES = 255, N_SLOTS = 257;
 static const int NZ_ENC = 128, NZ_VAE = 256, NZ_MID = 128, HID = 512, N_LSTM = 3, STATE = 3072;
 static const int MAX_LEN = 200, INIT_MID = 32;
+static const int REFIT_SPLITS = 16;
 
 // ---------------------------------------------------------------------------------------------
 // device containers
@@ -84,7 +94,12 @@ struct LevelW {
 struct gcpb200_ctx {
     gcpb200_config cfg;
     int Bp_max = 0, sms = 0, slot_chunk = 64, max_cluster = 2;
-    bool use_ref = false, weights_loaded = false;
+#if GCP_VERIFY
+    bool use_ref = false;                     // verification build only: SIMT kernels instead of tcgen05
+#else
+    static constexpr bool use_ref = false;    // the shipped library has exactly one code path
+#endif
+    bool weights_loaded = false;
     int64_t launches = 0;
     std::vector<void*> allocs;
     // weights
@@ -121,6 +136,9 @@ struct gcpb200_ctx {
     long long* scratch_ei = nullptr;
     long long* scratch_given = nullptr;
     int* frame_node = nullptr;
+    unsigned long long* topk_sel = nullptr;   // elite selection: the k selected composite keys (grown on demand)
+    int topk_cap = 0;
+    double* refit_part = nullptr;             // refit: per-split (sum, sum of squares) [REFIT_SPLITS][255*256][2]
     // overlapped upload of host noise (gcpb200_rollout_io.z_host)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_start = nullptr, ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -189,12 +207,16 @@ static std::vector<TraceMark>& trace_marks() {
     return v;
 }
 static bool trace_on() {
+#if GCP_VERIFY
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("GCPB200_TRACE");
         on = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return on == 1;
+#else
+    return false;
+#endif
 }
 static void trace_mark(cudaStream_t st, const char* name) {
     if (!trace_on()) return;
@@ -866,12 +888,16 @@ static EpiParams epi_linear(int act, bf16* ob, int ob_ld, float* of, int of_ld, 
 // The whole body (in + 3 GroupNorm layers) as one mlp_fused_kernel launch; result in c->tb like the unfused path.
 // GCPB200_NO_FUSED_MLP=1 keeps the four-launch path (A/B measurements).
 static bool fused_mlp_enabled() {
+#if GCP_VERIFY
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("GCPB200_NO_FUSED_MLP");
         on = (e != nullptr && e[0] == '1') ? 0 : 1;
     }
     return on == 1;
+#else
+    return true;
+#endif
 }
 static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
     static bool configured_dev[64] = {false};     // function attributes are per device
@@ -973,7 +999,15 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     gcpb200_ctx* c = new gcpb200_ctx();
     c->cfg = *cfg;
     c->sms = prop.multiProcessorCount;
-    c->use_ref = cfg->use_ref_kernels != 0;
+#if GCP_VERIFY
+    c->use_ref = cfg->reserved0 != 0;
+#else
+    if (cfg->reserved0 != 0) {
+        gcp_set_error("gcpb200_create: reserved0 must be 0");
+        delete c;
+        return -1;
+    }
+#endif
     c->Bp_max = (cfg->max_candidates + 127) / 128 * 128;
     c->slot_chunk = cfg->decoder_slot_chunk > 0 ? cfg->decoder_slot_chunk : 64;
     c->model = cfg->model;
@@ -986,8 +1020,10 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     // latent rows are [slot][candidate]: tree = start, 255 in-order nodes, goal; sequential = frames 0..199, goal
     c->n_slots = is_seq ? MAX_LEN + 1 : N_SLOTS;
     c->lstm_hid = is_seq ? 2 * HID : HID;
+#if GCP_VERIFY
     if (const char* e = getenv("GCPB200_GEMM_CLUSTER")) c->max_cluster = atoi(e) > 0 ? atoi(e) : 1;
     if (const char* e = getenv("GCPB200_SEQ_GRAPH")) c->seq_graph_on = atoi(e) != 0;
+#endif
     const size_t Bp = c->Bp_max, NL = is_seq ? Bp : 128 * Bp, NS = (size_t)c->n_slots * Bp, ND = 256 * Bp;
     int rc = 0;
     rc |= dalloc(c, &c->lat_f32, NS * NZ_ENC);
@@ -1029,6 +1065,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->scratch_ei, 8);
     rc |= dalloc(c, &c->scratch_given, Bp);
     rc |= dalloc(c, &c->frame_node, Bp * 256);
+    rc |= dalloc(c, &c->refit_part, (size_t)REFIT_SPLITS * N_NODES * NZ_VAE * 2, false);
     if (rc) {
         gcpb200_destroy(c);
         return -1;
@@ -1061,8 +1098,10 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         e = cudaFuncSetAttribute(dec_tail3_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail3_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES);
+#if GCP_VERIFY
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dec_tail_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * DT_PLANE_BYTES + 128);
+#endif
     if (e != cudaSuccess) {
         gcp_set_error("cudaFuncSetAttribute(dec_tail) failed: %s", cudaGetErrorString(e));
         gcpb200_destroy(c);
@@ -1083,6 +1122,7 @@ extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
     for (int i = 0; i < 5; ++i)
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     for (void* p : c->allocs) cudaFree(p);
+    if (c->topk_sel) cudaFree(c->topk_sel);
     delete c;
 }
 
@@ -1305,6 +1345,7 @@ static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int
             c->prof_tail_images += (long long)ns * B;
             ++c->prof_tail_launches;
         }
+#if GCP_VERIFY
         if (c->use_ref) {
             DecTailArgs a;
             memset(&a, 0, sizeof(a));
@@ -1313,7 +1354,9 @@ static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int
             a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
             a.head = pc; a.src0 = I_0; a.srcg = I_g; a.src_stride = images_shared ? 0 : 3072;
             dec_tail_ref_kernel<<<ns * B, 256, 6 * DT_PLANE_BYTES + 128, st>>>(a, c->w4p, c->w5p);
-        } else {
+        } else
+#endif
+        {
             DecTail3Args a;
             memset(&a, 0, sizeof(a));
             a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = images_shared ? 0 : 256 * 64;
@@ -1509,6 +1552,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         // 8 k outstanding 16-byte reads.  Reads beyond that queue inside the GPU's memory system and slow the tensor-core
         // kernels of the rollout stream (12-16 k outstanding: GEMMs and decoder 1.5x slower; 19 k: they stall until the
         // upload ends), fewer leave PCIe idle.  64 blocks x 32 threads x 4 reads in flight = 8192.
+#if GCP_VERIFY
         static int up_grid = 0, up_block = 0;
         if (up_grid == 0) {
             const char* eg = getenv("GCPB200_UPLOAD_GRID");
@@ -1520,6 +1564,9 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
                 up_block = 32;
             }
         }
+#else
+        const int up_grid = 64, up_block = 32;
+#endif
         for (int i = 0; i < 5; ++i) {
             upload_rows_kernel<<<up_grid, up_block, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
                                                                       reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
@@ -1660,7 +1707,10 @@ static int ensure_train_ws(gcpb200_ctx* c) {
     rc |= dalloc(c, &w.exist_df, Bc * N_NODES);
     rc |= dalloc(c, &w.cost_tgt, Bc);
     if (rc) return -1;
-    cudaError_t e = cudaFuncSetAttribute(dec_tail_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+#if GCP_VERIFY
+    e = cudaFuncSetAttribute(dec_tail_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES);
+#endif
     if (e != cudaSuccess) {
         gcp_set_error("cudaFuncSetAttribute(dec_tail_nll_kernel) failed: %s", cudaGetErrorString(e));
         return -1;
@@ -1861,8 +1911,9 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
         if (io->cost_pred) GCP_CUDA_CHECK(cudaMemcpyAsync(io->cost_pred, w.cost_pred, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         // ---- 8. reconstruction NLL of every real frame under the node bound to it, KL, scalar losses
         float* nll_bt = io->nll_per_frame ? io->nll_per_frame : w.nll_bt;
-        if (c->use_ref || c->z5m == nullptr) {
-            // SIMT path (verification mode): decoder tail + NLL of one frame per block
+#if GCP_VERIFY
+        if (c->use_ref) {
+            // SIMT path (verification build): decoder tail + NLL of one frame per block
             TailNllArgs ta;
             memset(&ta, 0, sizeof(ta));
             ta.x3 = w.x3.p; ta.skip_up = c->skip_up; ta.w4p = c->w4p; ta.w5p = c->w5p; ta.b4 = c->b4; ta.b5 = c->b5;
@@ -1870,7 +1921,9 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
             ta.Bp = Bp; ta.T = T; ta.lcap = MAX_LEN; ta.root_node = (1 << (DEPTH - 1)) - 1; ta.nll_bt = nll_bt;
             dec_tail_nll_kernel<<<B * T, 256, TN_SMEM_BYTES, st>>>(ta);
             LAUNCH_CHECK();
-        } else {
+        } else
+#endif
+        {
             // tcgen05 path: per 64-node chunk the tail kernel runs twice with the raw head (15 mixture-mean logits, 15
             // log-scales; fp32 [seq][node][pixel][16]), then one block per frame evaluates the mixture NLL of the frame
             // under the node bound to it.  All 255 nodes are decoded (half of them are bound to a frame); at 21 ns per
@@ -2255,7 +2308,19 @@ extern "C" int gcpb200_topk(gcpb200_ctx* c, const float* cost, int N, int k, int
         gcp_set_error("gcpb200_topk: bad arguments (N %d, k %d)", N, k);
         return -1;
     }
-    topk_rank_kernel<<<(N + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cost, N, k, idx, val);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (k > c->topk_cap) {
+        // rare (first call / larger k): cudaFree synchronises the device, so no in-flight kernel still reads the old array
+        if (c->topk_sel) GCP_CUDA_CHECK(cudaFree(c->topk_sel));
+        c->topk_sel = nullptr;
+        c->topk_cap = 0;
+        const int cap = std::max(k, 8192);
+        GCP_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->topk_sel), (size_t)cap * sizeof(unsigned long long)));
+        c->topk_cap = cap;
+    }
+    topk_select_kernel<<<1, TOPK_SELECT_THREADS, 0, st>>>(cost, N, k, c->topk_sel);
+    LAUNCH_CHECK();
+    topk_rank_kernel<<<(k + 255) / 256, 256, 0, st>>>(c->topk_sel, k, cost, idx, val);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2266,8 +2331,12 @@ extern "C" int gcpb200_refit(gcpb200_ctx* c, const float* z, const int32_t* elit
         gcp_set_error("gcpb200_refit: bad arguments");
         return -1;
     }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int per = N_NODES * NZ_VAE;
-    refit_kernel<<<(per + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, elite_idx, k, per, mean, stdv);
+    const int S = std::max(1, std::min(REFIT_SPLITS, k / 8));
+    refit_partial_kernel<<<dim3((per / 4 + 127) / 128, S), 128, 0, st>>>(z, elite_idx, k, per, c->refit_part);
+    LAUNCH_CHECK();
+    refit_final_kernel<<<(per + 255) / 256, 256, 0, st>>>(z, elite_idx, k, per, S, c->refit_part, mean, stdv);
     LAUNCH_CHECK();
     return 0;
 }

@@ -112,6 +112,7 @@ __device__ __forceinline__ void dt_build_up(uint8_t* in4, const bf16* x3row, int
 // SIMT verification kernel: same inputs / outputs / rounding points, direct convolution.
 // w4p [16][32][4][4], w5p [32][16][4][4] are the plain-layout bf16 weights.
 // ---------------------------------------------------------------------------------------------
+#ifdef GCPB200_VERIFY
 __global__ void __launch_bounds__(256) dec_tail_ref_kernel(const __grid_constant__ DecTailArgs a, const bf16* w4p,
                                                            const bf16* w5p) {
     extern __shared__ uint8_t smem_raw[];
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(256) dec_tail_ref_kernel(const __grid_constant
         for (int k = 0; k < 3; ++k) img[k * 1024 + y * 32 + x] = rgb[k] * 0.4f - 1.0f;
     }
 }
+#endif
 
 // per-candidate skip preparation: s0 [Bp][16][16][16] fp32 (NCHW) -> up-sampled, padded, bf16 planes
 __global__ void skip_prep_kernel(const float* __restrict__ s0, bf16* __restrict__ skip_up, int n_cand) {

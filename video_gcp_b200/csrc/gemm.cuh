@@ -603,8 +603,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// SIMT verification kernel (same args, same epilogue)
+// SIMT verification kernel (same args, same epilogue); GCPB200_VERIFY builds only
 // ---------------------------------------------------------------------------------------------
+#ifdef GCPB200_VERIFY
 template <int EPI>
 __global__ void __launch_bounds__(128) gemm_ref_kernel(const __grid_constant__ GemmArgs args, int BN) {
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
@@ -629,5 +630,6 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(const __grid_constant__ G
         epilogue_chunk<EPI>(args.epi, args.g, row, n0, acc);
     }
 }
+#endif
 
 }  // namespace gcp

@@ -67,12 +67,16 @@ inline int& gemm_pdl_suspended() {
     return s;
 }
 inline bool gemm_pdl_enabled() {
+#ifdef GCPB200_VERIFY
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("GCPB200_NO_PDL");
         on = (e != nullptr && e[0] == '1') ? 0 : 1;
     }
     return on == 1 && gemm_pdl_suspended() == 0;
+#else
+    return gemm_pdl_suspended() == 0;
+#endif
 }
 
 template <int BN, int EPI>
@@ -122,6 +126,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster)
     return 0;
 }
 
+#ifdef GCPB200_VERIFY
 template <int EPI>
 int launch_gemm_ref(const GemmArgs& a, int BN, cudaStream_t st) {
     dim3 grid(a.rows / GEMM_BM, a.N / BN);
@@ -129,9 +134,11 @@ int launch_gemm_ref(const GemmArgs& a, int BN, cudaStream_t st) {
     GCP_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+#endif
 
-// dispatch on (BN, EPI, use_ref)
+// dispatch on (BN, EPI); use_ref selects the SIMT verification kernels, which only the GCPB200_VERIFY build contains
 inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStream_t st, int num_sms, int cluster = 1) {
+#ifdef GCPB200_VERIFY
     if (use_ref) {
         switch (epi) {
             case EPI_LINEAR: return launch_gemm_ref<EPI_LINEAR>(a, BN, st);
@@ -139,7 +146,10 @@ inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStr
             case EPI_REPARAM: return launch_gemm_ref<EPI_REPARAM>(a, BN, st);
             case EPI_LSTM: return launch_gemm_ref<EPI_LSTM>(a, BN, st);
         }
-    } else if (BN == 128) {
+    }
+#endif
+    (void)use_ref;
+    if (BN == 128) {
         switch (epi) {
             case EPI_LINEAR: return launch_gemm_tc<128, EPI_LINEAR>(a, st, num_sms, cluster);
             case EPI_GN: return launch_gemm_tc<128, EPI_GN>(a, st, num_sms, cluster);

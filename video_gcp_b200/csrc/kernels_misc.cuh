@@ -304,50 +304,166 @@ __global__ void cost_sum_kernel(const float* __restrict__ rowcost, const long lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Elite selection (gcp/planning/cem/cem_planner.py:124-135): the k lowest costs in ascending order.
-// Rank by counting (stable: ties broken by index), O(N^2) compares spread over the whole chip; for
-// N = 65536 that is 4.3 G compares, well under a millisecond, and exact / deterministic.
+// Elite selection (gcp/planning/cem/cem_planner.py:124-135): `scores.argsort()[:k]`, the k lowest costs in ascending
+// order.  Two launches, exact and deterministic, O(N) + O(k^2 / chip):
+//   1. topk_select_kernel (one CTA): MSB-first radix select (8 bits per pass, warp-aggregated shared-memory
+//      histograms: __match_any_sync groups the lanes of a warp by bin, one atomic per group) of the k-th smallest
+//      64-bit composite key (order-preserving cost bits << 32 | index), then an ordered ballot / prefix-sum
+//      compaction of the k composites that are <= it.
+//   2. topk_rank_kernel: rank of every selected composite among the k by counting (tiles in shared memory) -> its
+//      output position.
+// Order rule = numpy's: ascending, every NaN after +inf, -0.0 == +0.0; ties (numpy's quicksort leaves them
+// unspecified) are broken by index, so every rank of a sharded planner selects the same elites.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) topk_rank_kernel(const float* __restrict__ cost, int n, int k,
-                                                        int* __restrict__ idx_out, float* __restrict__ val_out) {
-    __shared__ float tile[1024];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const float ci = i < n ? cost[i] : INFINITY;
-    int rank = 0;
-    for (int base = 0; base < n; base += 1024) {
-        for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = base + t < n ? cost[base + t] : INFINITY;
+__device__ __forceinline__ unsigned long long topk_composite(float x, int i) {
+    uint32_t key;
+    if (x != x) {
+        key = 0xFFFFFFFFu;                       // NaN sorts last
+    } else {
+        const uint32_t b = __float_as_uint(x + 0.0f);      // -0.0 + 0.0 = +0.0
+        key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    }
+    return ((unsigned long long)key << 32) | (uint32_t)i;
+}
+
+constexpr int TOPK_SELECT_THREADS = 1024;
+__global__ void __launch_bounds__(TOPK_SELECT_THREADS) topk_select_kernel(const float* __restrict__ cost, int n, int k,
+                                                                          unsigned long long* __restrict__ sel) {
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem;
+    __shared__ int wsum[TOPK_SELECT_THREADS / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_prefix = 0ull; s_krem = k; s_base = 0; }
+    unsigned long long mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        const int lim = min(1024, n - base);
-        for (int t = 0; t < lim; ++t) {
-            const float cj = tile[t];
-            rank += (cj < ci) || (cj == ci && base + t < i);
+        const unsigned long long prefix = s_prefix;
+        for (int i0 = 0; i0 < n; i0 += TOPK_SELECT_THREADS) {
+            const int i = i0 + tid;
+            int bin = -1;
+            if (i < n) {
+                const unsigned long long c = topk_composite(cost[i], i);
+                if ((c & mask) == prefix) bin = (int)((c >> shift) & 255ull);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // 8 bins per lane: inclusive warp scan of the lane totals, then the lane that crosses k_rem picks its bin
+            int h[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = hist[lane * 8 + q]; tot += h[q]; }
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int krem = s_krem, before = inc - tot;
+            if (before < krem && krem <= inc) {
+                int cum = before;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (cum < krem && krem <= cum + h[q]) {
+                        s_prefix = prefix | ((unsigned long long)(lane * 8 + q) << shift);
+                        s_krem = krem - cum;
+                    }
+                    cum += h[q];
+                }
+            }
+        }
+        mask |= 255ull << shift;
+        __syncthreads();
+    }
+    // composites are unique, so exactly k of them are <= the k-th smallest: compact them in index order
+    const unsigned long long kth = s_prefix;
+    for (int i0 = 0; i0 < n; i0 += TOPK_SELECT_THREADS) {
+        const int i = i0 + tid;
+        const unsigned long long c = i < n ? topk_composite(cost[i], i) : ~0ull;
+        const bool take = i < n && c <= kth;
+        const unsigned b = __ballot_sync(0xffffffffu, take);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (take) sel[off + __popc(b & ((1u << lane) - 1u))] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < TOPK_SELECT_THREADS / 32; ++w) t += wsum[w];
+            s_base += t;
         }
         __syncthreads();
     }
-    if (i < n && rank < k) {
-        idx_out[rank] = i;
-        if (val_out != nullptr) val_out[rank] = ci;
+}
+
+__global__ void __launch_bounds__(256) topk_rank_kernel(const unsigned long long* __restrict__ sel, int k,
+                                                        const float* __restrict__ cost, int* __restrict__ idx_out,
+                                                        float* __restrict__ val_out) {
+    __shared__ unsigned long long tile[1024];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const unsigned long long ci = i < k ? sel[i] : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < k; base += 1024) {
+        for (int t = threadIdx.x; t < 1024; t += 256) tile[t] = base + t < k ? sel[base + t] : ~0ull;
+        __syncthreads();
+        const int lim = min(1024, k - base);
+#pragma unroll 8
+        for (int t = 0; t < lim; ++t) rank += tile[t] < ci;
+        __syncthreads();
+    }
+    if (i < k) {
+        const int id = (int)(uint32_t)ci;
+        idx_out[rank] = id;
+        if (val_out != nullptr) val_out[rank] = cost[id];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Refit (gcp/planning/cem/sampler.py:44-46): mean / std (ddof 0) over the elite samples per (node, dim).
-// Thread per output element, elites streamed with coalesced reads; fp64 accumulation like numpy.
+// Refit (gcp/planning/cem/sampler.py:44-46): mean / std (ddof 0) over the elite samples per (node, dim), float64
+// accumulation like numpy.  HBM-bound: k elite rows of `per_cand` floats are read exactly once (float4, coalesced);
+// the k elites are split over gridDim.y CTAs per column block so that the whole chip streams, and every split writes
+// its (sum d, sum d^2) of the shifted values d = x - x_first (exact in float64; identical elites give std == 0
+// exactly) to `part`; refit_final_kernel adds the splits in a fixed order.
 // ---------------------------------------------------------------------------------------------
-__global__ void refit_kernel(const float* __restrict__ z, const int* __restrict__ elite, int k, int per_cand,
-                             float* __restrict__ mean, float* __restrict__ stdv) {
+__global__ void __launch_bounds__(128) refit_partial_kernel(const float* __restrict__ z, const int* __restrict__ elite, int k,
+                                                            int per_cand, double* __restrict__ part) {
+    const int e4 = blockIdx.x * blockDim.x + threadIdx.x;        // float4 column
+    if (e4 >= per_cand / 4) return;
+    const int S = gridDim.y, s = blockIdx.y;
+    const int i0 = (int)((long long)k * s / S), i1 = (int)((long long)k * (s + 1) / S);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(z + (size_t)elite[0] * per_cand) + e4);
+    double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(z + (size_t)elite[i] * per_cand) + e4);
+        const double d0 = (double)v.x - (double)x0.x, d1 = (double)v.y - (double)x0.y;
+        const double d2 = (double)v.z - (double)x0.z, d3 = (double)v.w - (double)x0.w;
+        a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
+        q[0] = fma(d0, d0, q[0]); q[1] = fma(d1, d1, q[1]); q[2] = fma(d2, d2, q[2]); q[3] = fma(d3, d3, q[3]);
+    }
+    double* o = part + ((size_t)s * per_cand + (size_t)e4 * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = a[j]; o[2 * j + 1] = q[j]; }
+}
+__global__ void refit_final_kernel(const float* __restrict__ z, const int* __restrict__ elite, int k, int per_cand, int S,
+                                   const double* __restrict__ part, float* __restrict__ mean, float* __restrict__ stdv) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= per_cand) return;
-    double s = 0.0;
-    for (int i = 0; i < k; ++i) s += (double)__ldg(z + (size_t)elite[i] * per_cand + e);
-    const double m = s / k;
-    double q = 0.0;
-    for (int i = 0; i < k; ++i) {
-        const double d = (double)__ldg(z + (size_t)elite[i] * per_cand + e) - m;
-        q += d * d;
+    double a = 0.0, q = 0.0;
+    for (int s = 0; s < S; ++s) {
+        a += part[((size_t)s * per_cand + e) * 2];
+        q += part[((size_t)s * per_cand + e) * 2 + 1];
     }
-    mean[e] = (float)m;
-    stdv[e] = (float)sqrt(q / k);
+    const double x0 = (double)__ldg(z + (size_t)elite[0] * per_cand + e);
+    const double md = a / k;
+    const double var = q / k - md * md;
+    mean[e] = (float)(x0 + md);
+    stdv[e] = (float)sqrt(var > 0.0 ? var : 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -542,6 +542,7 @@ constexpr int TN_SMEM_BYTES = 6 * DT_PLANE_BYTES + (TN_W4_FLOATS + TN_W5_FLOATS)
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+#ifdef GCPB200_VERIFY
 __global__ void __launch_bounds__(256) dec_tail_nll_kernel(const __grid_constant__ TailNllArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* in4 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(256) dec_tail_nll_kernel(const __grid_constant
     const double s = block_sum_d(nll_sum, red);
     if (tid == 0) a.nll_bt[blockIdx.x] = (float)(s * (double)pad);
 }
+#endif
 
 // Reconstruction NLL from the raw head outputs of the tcgen05 tail kernel (dec_tail3_raw_kernel run twice: mixture
 // means, log-scales): the same arithmetic as the second half of dec_tail_nll_kernel.  One block per (sequence, frame);

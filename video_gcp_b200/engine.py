@@ -24,11 +24,13 @@ def _stream():
 class Engine:
     """One context = one device.  Not thread-safe (same as the reference model object)."""
 
-    def __init__(self, device, max_candidates=1024, attach_cost_mdl=False, use_ref_kernels=False,
-                 decoder_slot_chunk=0, model="tree"):
+    def __init__(self, device, max_candidates=1024, attach_cost_mdl=False, decoder_slot_chunk=0, model="tree",
+                 lib=None, reserved0=0):
+        """lib / reserved0: test hooks -- tests/verify_lib.py passes the separately built verification library
+        (tests/cuda/libgcpb200_verify.so) and its SIMT cross-check switch; the product never sets them."""
         if not torch.cuda.is_available():
             raise _C.GcpB200Error("video_gcp_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
-        self.lib = _C.load()
+        self.lib = lib if lib is not None else _C.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _C.GcpB200Error("Engine device must be a CUDA device, got %s" % device)
@@ -37,14 +39,17 @@ class Engine:
         self.attach_cost_mdl = bool(attach_cost_mdl)
         self.model = model
         kind = {"tree": _C.MODEL_TREE, "sequential": _C.MODEL_SEQUENTIAL, "tree_adaptive": _C.MODEL_TREE_ADAPTIVE}[model]
-        cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(use_ref_kernels),
+        cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(reserved0),
                         int(decoder_slot_chunk), kind)
         h = C.c_void_p()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
+            self._check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
         self.h = h
         self.weights_loaded = False
         self._bufs = {}          # persistent output buffers (no allocator traffic on the hot path)
+
+    def _check(self, rc):
+        _C.check(rc, self.lib)
 
     def _buf(self, name, shape, dtype=torch.float32):
         """Output buffer reused across calls: contents are valid until the next call that writes `name`."""
@@ -83,7 +88,7 @@ class Engine:
             arr.append(_C.Tensor(k.encode(), C.c_void_p(t.data_ptr()), t.dim(), shape))
         tens = (_C.Tensor * len(arr))(*arr)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_load_weights(self.h, tens, len(arr)))
+            self._check(self.lib.gcpb200_load_weights(self.h, tens, len(arr)))
         self.weights_loaded = True
 
     # ------------------------------------------------------------------------------------------
@@ -143,7 +148,7 @@ class Engine:
             _ptr(out.get("regressed_state")), _ptr(out.get("distances")), _ptr(out.get("pruned_nodes")),
             _ptr(out.get("pruned_len")), float(prune_threshold))
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
+            self._check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
         return out
 
     def seq_rollout(self, I_0, I_g, z, end_ind=None, given_end_ind=None, seed=0, images_shared=False, want_images=True,
@@ -182,16 +187,24 @@ class Engine:
             _ptr(out["encodings"]), _ptr(out.get("mu")), _ptr(out.get("log_sigma")), _ptr(out.get("images")),
             _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")), _ptr(out.get("regressed_state")))
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_seq_rollout(self.h, C.byref(io), _stream()))
+            self._check(self.lib.gcpb200_seq_rollout(self.h, C.byref(io), _stream()))
         return out
 
-    def cost_l2_seq(self, images, end_ind, goal, dense=True, final_step_weight=1.0):
+    def _cost_out(self, out, B):
+        """Destination of a [B] cost vector: the caller's `out` (contiguous fp32 on this device; e.g. a slice of a larger
+        vector when a planner rolls out in chunks) or the persistent buffer the next cost call overwrites."""
+        if out is None:
+            return self._buf("cost_l2", (B,))
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B,)
+        return out
+
+    def cost_l2_seq(self, images, end_ind, goal, dense=True, final_step_weight=1.0, out=None):
         """L2 image cost over time-ordered image sequences images [B,n_frames,3,32,32] cut at end_ind."""
         B, n_frames = images.shape[:2]
-        cost = self._buf("cost_l2", (B,))
+        cost = self._cost_out(out, B)
         goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cost_l2_seq(self.h, _ptr(images), int(n_frames), _ptr(end_ind.contiguous()), _ptr(goal), B,
+            self._check(self.lib.gcpb200_cost_l2_seq(self.h, _ptr(images), int(n_frames), _ptr(end_ind.contiguous()), _ptr(goal), B,
                                                   int(dense), float(final_step_weight), _ptr(cost), _stream()))
         return cost
 
@@ -202,16 +215,16 @@ class Engine:
         D = flat.shape[2]
         dst = torch.empty(B, N_NODES, D, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_gather_nodes(self.h, _ptr(flat), _ptr(nodes.contiguous()), _ptr(length.contiguous()), B, D,
+            self._check(self.lib.gcpb200_gather_nodes(self.h, _ptr(flat), _ptr(nodes.contiguous()), _ptr(length.contiguous()), B, D,
                                                    _ptr(dst), _stream()))
         return dst
 
-    def cost_l2_nodes(self, images_df, nodes, length, goal, dense=True, final_step_weight=1.0):
+    def cost_l2_nodes(self, images_df, nodes, length, goal, dense=True, final_step_weight=1.0, out=None):
         B = images_df.shape[0]
-        cost = self._buf("cost_l2", (B,))
+        cost = self._cost_out(out, B)
         goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cost_l2_nodes(self.h, _ptr(images_df), _ptr(nodes.contiguous()), _ptr(length.contiguous()),
+            self._check(self.lib.gcpb200_cost_l2_nodes(self.h, _ptr(images_df), _ptr(nodes.contiguous()), _ptr(length.contiguous()),
                                                     _ptr(goal), B, int(dense), float(final_step_weight), _ptr(cost), _stream()))
         return cost
 
@@ -222,24 +235,24 @@ class Engine:
         D = flat.shape[2]
         dst = torch.empty(B, MAX_LEN, D, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_prune_gather(self.h, _ptr(flat), _ptr(end_ind.contiguous()), B, D, _ptr(dst), _stream()))
+            self._check(self.lib.gcpb200_prune_gather(self.h, _ptr(flat), _ptr(end_ind.contiguous()), B, D, _ptr(dst), _stream()))
         return dst
 
-    def cost_l2(self, images_df, end_ind, goal, dense=True, final_step_weight=1.0):
+    def cost_l2(self, images_df, end_ind, goal, dense=True, final_step_weight=1.0, out=None):
         B = images_df.shape[0]
-        cost = self._buf("cost_l2", (B,))
+        cost = self._cost_out(out, B)
         goal = goal.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cost_l2(self.h, _ptr(images_df), _ptr(end_ind.contiguous()), _ptr(goal), B, int(dense),
+            self._check(self.lib.gcpb200_cost_l2(self.h, _ptr(images_df), _ptr(end_ind.contiguous()), _ptr(goal), B, int(dense),
                                               float(final_step_weight), _ptr(cost), _stream()))
         return cost
 
-    def cost_learned(self, e_df, end_ind, goal_seq):
+    def cost_learned(self, e_df, end_ind, goal_seq, out=None):
         B = e_df.shape[0]
-        cost = torch.empty(B, device=self.device, dtype=torch.float32)
+        cost = torch.empty(B, device=self.device, dtype=torch.float32) if out is None else self._cost_out(out, B)
         goal_seq = goal_seq.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cost_learned(self.h, _ptr(e_df), _ptr(end_ind.contiguous()), B, _ptr(goal_seq),
+            self._check(self.lib.gcpb200_cost_learned(self.h, _ptr(e_df), _ptr(end_ind.contiguous()), B, _ptr(goal_seq),
                                                    goal_seq.shape[0], _ptr(cost), _stream()))
         return cost
 
@@ -257,7 +270,7 @@ class Engine:
             n_seg = int(seg_off.shape[0]) - 1
         cost = torch.empty(n_seg if seg_off is not None else n, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cost_pairs(self.h, _ptr(lat), _ptr(idx1), _ptr(idx2), n, _ptr(seg_off), n_seg,
+            self._check(self.lib.gcpb200_cost_pairs(self.h, _ptr(lat), _ptr(idx1), _ptr(idx2), n, _ptr(seg_off), n_seg,
                                                  _ptr(cost), _stream()))
         return cost
 
@@ -270,7 +283,7 @@ class Engine:
         action = torch.empty(n, 2, **f32)
         enc = torch.empty(n, NZ_ENC, **f32) if want_enc else None
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_infer_action(self.h, _ptr(img), _ptr(target_latent), n, _ptr(action), _ptr(enc),
+            self._check(self.lib.gcpb200_infer_action(self.h, _ptr(img), _ptr(target_latent), n, _ptr(action), _ptr(enc),
                                                    _stream()))
         return (action, enc) if want_enc else action
 
@@ -279,14 +292,14 @@ class Engine:
         idx = torch.empty(k, device=self.device, dtype=torch.int32)
         val = torch.empty(k, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_topk(self.h, _ptr(cost.contiguous()), N, k, _ptr(idx), _ptr(val), _stream()))
+            self._check(self.lib.gcpb200_topk(self.h, _ptr(cost.contiguous()), N, k, _ptr(idx), _ptr(val), _stream()))
         return idx, val
 
     def refit(self, z, elite_idx):
         mean = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
         std = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_refit(self.h, _ptr(z), _ptr(elite_idx.contiguous()), elite_idx.shape[0], _ptr(mean),
+            self._check(self.lib.gcpb200_refit(self.h, _ptr(z), _ptr(elite_idx.contiguous()), elite_idx.shape[0], _ptr(mean),
                                             _ptr(std), _stream()))
         return mean, std
 
@@ -294,7 +307,7 @@ class Engine:
                      out=None):
         z = out if out is not None else torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_sample_noise(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
+            self._check(self.lib.gcpb200_sample_noise(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
                                                    int(first_candidate_id), int(n), float(min(clip, 3.0e38)), _ptr(z),
                                                    _stream()))
         return z
@@ -304,7 +317,7 @@ class Engine:
         n = ids.shape[0]
         z = torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_sample_noise_ids(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
+            self._check(self.lib.gcpb200_sample_noise_ids(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
                                                        _ptr(ids.contiguous()), int(n), float(min(clip, 3.0e38)), _ptr(z),
                                                        _stream()))
         return z
@@ -353,7 +366,7 @@ class Engine:
             setattr(io, k, _ptr(v))
         self._train_refs = ins            # keep inputs alive until the (stream-ordered) call has run
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_forward_loss(self.h, C.byref(io), _stream()))
+            self._check(self.lib.gcpb200_forward_loss(self.h, C.byref(io), _stream()))
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -366,7 +379,7 @@ class Engine:
         assert y.shape[0] == B and y.shape[2] == dim, (x.shape, y.shape)
         out = self._buf("cdist", (B, n, y.shape[1]))
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_cdist_mean(self.h, _ptr(x), _ptr(y), B, n, y.shape[1], dim, _ptr(out), _stream()))
+            self._check(self.lib.gcpb200_cdist_mean(self.h, _ptr(x), _ptr(y), B, n, y.shape[1], dim, _ptr(out), _stream()))
         self._dtw_refs = (x, y)
         return out
 
@@ -383,7 +396,7 @@ class Engine:
         if want_bf:
             out["w_bf"] = self._buf("soft_dtw_w_bf", (B, r, c))
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_soft_dtw(self.h, _ptr(cost), float(temp), _ptr(ei), B, r, c, _ptr(ws), _ptr(out["w"]),
+            self._check(self.lib.gcpb200_soft_dtw(self.h, _ptr(cost), float(temp), _ptr(ei), B, r, c, _ptr(ws), _ptr(out["w"]),
                                                _ptr(out.get("w_bf")), _ptr(out["rowsum_max"]), _stream()))
         self._dtw_refs = (cost, ei)
         if want_tables:
@@ -405,7 +418,7 @@ class Engine:
         if want_matches:
             out["match_inds"] = self._buf("dtw_match", (B, c), i32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_dtw(self.h, _ptr(cost), int(f64), _ptr(ei), B, r, c, _ptr(out["acc"]), _ptr(out["dist"]),
+            self._check(self.lib.gcpb200_dtw(self.h, _ptr(cost), int(f64), _ptr(ei), B, r, c, _ptr(out["acc"]), _ptr(out["dist"]),
                                           _ptr(out["path_p"]), _ptr(out["path_q"]), _ptr(out["path_len"]),
                                           _ptr(out.get("match_inds")), _stream()))
         self._dtw_refs = (cost, ei)
@@ -418,7 +431,7 @@ class Engine:
         row = src[0].numel()
         out = torch.empty((idx.shape[0],) + tuple(src.shape[1:]), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_gather_rows(self.h, _ptr(src), _ptr(idx), idx.shape[0], row, _ptr(out), _stream()))
+            self._check(self.lib.gcpb200_gather_rows(self.h, _ptr(src), _ptr(idx), idx.shape[0], row, _ptr(out), _stream()))
         return out
 
     def launch_count(self):
@@ -427,14 +440,14 @@ class Engine:
     PHASES = ("encoder_length", "tree_recursion", "decoder_gemm", "decoder_tail", "heads", "rollout_total")
 
     def profile_enable(self, on=True):
-        _C.check(self.lib.gcpb200_profile_enable(self.h, int(on)))
+        self._check(self.lib.gcpb200_profile_enable(self.h, int(on)))
 
     def profile_read(self):
         """dict phase -> ms accumulated since the last read, plus decoder-tail image / launch counts."""
         ms = (C.c_double * 6)()
         imgs, launches = C.c_int64(), C.c_int64()
         with torch.cuda.device(self.index):
-            _C.check(self.lib.gcpb200_profile_read(self.h, ms, C.byref(imgs), C.byref(launches)))
+            self._check(self.lib.gcpb200_profile_read(self.h, ms, C.byref(imgs), C.byref(launches)))
         out = {k: ms[i] for i, k in enumerate(self.PHASES)}
         out["tail_images"], out["tail_launches"] = imgs.value, launches.value
         return out

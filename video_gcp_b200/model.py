@@ -145,7 +145,7 @@ class _GCPModelBase(nn.Module):
     def _make_dense_rec(self):
         raise NotImplementedError
 
-    def __init__(self, params, logger=None, max_candidates=1024, use_ref_kernels=False):
+    def __init__(self, params, logger=None, max_candidates=1024):
         super().__init__()
         self._logger = logger
         self._hp = build_hparams(params)
@@ -165,7 +165,6 @@ class _GCPModelBase(nn.Module):
         self._canonical_keys = list(canon.keys())
         self.device = torch.device("cpu")
         self._max_candidates = max_candidates
-        self._use_ref_kernels = use_ref_kernels
         self._engine = None
         self._dirty = True
         self._val_mode = False
@@ -194,7 +193,7 @@ class _GCPModelBase(nn.Module):
             if dev.type != "cuda":
                 dev = next(self.parameters()).device
             self._engine = Engine(dev, self._max_candidates, attach_cost_mdl=self._hp.attach_cost_mdl,
-                                  use_ref_kernels=self._use_ref_kernels, model=self.ENGINE_KIND)
+                                  model=self.ENGINE_KIND)
             self._dirty = True
         if self._dirty:
             sd = {k: v for k, v in nn.Module.state_dict(self).items() if k in set(self._canonical_keys)}
@@ -359,7 +358,10 @@ class TreeModel(_GCPModelBase):
         outputs.aux_indices = aux
         outputs.eps = eps
         outputs["_train_losses"] = res["losses"].clone()      # the engine's buffer is overwritten by the next call
-        outputs["_nll_per_frame"], outputs["_kl_per_seq"] = res["nll_per_frame"], res["kl_per_seq"]
+        # the per-frame / per-sequence breakdowns are small: own copies, so a validation forward before logging does not
+        # change the previous step's `losses.*.breakdown`.  Every other field above is a VIEW of an engine buffer that
+        # the next forward of this model overwrites (same lifetime rule as the rollout outputs, see Engine.rollout)
+        outputs["_nll_per_frame"], outputs["_kl_per_seq"] = res["nll_per_frame"].clone(), res["kl_per_seq"].clone()
         return outputs
 
     def loss(self, inputs, outputs, log_error_arr=False):

@@ -10,8 +10,8 @@ import copy
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
+from .. import dist_utils
 from ..types import AttrDict, ParamDict
 from .cost_fcn import L2ImageCost, LearnedCostEstimate
 from .sampler import FlatCEMSampler, ImageHierarchicalTreeCEMSampler
@@ -27,8 +27,10 @@ class CEMPlanner:
         self._logs = []
 
     def _default_hparams(self):
+        # max_rollout_bs: the reference default is 100 (cem_planner.py:31); the device pads a rollout to 128-row tiles,
+        # so chunks that are multiples of 128 waste nothing -- one chunk of up to 1024 candidates by default
         return ParamDict(
-            horizon=None, action_dim=None, n_iters=1, batch_size=64, max_rollout_bs=100, elite_frac=0.1,
+            horizon=None, action_dim=None, n_iters=1, batch_size=64, max_rollout_bs=1024, elite_frac=0.1,
             cost_fcn=L2ImageCost, dense_cost=False, final_step_cost_weight=1.0,
             sampler=FlatCEMSampler, sampler_clip_val=float("Inf"), initial_std=3e-1,
             verbose=False, dump_planning_data=False, use_delta_state_actions=False, use_inferred_actions=True,
@@ -45,64 +47,96 @@ class CEMPlanner:
     def append_latent(self):
         return getattr(self._sampler, "append_latent", False)
 
-    # ---- sharding -----------------------------------------------------------------------------
-    @staticmethod
-    def _world():
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(), dist.get_world_size()
-        return 0, 1
+    @property
+    def engine(self):
+        return self._simulator._model.engine
+
+    def _chunks(self, n):
+        """Chunk boundaries of CEMPlanner._rollout (cem_planner.py:115-122): max(n // max_rollout_bs, 1) chunks of
+        max_rollout_bs -- the remainder beyond the last full chunk is dropped, one short chunk when n < max_rollout_bs."""
+        bs = max(int(self._hp.max_rollout_bs), 1)
+        return [(i * bs, min((i + 1) * bs, n)) for i in range(max(n // bs, 1))]
 
     def _rollout_costs(self, state, goal_state, z):
-        """Rolls out device samples z in chunks of max_rollout_bs; returns (costs, chunks)."""
-        bs = max(int(self._hp.max_rollout_bs), 1)
-        costs, chunks = [], []
-        for s in range(0, z.shape[0], bs):
-            ro = self._simulator.rollout_device(state, goal_state, z[s:s + bs], self._hp.max_seq_len)
-            costs.append(self._cost_fcn.device_cost(ro))
-            chunks.append((s, ro))
-        return torch.cat(costs), chunks
+        """Rolls out samples z (device tensor, or pinned host tensor) chunk by chunk; returns the [n_used] cost vector.
+        Every chunk's costs are written into their own slice of one preallocated vector: the rollout / cost buffers of
+        the engine are persistent and reused by the next chunk, so nothing else of a chunk is kept."""
+        chunks = self._chunks(z.shape[0])
+        cost = torch.empty(chunks[-1][1], device=self.engine.device, dtype=torch.float32)
+        if len(chunks) > 1 and not getattr(self._cost_fcn, "chunkable", True):
+            raise NotImplementedError("%s needs all candidates in one rollout (raise max_rollout_bs)" % type(self._cost_fcn).__name__)
+        z_dev = []
+        for s, e in chunks:
+            ro = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len)
+            self._cost_fcn.device_cost(ro, out=cost[s:e])
+            if not z.is_cuda:
+                z_dev.append(ro.z if len(chunks) == 1 else ro.z.clone())    # device copy of host-resident samples
+        return cost, (z if z.is_cuda else (z_dev[0] if len(z_dev) == 1 else torch.cat(z_dev)))
 
-    def cem_iteration(self, state, goal_state):
-        """One sharded CEM iteration on the device.  Returns (all costs [N], elite ids [k], elite costs)."""
-        rank, world = self._world()
+    def cem_iteration(self, state, goal_state, samples=None):
+        """One CEM iteration on the device (cem_planner.py:58-69): sample -> rollout -> cost -> elites -> refit.
+        With torch.distributed initialised the N candidates are sharded over the ranks (global candidate ids
+        [rank * N/R, (rank+1) * N/R)); one all-gather of the costs, the same top-k on every rank, elites regenerated from
+        the shared counter-based noise stream.  `samples` (optional, single rank only): this iteration's candidates,
+        [N,255,256] on the device or in pinned host memory (the reference simulator's contract), instead of a draw.
+        Returns (costs [N_used], elite ids [k] int32, elite costs [k], elite samples [k,255,256])."""
+        rank, world = dist_utils.world()
         N = int(self._hp.batch_size)
-        assert N % world == 0, "batch_size must divide over ranks"
-        n_loc = N // world
-        first = rank * n_loc
-        z = self._sampler.sample_device(n_loc, first_id=first)
-        cost_loc, chunks = self._rollout_costs(state, goal_state, z)
-        if world > 1:
-            cost = torch.empty(N, device=cost_loc.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(cost, cost_loc.contiguous())
+        first, last = dist_utils.shard_range(N, rank, world)
+        if samples is not None:
+            if world > 1:
+                raise ValueError("injected samples are not sharded; use the sampler's counter-based stream")
+            z = samples
         else:
-            cost = cost_loc
+            z = self._sampler.sample_device(last - first, first_id=first)
+        cost_loc, z = self._rollout_costs(state, goal_state, z)
+        if world > 1 and cost_loc.shape[0] != last - first:
+            raise ValueError("sharded CEM needs batch_size / world_size to be a multiple of max_rollout_bs (or smaller)")
+        cost = dist_utils.gather_costs(cost_loc)
         k = max(int(N * self._hp.elite_frac), 1)
-        idx, val = self._simulator._model.engine.topk(cost, k)
+        idx, val = self.engine.topk(cost, k)
         if world > 1:
             z_elite = self._sampler.regenerate(idx)
             self._sampler.fit_device(z_elite, torch.arange(k, device=idx.device, dtype=torch.int32))
         else:
-            z_elite = z[idx.long()]
+            z_elite = None
             self._sampler.fit_device(z, idx)
-        return cost, idx, val, z_elite, chunks
+        return cost, idx, val, (z, z_elite)
+
+    def _elite_samples(self, packed, idx):
+        z, z_elite = packed
+        return z_elite if z_elite is not None else z[idx.long()]
+
+    def _rollout_host(self, state, goal_state, z):
+        """Final rollout of the best samples (cem_planner.py:81-82), joined over chunks, as host lists."""
+        out = None
+        for s, e in self._chunks(z.shape[0]):
+            part = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len).to_host(self._simulator._append_latent)
+            if out is None:
+                out = part
+            else:
+                for key in out:
+                    out[key] = out[key] + part[key]
+        return out
 
     def __call__(self, state, goal_state):
         self._sampler.init()
         logs = []
-        z_elite = val = None
+        best = val = None
         for _ in range(self._hp.n_iters):
-            cost, idx, val, z_elite, chunks = self.cem_iteration(state, goal_state)
+            cost, idx, val, packed = self.cem_iteration(state, goal_state)
+            best = self._elite_samples(packed, idx)
             logs.append(AttrDict(elite_scores=val.cpu().numpy(), goal_state=goal_state))
         # final rollout of the elites with the best samples (cem_planner.py:81-96)
-        ro = self._simulator.rollout_device(state, goal_state, z_elite, self._hp.max_seq_len)
-        final = ro.to_host(self._simulator._append_latent)
+        final = self._rollout_host(state, goal_state, best)
         self._sampler.sync_host()
+        scores = val.cpu().numpy()
         logs.append(AttrDict(elite_rollouts=copy.deepcopy(self._maybe_split_image(final.predictions)),
-                             elite_scores=val.cpu().numpy(), dists=self._sampler.get_dists(), goal_state=goal_state,
+                             elite_scores=scores, dists=self._sampler.get_dists(), goal_state=goal_state,
                              elite_states=copy.deepcopy(final.states)))
         self._logs.append(logs)
-        best_actions = self._get_action_plan(final, z_elite)
-        return final.predictions[0], best_actions[0], final.latents[0], float(val[0])
+        best_actions = self._get_action_plan(final, best)
+        return final.predictions[0], best_actions[0], final.latents[0], float(scores[0])
 
     def _maybe_split_image(self, rollout):
         if hasattr(self._cost_fcn, "_split_state_rollout") and self._simulator._append_latent:

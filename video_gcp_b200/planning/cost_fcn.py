@@ -51,11 +51,14 @@ class L2ImageCost(CostFcn, ImageCost):
         super().__init__(dense_cost, final_step_weight)
         self.engine = engine
 
-    def device_cost(self, ro):
+    def device_cost(self, ro, out=None):
+        """[B] costs of a DeviceRollouts; `out`: caller-owned destination (else an engine buffer that the next cost
+        call overwrites)."""
         if ro.sequential:
             return ro.model.engine.cost_l2_seq(ro.images_seq, ro.end_ind, ro.goal_chw, self._dense_cost,
-                                               self._final_step_weight)
-        return ro.model.engine.cost_l2(ro.images_df, ro.end_ind, ro.goal_chw, self._dense_cost, self._final_step_weight)
+                                               self._final_step_weight, out=out)
+        return ro.model.engine.cost_l2(ro.images_df, ro.end_ind, ro.goal_chw, self._dense_cost, self._final_step_weight,
+                                       out=out)
 
     def __call__(self, cem_outputs, goal):
         if isinstance(cem_outputs, DeviceRollouts):
@@ -100,8 +103,8 @@ class LearnedCostEstimate:
     def engine(self):
         return self._model.engine
 
-    def device_cost(self, ro, goal_seq):
-        return ro.model.engine.cost_learned(ro.e_df, ro.end_ind, goal_seq)
+    def device_cost(self, ro, goal_seq, out=None):
+        return ro.model.engine.cost_learned(ro.e_df, ro.end_ind, goal_seq, out=out)
 
     def pairs_device(self, lat, idx1, idx2, seg_off=None):
         """Pair costs over rows of a device latent table (per pair, or summed per segment): what the hierarchical
@@ -141,11 +144,13 @@ class ImageWrappedLearnedCostFcn(LearnedCostEstimate, ImageCost):
     """Unpacks image+latent rollouts; every candidate's goal is the LAST candidate's latent rollout
     (the reference's own HACK, cost_fcn.py:108-116)."""
 
-    def device_cost(self, ro, goal_seq=None):
+    chunkable = False       # the "goal" is the last candidate of the WHOLE batch: one rollout call per CEM iteration
+
+    def device_cost(self, ro, goal_seq=None, out=None):
         last = len(ro) - 1
         L = int(ro.end_ind[last]) + 1
         goal = ro.model.engine.prune_gather(ro.e_df[last:last + 1], ro.end_ind[last:last + 1])[0, :L]
-        return ro.model.engine.cost_learned(ro.e_df, ro.end_ind, goal)
+        return ro.model.engine.cost_learned(ro.e_df, ro.end_ind, goal, out=out)
 
     def __call__(self, start_enc, goal_enc=None):
         if isinstance(start_enc, DeviceRollouts):

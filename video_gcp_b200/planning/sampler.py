@@ -19,7 +19,8 @@ class CEMSampler:
         self._initial_std = initial_std
         self.engine = None
         self.seed = 0
-        self._iter = 0
+        self._draws = 0          # device draws so far: never reset, so no two draws of a sampler share a noise stream
+        self._last_seed = 0
         self.init()
 
     def attach(self, engine, seed=0):
@@ -35,7 +36,6 @@ class FlatCEMSampler(CEMSampler):
         self.mean = np.zeros((self._n_steps, self._action_dim))
         self.std = self._initial_std * np.ones((self._n_steps, self._action_dim))
         self._mean_d = self._std_d = None
-        self._iter = 0
 
     # ---- reference contract (host numpy) ----
     def sample(self, n_samples):
@@ -53,23 +53,30 @@ class FlatCEMSampler(CEMSampler):
         return AttrDict(mean=self.mean, std=self.std)
 
     # ---- device path ----
-    def _iter_seed(self):
-        return (self.seed * 1000003 + self._iter) & 0xFFFFFFFFFFFFFFFF
+    def _next_seed(self):
+        """Philox key of the next device draw.  The reference draws from the advancing np.random stream, so every CEM
+        iteration AND every replan sees fresh samples (sampler.py:40-42); here the draw counter plays that role: it
+        advances with every sample_device() call and init() does not reset it.  Ranks of a sharded planner make the
+        same sequence of calls, so they agree on the key without communicating."""
+        seed = (self.seed * 1000003 + self._draws) & 0xFFFFFFFFFFFFFFFF
+        self._draws += 1
+        self._last_seed = seed
+        return seed
 
     def sample_device(self, n_samples, first_id=0, out=None):
         assert self.engine is not None, "attach(engine) first"
-        return self.engine.sample_noise(n_samples, self._mean_d, self._std_d, float(self._initial_std), self._iter_seed(),
+        return self.engine.sample_noise(n_samples, self._mean_d, self._std_d, float(self._initial_std), self._next_seed(),
                                         first_id, self._clip_val, out=out)
 
     def regenerate(self, ids):
-        """Noise of the given global candidate ids (int32 cuda tensor), this iteration's distribution."""
+        """Noise of the given global candidate ids (int32 device tensor) of the LATEST draw (same key, same
+        distribution): bit-identical to the rows sample_device produced for those ids on whichever rank owned them."""
         return self.engine.sample_noise_ids(ids.int(), self._mean_d, self._std_d, float(self._initial_std),
-                                            self._iter_seed(), self._clip_val)
+                                            self._last_seed, self._clip_val)
 
     def fit_device(self, z, elite_idx):
-        """Refit from rows `elite_idx` (int32 cuda) of device samples z."""
+        """Refit from rows `elite_idx` (int32 device tensor) of device samples z."""
         self._mean_d, self._std_d = self.engine.refit(z, elite_idx)
-        self._iter += 1
 
     def sync_host(self):
         if self._mean_d is not None:
@@ -107,8 +114,7 @@ class ImageHierarchicalTreeCEMSampler(SimpleTreeCEMSampler):
             return      # base-class constructor calls init() before the tree parameters exist
         self._optimizer = ImageHierarchicalTreeLatentOptimizer(
             self._action_dim, list(self._sampling_rates_per_layer), self._n_layer_hierarchy, self._subgoal_cost_fcn,
-            self._ll_cost_fcn, self._n_ll_samples, engine=self.engine, rng=self._rng, seed=self._iter_seed())
-        self._iter += 1
+            self._ll_cost_fcn, self._n_ll_samples, engine=self.engine, rng=self._rng, seed=self._next_seed())
 
     def sample(self, n_samples):
         z = self._optimizer.sample()
