@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- tree-GCP CEM rollouts/sec on B200 (BASELINE.json metric, config 2).
 
-A "step" is one pass of the CEM hot path over one batch of synthetic candidates of the 25-room shape:
-batched GCP-tree rollout (encoder, sampled length, 8 TreeLSTM levels, all 255 nodes decoded, pruning,
-inverse model / state regressor / existence heads) + dense L2 image cost + (N>1: one NCCL all-gather of the
-costs) + elite top-k + refit.  `value` times it with the noise already resident in HBM; `e2e` goes through
-the reference-facing simulator call with HOST (pinned) noise and start/goal images, copies inside the
-timed region, and reads costs + elite indices back.
+A "step" is ONE ITERATION OF THE PRODUCT'S FLAT CEM LOOP, `ImageCEMPlanner.cem_iteration`
+(video_gcp_b200/planning/cem_planner.py; reference gcp/planning/cem/cem_planner.py:58-69) over one batch of synthetic
+candidates of the 25-room shape: draw the candidates (device Philox, keyed by global candidate id) -> batched GCP-tree
+rollout (encoder, sampled length, 8 TreeLSTM levels, all 255 nodes decoded, pruning, inverse model / state regressor /
+existence heads) -> dense L2 image cost -> (N>1: one NCCL all-gather of the costs) -> elite top-k -> refit.
+
+  value            the step with everything resident in HBM (the two 12 KB start / goal images are the call's arguments)
+  e2e              the same planner call from HOST start / goal images (pinned), costs + elite ids read back to the host
+  e2e_host_noise   the reference simulator's contract: this step's 267 MB of candidates come from pinned HOST memory
+                   (`simulator.rollout(state, goal, samples, ...)`, cem_simulator.py:14), copied inside the timed region
+  e2e_planner      a whole `planner(state, goal)` call: n_iters iterations + final rollout of the elites + plan to host
+  value_pruned     planner mode "decode only what the cost reads" (kept nodes only, L2 cost folded into the decoder
+                   tail); identical costs / elites, fewer executed FLOPs -- a second figure, `value` stays canonical
 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference      (CPU restatement of the reference on the host cores)
+  python bench.py --gpus N --candidates-total 65536        (strong scaling: config 5's sweep, sharded over N ranks)
+  python bench.py --config seq                             (BASELINE config 3: sequential GCP rollout)
+  python bench.py --impl reference      (the UNMODIFIED reference staged under baseline/_ref, on the host cores)
 """
 import argparse
 import json
@@ -19,6 +28,7 @@ import subprocess
 import sys
 import threading
 import time
+from functools import partial
 
 import numpy as np
 import torch
@@ -29,6 +39,7 @@ sys.path.insert(0, ROOT)
 METRIC = "tree-GCP CEM rollouts/sec"
 UNIT = "rollouts/s"
 FLOP_PER_ROLLOUT = 16.754e9          # canonical work, BASELINE.md section 3 (8.377 GMAC)
+SEQ_FLOP_PER_ROLLOUT = 2 * 9.76e9    # sequential GCP: 199 steps x (prior MLP + 3 x 1024-wide LSTM) + decoder
 TAIL_FLOP_PER_IMAGE = 2 * (8.388608e6 + 7.8643e6)   # the two full-resolution decoder convolutions (canonical count)
 # tensor-core FLOPs dec_tail3_kernel actually issues per image: 2 tiles x 2 convs x 28 tcgen05.mma of 128x64x16.  It is
 # BELOW the canonical count because the encoder-skip half of conv 32->16 is a per-candidate constant computed once,
@@ -44,7 +55,10 @@ ELITE_FRAC = 0.1
 TAIL_TRAFFIC_BYTES_B1024 = (528.97e6 + 746.97e6 + 3 * (537.36e6 + 758.71e6)) / 4
 
 
-def workload(cands):
+def workload(cands, config="tree"):
+    if config == "seq":
+        return ("25-room sequential GCP (blox vrnn) rollout, one start/goal pair, %d candidates per GPU, 199 recurrent steps, "
+                "200 frames decoded per candidate, sampled rollout length, dense L2 image cost, elite_frac 0.1" % cands)
     return ("25-room gcp_tree CEM planning rollout, one start/goal pair, %d candidates per GPU, depth-8 tree, "
             "255 nodes decoded per candidate, sampled rollout length, dense L2 image cost, elite_frac 0.1" % cands)
 
@@ -91,12 +105,43 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)", 1650.0
 
 
-def oracle_step(sd, O, state, goal, n, seed):
-    """One CEM iteration of the CPU restatement on n candidates; returns seconds."""
+_ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs that are local to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any pinned
+    host buffer is allocated: first-touch then places the staging memory on the GPU's own NUMA node, so 8 ranks pulling
+    267 MB of host noise per step do not all cross the same socket interconnect (round-1 finding: e2e efficiency 0.84 at
+    N=8 with unplaced buffers).  Best effort; returns a short description for the JSON line."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            global _ORIG_AFFINITY
+            _ORIG_AFFINITY = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+            return "%s -> %d local cpus" % (bdf, len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
+def port_step(sd, O, state, goal, n, seed):
+    """One CEM iteration of the CPU restatement (oracle port) on n candidates; returns seconds."""
     r = np.random.default_rng(seed)
-    samples = r.normal(0, 0.3, size=(n, 255, 256))
     end = r.integers(2, 200, size=n)
     t0 = time.perf_counter()
+    samples = r.normal(0, 0.3, size=(n, 255, 256))
     with torch.no_grad():
         ro = O.simulator_rollout(sd, state, goal, samples, end)
     imgs = [p[:, :3072].reshape(-1, 3, 32, 32) for p in ro["predictions"]]
@@ -106,35 +151,68 @@ def oracle_step(sd, O, state, goal, n, seed):
     return time.perf_counter() - t0
 
 
+def cpu_reference_arm(sd, state, goal, n, steps, warmup):
+    """Times the reference's CPU path on the host cores: the UNMODIFIED reference staged under baseline/_ref when it is
+    there (kind "reference"), else the oracle port.  Returns (rollouts/s, seconds per step, kind, cores)."""
+    from oracle import ref_arm
+    if _ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, _ORIG_AFFINITY)       # the CPU arm may use every host core again
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    if ref_arm.available():
+        R = ref_arm.ReferenceCEM(sd, cores)
+        fn, kind = (lambda s: R.step(state, goal, n, max(ELITE_FRAC, 1.0 / n), s)), "reference"
+    else:
+        from oracle import gcp_oracle as O
+        fn, kind = (lambda s: port_step(sd, O, state, goal, n, s)), "port"
+    for w in range(warmup):
+        fn(100 + w)
+    t = sum(fn(200 + s) for s in range(steps))
+    return n * steps / t, t / steps, kind, cores
+
+
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python reference
-    itself cannot travel to the GPU box).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the step on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import gcp_oracle as O
     from video_gcp_b200 import hparams
     from video_gcp_b200.synthetic import synthetic_state_dict
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     hp = hparams.build_hparams(hparams.gcp_tree_25room_config(batch_size=1))
     sd = synthetic_state_dict(hp, 1)
     r = np.random.default_rng(0)
     state = r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
     goal = r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
     n = args.ref_sample
-    for w in range(args.warmup):
-        oracle_step(sd, O, state, goal, n, 100 + w)
-    t = sum(oracle_step(sd, O, state, goal, n, 200 + s) for s in range(args.steps))
-    v = n * args.steps / t
+    v, sec, kind, cores = cpu_reference_arm(sd, state, goal, n, args.steps, min(args.warmup, 1))
     sample = "%d of %d candidates per step (same per-candidate work)" % (n, args.candidates)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload(args.candidates), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def timed(fn, steps, warmup, world, dev, dist):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
 
 
 def main():
@@ -143,17 +221,24 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--candidates", type=int, default=1024, help="candidates per GPU")
-    ap.add_argument("--ref-sample", type=int, default=16, help="candidates per CPU-reference step")
+    ap.add_argument("--config", default="tree", choices=["tree", "seq"])
+    ap.add_argument("--candidates", type=int, default=1024, help="candidates per GPU (weak scaling)")
+    ap.add_argument("--candidates-total", type=int, default=0,
+                    help="total candidates, sharded over the ranks (strong scaling; BASELINE config 5)")
+    ap.add_argument("--ref-sample", type=int, default=8, help="candidates per CPU-reference step")
+    ap.add_argument("--planner-iters", type=int, default=2, help="n_iters of the e2e_planner call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only value / e2e (skip e2e_host_noise, e2e_planner, value_pruned)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "seq":
+        return main_seq(args)
 
     import torch.distributed as dist
     from video_gcp_b200 import hparams
     from video_gcp_b200.model import TreeModel
-    from video_gcp_b200.planning import GCPImageSimulator, L2ImageCost, SimpleTreeCEMSampler
+    from video_gcp_b200.planning import GCPImageSimulator, ImageCEMPlanner, L2ImageCost, SimpleTreeCEMSampler
     from video_gcp_b200.synthetic import synthetic_state_dict
 
     rank = int(os.environ.get("RANK", "0"))
@@ -161,91 +246,145 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.candidates
+    strong = args.candidates_total > 0
+    if strong:
+        assert args.candidates_total % world == 0, "--candidates-total must divide over the ranks"
+        B = args.candidates_total // world
+    else:
+        B = args.candidates
     N = B * world
     k = max(int(N * ELITE_FRAC), 1)
+    chunk = min(B, 8192)                      # rollout chunk = engine capacity (3.5 GB of workspace per 1024 candidates)
+    assert B % chunk == 0
 
     hp_cfg = hparams.gcp_tree_25room_config(batch_size=1)
-    model = TreeModel(hp_cfg, None, max_candidates=B)
+    model = TreeModel(hp_cfg, None, max_candidates=chunk)
     model.load_state_dict(synthetic_state_dict(model._hp, 1), strict=True)
     model.device = dev
     model.eval()
     eng = model.engine
     sim = GCPImageSimulator(model, append_latent=False)
-    cost_fcn = L2ImageCost(True, 1.0)
-    sampler = SimpleTreeCEMSampler(float("inf"), 200, 256, 0.3, n_level_hierarchy=8).attach(eng, seed=7)
+
+    def make_planner(n_iters=1, seed=7):
+        return ImageCEMPlanner(dict(batch_size=N, n_iters=n_iters, elite_frac=ELITE_FRAC, cost_fcn=L2ImageCost, dense_cost=True,
+                                    final_step_cost_weight=1.0, sampler=partial(SimpleTreeCEMSampler, n_level_hierarchy=8),
+                                    max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=chunk, seed=seed), sim)
+
+    planner = make_planner()
+    planner._sampler.init()
 
     r = np.random.default_rng(0)
     state = r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
     goal = r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)
-    # resident inputs for `value`; pinned host inputs for `e2e`
-    z_dev = sampler.sample_device(B, first_id=rank * B)
-    z_host = z_dev.cpu().pin_memory()
     state_t = torch.as_tensor(state).pin_memory()
     goal_t = torch.as_tensor(goal).pin_memory()
 
-    def cem_tail(ro, z):
-        cost_loc = cost_fcn.device_cost(ro)
-        if world > 1:
-            cost = torch.empty(N, device=dev, dtype=torch.float32)
-            dist.all_gather_into_tensor(cost, cost_loc)
-        else:
-            cost = cost_loc
-        idx, val = eng.topk(cost, k)
-        if world > 1:
-            # elites of other ranks are regenerated from the shared counter-based RNG (no payload)
-            z_elite = sampler.regenerate(idx)
-            mean, std = eng.refit(z_elite, torch.arange(k, device=dev, dtype=torch.int32))
-        else:
-            mean, std = eng.refit(z, idx)
-        return cost, idx, val, mean
-
-    def step_resident():
-        ro = sim.rollout_device(state_t, goal_t, z_dev, 200)
-        return cem_tail(ro, z_dev)
+    def step_value():
+        return planner.cem_iteration(state_t, goal_t)
 
     def step_e2e():
-        # the pinned host noise goes straight into the simulator call: the library uploads it level by level on
-        # its copy stream (all 267 MB inside this step), overlapped with the encoder and the upper tree levels
-        ro = sim.rollout_device(state_t, goal_t, z_host, 200)
-        cost, idx, val, mean = cem_tail(ro, ro.z)
+        cost, idx, val, _ = planner.cem_iteration(state_t, goal_t)
         return cost.cpu(), idx.cpu()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
     l0 = eng.launch_count()
-    ms = timed(step_resident, args.steps, args.warmup)
-    launches = (eng.launch_count() - l0) * args.steps // (args.steps + args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms = timed(step_value, args.steps, args.warmup, world, dev, dist)
+    launches = (eng.launch_count() - l0) // (args.steps + args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), world, dev, dist)
     clk = clocks.stop() if rank == 0 else None
+
+    extras = {}
+    if not args.no_extras:
+        # ---- the reference simulator's contract: candidates in pinned HOST memory (this rank's slice), copied in the call
+        n_host = min(B, chunk)
+        z_host = planner._sampler.sample_device(n_host, first_id=rank * B).cpu().pin_memory()
+        cost_fcn = planner._cost_fcn
+
+        def step_host_noise():
+            ro = sim.rollout_device(state_t, goal_t, z_host, 200)
+            c = cost_fcn.device_cost(ro)
+            if world > 1:
+                full = torch.empty(n_host * world, device=dev, dtype=torch.float32)
+                dist.all_gather_into_tensor(full, c)
+                c = full
+            idx, val = eng.topk(c, max(int(n_host * world * ELITE_FRAC), 1))
+            if world == 1:
+                eng.refit(ro.z, idx)
+            return c.cpu(), idx.cpu()
+
+        ms_hn = timed(step_host_noise, args.steps, 3, world, dev, dist)
+        extras["e2e_host_noise"] = {
+            "value": n_host * world * args.steps / (ms_hn * 1e-3), "unit": UNIT, "ms_per_step": ms_hn / args.steps,
+            "h2d_bytes_per_step": int(z_host.numel() * 4 + 2 * 3072 * 4), "d2h_bytes_per_step": int(n_host * world * 4 + k * 4),
+            "candidates_per_gpu": n_host, "numa": numa,
+            "note": "simulator.rollout(state, goal, samples) with this rank's samples in pinned host memory + cost + "
+                    "all-gather + top-k" + (" + refit" if world == 1 else " (no refit: injected samples are not regenerable)")}
+        del z_host
+
+        # ---- a whole planner call: n_iters iterations + final rollout of the elites + the plan on the host
+        if B <= chunk:
+            pl2 = make_planner(n_iters=args.planner_iters, seed=11)
+
+            def plan():
+                return pl2(state_t, goal_t)
+
+            plan()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            n_plans = 3
+            for _ in range(n_plans):
+                frames, actions, latents, score = plan()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item()) / n_plans
+            extras["e2e_planner"] = {
+                "ms_per_plan": dt * 1e3, "n_iters": args.planner_iters, "rollouts_per_plan": args.planner_iters * N + k,
+                "value": (args.planner_iters * N + k) / dt, "unit": UNIT,
+                "note": "ImageCEMPlanner.__call__(state, goal): %d CEM iterations over %d candidates, final rollout of the %d "
+                        "elites, elite rollouts + plan copied to the host (host wall clock, synchronised)" % (args.planner_iters, N, k)}
+
+    # ---- N > 1: every rank must hold the same elites / distribution, and rank 0 must reproduce any rank's costs
+    rank_consistent = None
+    if world > 1:
+        seed0 = model.seed
+        cost, idx, val, packed = planner.cem_iteration(state_t, goal_t)
+        chk = torch.stack([idx.double().sum(), (idx.double() * torch.arange(1, k + 1, device=dev)).sum(),
+                           planner._sampler._mean_d.double().sum(), planner._sampler._std_d.double().sum(), cost.double().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        reroll = True
+        if rank == 0:
+            # re-roll the LAST rank's candidate ids here: same global ids (regenerated from the shared noise stream), same
+            # rollout seeds as that rank used -> its slice of the gathered cost vector, bit for bit
+            other = world - 1
+            ids = torch.arange(other * B, (other + 1) * B, device=dev, dtype=torch.int32)
+            model.seed = seed0
+            c2 = torch.empty(B, device=dev)
+            for s, e in planner._chunks(B):
+                z2 = planner._sampler.regenerate(ids[s:e])
+                ro = sim.rollout_device(state_t, goal_t, z2, 200)
+                planner._cost_fcn.device_cost(ro, out=c2[s:e])
+            reroll = bool(torch.equal(c2, cost[other * B:(other + 1) * B]))
+        flag = torch.tensor([1.0 if (same and reroll) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        rank_consistent = bool(flag.item() == 1.0)
 
     # ---- roofline of the dominant kernel (decoder tail conv), timed live with CUDA events on its stream
     eng.profile_enable(True)
     for _ in range(2):
-        step_resident()
+        step_value()
     torch.cuda.synchronize()
     prof = eng.profile_read()
     eng.profile_enable(False)
@@ -264,14 +403,17 @@ def main():
     phase_ms = {p: round(prof[p] / 2, 3) for p in eng.PHASES}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload(B), "candidates_total": N, "elites": k,
-                   "l2": "inputs larger than L2 (noise z = %.0f MB read per step; images written %.1f GB)"
+        "config": {"workload": workload(B), "candidates_total": N, "candidates_per_gpu": B, "rollout_chunk": chunk, "elites": k,
+                   "step": "ImageCEMPlanner.cem_iteration (sample -> rollout -> L2 cost -> all-gather -> top-k -> refit)",
+                   "l2": "inputs larger than L2 (noise z = %.0f MB drawn + read per step; images written %.1f GB)"
                          % (B * 255 * 256 * 4 / 1e6, B * 255 * 3072 * 4 / 1e9),
                    "parallelism": "candidates sharded over %d rank(s), cost all-gather" % world},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(z_host.numel() * 4 + 2 * 3072 * 4),
-                "d2h_bytes_per_step": int(N * 4 + k * 4), "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * 3072 * 4),
+                "d2h_bytes_per_step": int(N * 4 + k * 4), "ms_per_step": ms_e2e / args.steps,
+                "note": "planner call from pinned host start / goal images; the candidates are drawn inside the call (as the "
+                        "reference planner does with np.random); costs + elite ids copied back every step"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "dec_tail3_kernel", "achieved": tail_tf, "peak": peak_tf,
@@ -281,7 +423,7 @@ def main():
                                   "frac_of_burst": tail_tf * TAIL_EXECUTED_FLOP_PER_IMAGE / TAIL_FLOP_PER_IMAGE / peak_burst,
                                   "note": "tcgen05 FLOPs actually issued (29.36 MFLOP/image vs 32.51 canonical: shared "
                                           "skip half + unused mixture-scale channels are not computed)"},
-                     "traffic": TAIL_TRAFFIC_BYTES_B1024 if B == 1024 else None,
+                     "traffic": TAIL_TRAFFIC_BYTES_B1024 if chunk == 1024 else None,
                      "traffic_note": "bytes per launch, ncu dram read+write (profiles/r1k_dec_tail3_ncu_full.txt)",
                      "peak_source": peak_src,
                      "ms_per_launch": tail_ms, "images_per_launch": tail_imgs},
@@ -290,17 +432,105 @@ def main():
                           "frac": value / world * FLOP_PER_ROLLOUT / 1e12 / peak_tf},
         "phase_ms_per_step": phase_ms,
     }
+    out.update(extras)
+    if rank_consistent is not None:
+        out["rank_consistent"] = rank_consistent
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import gcp_oracle as O
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
         sd = synthetic_state_dict(model._hp, 1)
         n = args.ref_sample
-        oracle_step(sd, O, state, goal, 4, 1)
-        t = sum(oracle_step(sd, O, state, goal, n, 10 + s) for s in range(3))
-        out["cpu_baseline"] = {"value": 3 * n / t, "unit": UNIT, "cores": cores, "kind": "port",
+        v, sec, kind, cores = cpu_reference_arm(sd, state, goal, n, 3, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                "sample": "3 steps of %d candidates (of %d), same per-candidate work" % (n, B)}
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_seq(args):
+    """BASELINE config 3: the sequential GCP rollout (199-step recurrence) + dense L2 cost + elite top-k; one line, same
+    schema.  Single GPU or replicas sharded by candidate like the tree path."""
+    import torch.distributed as dist
+    from video_gcp_b200 import hparams
+    from video_gcp_b200.model import SequentialModel
+    from video_gcp_b200.planning import GCPImageSimulator, L2ImageCost
+    from video_gcp_b200.synthetic import synthetic_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.candidates
+    N = B * world
+    k = max(int(N * ELITE_FRAC), 1)
+    model = SequentialModel(hparams.gcp_sequential_25room_config(batch_size=1), None, max_candidates=B)
+    model.load_state_dict(synthetic_state_dict(model._hp, 1), strict=True)
+    model.device = dev
+    model.eval()
+    eng = model.engine
+    sim = GCPImageSimulator(model, append_latent=False)
+    cost_fcn = L2ImageCost(True, 1.0)
+    r = np.random.default_rng(0)
+    state_t = torch.as_tensor(r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)).pin_memory()
+    goal_t = torch.as_tensor(r.uniform(0, 1, size=(1, 32, 32, 3)).astype(np.float32)).pin_memory()
+    z_dev = torch.randn(B, 199, 256, device=dev) * 0.3
+    z_host = z_dev.cpu().pin_memory()
+
+    def tail(ro):
+        c = cost_fcn.device_cost(ro)
+        if world > 1:
+            full = torch.empty(N, device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(full, c)
+            c = full
+        idx, val = eng.topk(c, k)
+        return c, idx
+
+    def step_value():
+        return tail(sim.rollout_device(state_t, goal_t, z_dev, 200))
+
+    def step_e2e():
+        c, idx = tail(sim.rollout_device(state_t, goal_t, z_host, 200))
+        return c.cpu(), idx.cpu()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    l0 = eng.launch_count()
+    ms = timed(step_value, args.steps, args.warmup, world, dev, dist)
+    launches = (eng.launch_count() - l0) // (args.steps + args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), world, dev, dist)
+    clk = clocks.stop() if rank == 0 else None
+    eng.profile_enable(True)
+    for _ in range(2):
+        step_value()
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_tf, peak_hbm, peak_src, peak_burst = measured_peaks()
+    value = N * args.steps / (ms * 1e-3)
+    rec_ms = prof["tree_recursion"] / 2
+    print(json.dumps({
+        "metric": "sequential-GCP CEM rollouts/sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload(B, "seq"), "candidates_total": N, "elites": k,
+                   "l2": "inputs larger than L2 (images written %.1f GB per step)" % (B * 200 * 3072 * 4 / 1e9)},
+        "e2e": {"value": N * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(z_host.numel() * 4 + 2 * 3072 * 4),
+                "d2h_bytes_per_step": int(N * 4 + k * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "199-step recurrence (prior MLP + reparametrisation + 3 LSTM cells + output)",
+                     "achieved": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12 / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "note": "whole-step canonical FLOPs (2 x 9.76 GMAC per rollout) over the step time"},
+        "phase_ms_per_step": {p: round(prof[p] / 2, 3) for p in eng.PHASES}, "recurrence_ms": rec_ms,
+    }))
     if world > 1:
         dist.destroy_process_group()
 

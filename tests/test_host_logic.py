@@ -73,21 +73,89 @@ def test_frame_nodes_match_golden(golden_dir):
         assert (g["timesteps"][e][nodes] == np.arange(e + 1)).all()
 
 
+# ---- the flat CEM planner's sharded loop (cem_planner.py:55-96 here video_gcp_b200/planning/cem_planner.py) on the CPU: the
+# planner only talks to its engine / simulator / cost function through a handful of calls, so a host stand-in with the
+# same counter-based noise contract exercises the REAL CEMPlanner.cem_iteration -- shard ranges, the cost all-gather
+# (gloo), the top-k on every rank, elite regeneration and the refit -- without a GPU.
+class _HostEngine:
+    device = torch.device("cpu")
+    SHAPE = (7, 4)
+
+    def sample_noise_ids(self, ids, mean=None, std=None, std_scalar=1.0, seed=0, clip=float("inf")):
+        rows = []
+        for g in ids.tolist():          # row of global candidate id g depends on (seed, g) only
+            gen = torch.Generator().manual_seed((int(seed) * 1000003 + int(g)) % (2 ** 63))
+            rows.append(torch.randn(self.SHAPE, generator=gen))
+        n = torch.stack(rows)
+        m = torch.zeros(self.SHAPE) if mean is None else mean
+        s = torch.full(self.SHAPE, float(std_scalar)) if std is None else std
+        return (m + s * n).clamp(-clip, clip)
+
+    def sample_noise(self, n, mean=None, std=None, std_scalar=1.0, seed=0, first_candidate_id=0, clip=float("inf"), out=None):
+        return self.sample_noise_ids(torch.arange(first_candidate_id, first_candidate_id + n), mean, std, std_scalar, seed, clip)
+
+    def topk(self, cost, k):
+        idx = torch.argsort(cost, stable=True)[:k]
+        return idx.int(), cost[idx]
+
+    def refit(self, z, elite_idx):
+        e = z[elite_idx.long()].double()
+        return e.mean(0).float(), e.std(0, unbiased=False).float()
+
+
+class _HostRollouts:
+    def __init__(self, z):
+        self.z = z
+
+
+class _HostSimulator:
+    _append_latent = False
+
+    def __init__(self):
+        self._model = type("M", (), {"engine": _HostEngine()})()
+
+    def rollout_device(self, state, goal_state, samples, rollout_len):
+        return _HostRollouts(samples)
+
+
+class _HostCost:
+    def __init__(self, dense_cost, final_step_weight):
+        pass
+
+    def device_cost(self, ro, out=None):
+        c = ((ro.z - 0.1) ** 2).flatten(1).sum(1)
+        out.copy_(c)
+        return out
+
+
+def _planner_trace(n_total, n_iters, max_bs):
+    from video_gcp_b200.planning.cem_planner import CEMPlanner
+    from video_gcp_b200.planning.sampler import FlatCEMSampler
+    pl = CEMPlanner(dict(batch_size=n_total, n_iters=n_iters, elite_frac=0.1, cost_fcn=_HostCost, sampler=FlatCEMSampler,
+                         max_seq_len=7, action_dim=4, seed=5, max_rollout_bs=max_bs), _HostSimulator())
+    pl._sampler.init()
+    trace = []
+    for _ in range(n_iters):
+        cost, idx, val, packed = pl.cem_iteration(None, None)
+        best = pl._elite_samples(packed, idx)
+        trace.append((cost.tolist(), idx.tolist(), val.tolist(), best.flatten().tolist(),
+                      pl._sampler._mean_d.flatten().tolist(), pl._sampler._std_d.flatten().tolist()))
+    return trace
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     from video_gcp_b200 import dist_utils
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-    n_total = 64
-    first, last = dist_utils.shard_range(n_total)
-    g = torch.Generator().manual_seed(123)
-    all_cost = torch.rand(n_total, generator=g)
-    cost = dist_utils.gather_costs(all_cost[first:last].clone())
-    order = torch.argsort(cost, stable=True)[:6]
-    q.put((rank, first, last, bool(torch.equal(cost, all_cost)), order.tolist()))
+    first, last = dist_utils.shard_range(64)
+    trace = _planner_trace(64, 2, 16)        # 32 candidates per rank in two chunks of 16
+    q.put((rank, first, last, trace))
     dist.destroy_process_group()
 
 
-def test_sharded_cost_gather_gloo_world2():
+def test_sharded_planner_loop_gloo_world2():
+    """(e): two ranks running CEMPlanner.cem_iteration end with the same elites / mean / std, and these equal a single
+    process run over the same 64 global candidate ids, bit for bit."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -99,8 +167,28 @@ def test_sharded_cost_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert [r[1:3] for r in res] == [(0, 32), (32, 64)]
-    assert all(r[3] for r in res)                 # gathered vector == global cost vector on every rank
-    assert res[0][4] == res[1][4]                 # identical elite ids everywhere
+    assert res[0][3] == res[1][3]                 # identical costs, elite ids, elite samples, mean, std on every rank
+    single = _planner_trace(64, 2, 64)
+    assert res[0][3] == single                    # and identical to one process over the same global ids
+    k = len(single[0][1])
+    assert k == 6 and single[0][1] == sorted(range(64), key=lambda i: (single[0][0][i], i))[:k]
+    assert single[1][0] != single[0][0]           # the second iteration drew from the refitted distribution, fresh noise
+
+
+def test_planner_chunks_follow_reference_rollout_split():
+    """CEMPlanner._rollout (cem_planner.py:115-122): max(n // bs, 1) chunks; costs of every chunk land in their own slice
+    (the round-1 bug: equal-sized chunks aliased one engine buffer and the last chunk's costs were repeated)."""
+    from video_gcp_b200.planning.cem_planner import CEMPlanner
+    from video_gcp_b200.planning.sampler import FlatCEMSampler
+    pl = CEMPlanner(dict(batch_size=48, cost_fcn=_HostCost, sampler=FlatCEMSampler, max_seq_len=7, action_dim=4,
+                         max_rollout_bs=16), _HostSimulator())
+    assert pl._chunks(48) == [(0, 16), (16, 32), (32, 48)] and pl._chunks(10) == [(0, 10)] and pl._chunks(40) == [(0, 16), (16, 32)]
+    z = pl._sampler.sample_device(48)
+    cost, zz = pl._rollout_costs(None, None, z)
+    assert torch.equal(cost, ((z - 0.1) ** 2).flatten(1).sum(1)) and torch.equal(zz, z)
+    # replans draw fresh noise: init() resets the distribution, not the draw counter
+    pl._sampler.init()
+    assert not torch.equal(pl._sampler.sample_device(48), z)
 
 
 def test_train_aux_indices_follow_reference_draws(golden_dir):

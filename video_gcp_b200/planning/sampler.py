@@ -21,6 +21,7 @@ class CEMSampler:
         self.seed = 0
         self._draws = 0          # device draws so far: never reset, so no two draws of a sampler share a noise stream
         self._last_seed = 0
+        self._last_dist = (None, None)
         self.init()
 
     def attach(self, engine, seed=0):
@@ -61,6 +62,7 @@ class FlatCEMSampler(CEMSampler):
         seed = (self.seed * 1000003 + self._draws) & 0xFFFFFFFFFFFFFFFF
         self._draws += 1
         self._last_seed = seed
+        self._last_dist = (self._mean_d, self._std_d)      # the distribution this draw is taken from (regenerate uses it)
         return seed
 
     def sample_device(self, n_samples, first_id=0, out=None):
@@ -71,8 +73,8 @@ class FlatCEMSampler(CEMSampler):
     def regenerate(self, ids):
         """Noise of the given global candidate ids (int32 device tensor) of the LATEST draw (same key, same
         distribution): bit-identical to the rows sample_device produced for those ids on whichever rank owned them."""
-        return self.engine.sample_noise_ids(ids.int(), self._mean_d, self._std_d, float(self._initial_std),
-                                            self._last_seed, self._clip_val)
+        mean, std = self._last_dist
+        return self.engine.sample_noise_ids(ids.int(), mean, std, float(self._initial_std), self._last_seed, self._clip_val)
 
     def fit_device(self, z, elite_idx):
         """Refit from rows `elite_idx` (int32 device tensor) of device samples z."""
