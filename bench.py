@@ -268,11 +268,13 @@ def main():
     eng = model.engine
     sim = GCPImageSimulator(model, append_latent=False)
 
-    def make_planner(n_iters=1, seed=7):
+    def make_planner(n_iters=1, seed=7, pruned=False):
         return ImageCEMPlanner(dict(batch_size=N, n_iters=n_iters, elite_frac=ELITE_FRAC, cost_fcn=L2ImageCost, dense_cost=True,
                                     final_step_cost_weight=1.0, sampler=partial(SimpleTreeCEMSampler, n_level_hierarchy=8),
-                                    max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=chunk, seed=seed), sim)
+                                    max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=chunk, seed=seed,
+                                    prune_before_decode=pruned), sim)
 
+    # `value` / `e2e`: the canonical workload, all 255 nodes of every candidate decoded (what the reference computes)
     planner = make_planner()
     planner._sampler.init()
 
@@ -327,9 +329,34 @@ def main():
                     "all-gather + top-k" + (" + refit" if world == 1 else " (no refit: injected samples are not regenerable)")}
         del z_host
 
+        # ---- planner mode: decode only the nodes the planner reads, L2 cost folded into the decoder tail (no image writes)
+        plp = make_planner(pruned=True)
+        plp._sampler.init()
+        ms_p = timed(lambda: plp.cem_iteration(state_t, goal_t), args.steps, args.warmup, world, dev, dist)
+        # same candidates, same rollout seeds -> the two modes must agree bit for bit (checked outside the timed region)
+        pa, pb = make_planner(seed=31), make_planner(seed=31, pruned=True)
+        pa._sampler.init(), pb._sampler.init()
+        model.seed = 1000
+        ca, ia, va, _ = pa.cem_iteration(state_t, goal_t)
+        kept = float((sim._model.engine._bufs[("end_ind", (chunk,), torch.int64)].double() + 1).mean()) if B == chunk else None
+        model.seed = 1000
+        cb, ib, vb, _ = pb.cem_iteration(state_t, goal_t)
+        same = bool(torch.equal(ia, ib) and torch.equal(pa._sampler._mean_d, pb._sampler._mean_d)
+                    and torch.equal(pa._sampler._std_d, pb._sampler._std_d))
+        cost_rel = float(((ca - cb).abs().max() / ca.abs().max()).item())
+        DEC_FLOP_PER_NODE = 0.69 * FLOP_PER_ROLLOUT / 255          # decoder = 69 % of the canonical work
+        executed = None if kept is None else FLOP_PER_ROLLOUT - DEC_FLOP_PER_NODE * (255 - kept)
+        extras["value_pruned"] = {
+            "value": N * args.steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / args.steps,
+            "speedup_vs_value": ms / ms_p, "kept_nodes_mean": kept, "executed_flop_per_rollout": executed,
+            "same_elites_and_refit_as_full_decode": same, "cost_max_rel_diff_vs_image_cost_kernel": cost_rel,
+            "note": "ImageCEMPlanner(prune_before_decode=True).cem_iteration: only the end_ind+1 nodes balanced pruning keeps "
+                    "are decoded, the L2 cost is reduced in the decoder-tail epilogue, no image is written; `value` (all 255 "
+                    "nodes, canonical FLOPs) stays the headline"}
+
         # ---- a whole planner call: n_iters iterations + final rollout of the elites + the plan on the host
         if B <= chunk:
-            pl2 = make_planner(n_iters=args.planner_iters, seed=11)
+            pl2 = make_planner(n_iters=args.planner_iters, seed=11, pruned=True)
 
             def plan():
                 return pl2(state_t, goal_t)

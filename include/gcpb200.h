@@ -107,6 +107,19 @@ typedef struct {
     int32_t* pruned_nodes;   /* [B,255] depth-first indices of the kept nodes, in order (first pruned_len[c] valid) */
     int32_t* pruned_len;     /* [B] number of kept nodes: node 0 and every node n with sigmoid(distance[n-1]) <= threshold */
     float prune_threshold;   /* learned_pruning_threshold (0 -> the reference default 0.5) */
+    /* ---- planner mode, GCPB200_MODEL_TREE only (all zero / NULL = the reference behaviour: every node decoded) ----
+     * The CEM planner reads only the frames balanced pruning keeps (end_ind + 1 of the 255 nodes, known before the decoder
+     * runs; cem_simulator.py:29-61, tree.py:52-65) and, with the L2 image cost, only their distance to the goal image
+     * (cost_fcn.py:65-72). */
+    int decode_kept_only;    /* 1: decode only the kept nodes.  images_df (if given) receives exactly those nodes' images at
+                                their depth-first positions -- the entries of pruned-away nodes are left untouched -- so
+                                gcpb200_prune_gather / gcpb200_cost_l2 on it give the same bits as after a full decode */
+    const float* l2_goal;    /* [3,32,32] goal image in [-1,1] or NULL: with l2_cost, the L2 image cost is reduced inside
+                                the decoder-tail kernel from the accumulators (images_df may then be NULL: no image is
+                                written at all) */
+    float* l2_cost;          /* [B] L2ImageCost of every candidate (cost_fcn.py:9-22,65-72); same bits in both decode modes */
+    int l2_dense;            /* dense_cost: sum over frames (1) or last frame only (0) */
+    float l2_final_step_weight;
 } gcpb200_rollout_io;
 
 /* I/O of the sequential GCP rollout (SequentialModel forward in val_mode with injected z, default phase as the

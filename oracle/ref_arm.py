@@ -29,14 +29,15 @@ class ReferenceCEM:
             sys.path.insert(0, ROOT)
         from oracle import refshim
         refshim.REFERENCE_ROOT = STAGED
-        refshim.install()
-        import torch
-        from blox import AttrDict
-        from experiments.prediction.base_configs import gcp_tree as base_conf
-        from gcp.planning.cem import cost_fcn
-        from gcp.planning.cem.cem_simulator import GCPImageSimulator
-        from gcp.planning.cem.sampler import SimpleTreeCEMSampler
-        from gcp.prediction.models.tree.tree import TreeModel
+        with contextlib.redirect_stdout(io.StringIO()):      # the reference prints at import; bench.py prints ONE line
+            refshim.install()
+            import torch
+            from blox import AttrDict
+            from experiments.prediction.base_configs import gcp_tree as base_conf
+            from gcp.planning.cem import cost_fcn
+            from gcp.planning.cem.cem_simulator import GCPImageSimulator
+            from gcp.planning.cem.sampler import SimpleTreeCEMSampler
+            from gcp.prediction.models.tree.tree import TreeModel
         torch.set_num_threads(threads or os.cpu_count())
         h = AttrDict(base_conf.model_config)          # experiments/control/25room/gcp_tree/mod_hyper.py:33-55
         h.update({

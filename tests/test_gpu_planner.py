@@ -337,3 +337,80 @@ def test_sharded_planner_nccl_two_ranks(dev, sd):
         assert torch.equal(z[idx.long()].cpu(), res[0][it][2])
         assert torch.equal(pl._sampler._mean_d.cpu(), res[0][it][3]) and torch.equal(pl._sampler._std_d.cpu(), res[0][it][4])
     model.engine.close()
+
+
+# ---- planner mode: decode only what balanced pruning keeps, L2 cost folded into the decoder tail ------------------------
+@pytest.mark.parametrize("shared", [True, False])
+def test_prune_before_decode_is_bit_identical(dev, sd, shared):
+    """gcpb200_rollout_io.decode_kept_only / l2_cost against the full decode (all 255 nodes): the pruned frames, the
+    fused cost and everything else are the same BITS -- a row of the decoder GEMMs and an image of the tail kernel depend
+    only on their own latent row, wherever that row sits -- and the fused cost equals the image-reading cost kernel to
+    summation order.  300 candidates (not a tile multiple), lengths from 1 to 199, shared and per-candidate start/goal."""
+    from video_gcp_b200.engine import Engine
+    from video_gcp_b200.synthetic import synthetic_rollout_inputs
+    B = 300
+    eng = Engine(dev, max_candidates=384, attach_cost_mdl=True)
+    eng.load_weights(sd)
+    inp = synthetic_rollout_inputs(B, seed=8, shared_images=shared)
+    inp["end_ind"][:6] = torch.tensor([1, 2, 199, 3, 127, 128])
+    nimg = 1 if shared else B
+    I0, Ig, z, ei = inp["I_0"][:nimg].to(dev), inp["I_g"][:nimg].to(dev), inp["z"].to(dev), inp["end_ind"].to(dev)
+    goal = Ig[0]
+    kw = dict(end_ind=ei, images_shared=shared, fresh=True)
+    full = eng.rollout(I0, Ig, z, **kw)
+    cost_kernel = eng.cost_l2(full["images_df"], full["end_ind"], goal, True, 0.7).clone()
+    frames_full = eng.prune_gather(full["images_df"], full["end_ind"])
+    full_fused = eng.rollout(I0, Ig, z, l2_goal=goal, l2_dense=True, l2_final_step_weight=0.7, **kw)
+    assert torch.equal(full_fused["images_df"], full["images_df"])
+    # kept-only, images requested: the persistent image buffer keeps its sentinel wherever a node is pruned away
+    sentinel = eng._buf("images_df", (B, 255, 3, 32, 32)).fill_(7.0)
+    kept = eng.rollout(I0, Ig, z, end_ind=ei, images_shared=shared, decode_kept_only=True, l2_goal=goal, l2_dense=True,
+                       l2_final_step_weight=0.7)
+    assert kept["images_df"].data_ptr() == sentinel.data_ptr()
+    frames_kept = eng.prune_gather(kept["images_df"], kept["end_ind"])
+    assert torch.equal(frames_kept, frames_full)
+    from video_gcp_b200.pruning import frame_nodes
+    for c in (0, 1, 2, 4, 5, 17, B - 1):
+        keep = torch.zeros(255, dtype=torch.bool)
+        keep[torch.as_tensor(frame_nodes(int(inp["end_ind"][c])))] = True
+        img = kept["images_df"][c].cpu()
+        assert torch.equal(img[keep], full["images_df"][c].cpu()[keep])
+        assert bool((img[~keep] == 7.0).all())
+    cost_kept = kept["l2_cost"].clone()
+    # kept-only without images: nothing but the cost leaves the decoder
+    nocopy = eng.rollout(I0, Ig, z, end_ind=ei, images_shared=shared, decode_kept_only=True, want_images=False, l2_goal=goal,
+                         l2_dense=True, l2_final_step_weight=0.7, fresh=True)
+    assert "images_df" not in nocopy
+    assert torch.equal(nocopy["l2_cost"], cost_kept) and torch.equal(full_fused["l2_cost"], cost_kept)
+    assert float(((cost_kept - cost_kernel).abs() / cost_kernel.abs()).max()) < 2e-6
+    last = eng.rollout(I0, Ig, z, end_ind=ei, images_shared=shared, decode_kept_only=True, want_images=False, l2_goal=goal,
+                       l2_dense=False, l2_final_step_weight=1.0, fresh=True)["l2_cost"]
+    assert float(((last - eng.cost_l2(full["images_df"], full["end_ind"], goal, False, 1.0)).abs() / last.abs()).max()) < 2e-6
+    for k in ("e_df", "existence", "actions", "regressed_state", "model_enc_seq", "seq_len_logits"):
+        assert torch.equal(nocopy[k], full[k]), k
+    eng.close()
+
+
+def test_planner_pruned_mode_equals_full_decode(dev, sd):
+    """ImageCEMPlanner with prune_before_decode True / False: same candidates and rollout seeds -> identical elite ids,
+    refit and plan (frames, actions, latents), two iterations + the final elite rollout; sampled lengths."""
+    N = 256
+    rng = np.random.default_rng(6)
+    state, goal = _images(rng)
+    model = _model(sd, dev, N)
+    res = []
+    for pruned in (False, True):
+        from functools import partial
+        from video_gcp_b200.planning import GCPImageSimulator, ImageCEMPlanner, L2ImageCost, SimpleTreeCEMSampler
+        pl = ImageCEMPlanner(dict(batch_size=N, n_iters=2, elite_frac=0.1, cost_fcn=L2ImageCost, dense_cost=True,
+                                  final_step_cost_weight=1.0, sampler=partial(SimpleTreeCEMSampler, n_level_hierarchy=8),
+                                  max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=128, seed=13,
+                                  prune_before_decode=pruned), GCPImageSimulator(model, append_latent=True))
+        model.seed = 50
+        frames, actions, latents, score = pl(state, goal)
+        res.append((frames.copy(), actions.copy(), latents.copy(), score, pl._sampler.get_dists()))
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert abs(a[3] - b[3]) <= 2e-6 * abs(a[3])
+    assert np.array_equal(a[4].mean, b[4].mean) and np.array_equal(a[4].std, b[4].std)
+    model.engine.close()

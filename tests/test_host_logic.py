@@ -114,7 +114,7 @@ class _HostSimulator:
     def __init__(self):
         self._model = type("M", (), {"engine": _HostEngine()})()
 
-    def rollout_device(self, state, goal_state, samples, rollout_len):
+    def rollout_device(self, state, goal_state, samples, rollout_len, planner_mode=None):
         return _HostRollouts(samples)
 
 

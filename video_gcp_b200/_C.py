@@ -30,7 +30,9 @@ class RolloutIO(C.Structure):
                 ("log_sigma_df", C.c_void_p), ("images_df", C.c_void_p), ("existence", C.c_void_p),
                 ("model_enc_seq", C.c_void_p), ("actions", C.c_void_p), ("regressed_state", C.c_void_p),
                 ("distances", C.c_void_p), ("pruned_nodes", C.c_void_p), ("pruned_len", C.c_void_p),
-                ("prune_threshold", C.c_float)]
+                ("prune_threshold", C.c_float),
+                ("decode_kept_only", C.c_int), ("l2_goal", C.c_void_p), ("l2_cost", C.c_void_p), ("l2_dense", C.c_int),
+                ("l2_final_step_weight", C.c_float)]
 
 
 class SeqIO(C.Structure):

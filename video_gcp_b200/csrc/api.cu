@@ -136,6 +136,10 @@ struct gcpb200_ctx {
     long long* scratch_ei = nullptr;
     long long* scratch_given = nullptr;
     int* frame_node = nullptr;
+    // planner mode "decode kept nodes only": compacted latent rows + their (candidate, node), per-image L2 sums
+    DevBuf latc;
+    int *row_cand = nullptr, *row_node = nullptr, *row_off = nullptr, *n_rows = nullptr;
+    float* frame_sq = nullptr;
     unsigned long long* topk_sel = nullptr;   // elite selection: the k selected composite keys (grown on demand)
     int topk_cap = 0;
     double* refit_part = nullptr;             // refit: per-split (sum, sum of squares) [REFIT_SPLITS][255*256][2]
@@ -833,8 +837,12 @@ static Seg seg(const DevBuf& b, int col0, int k_len, int mode = ROW_LEVEL, int r
     s.buf = &b; s.col0 = col0; s.k_len = k_len; s.mode = mode; s.row_base = row_base;
     return s;
 }
+struct GemmDyn {          // device-side row count of a launch (GemmArgs::rows_dev / rows_dev_base)
+    const int* rows_dev;
+    int base;
+};
 static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const std::vector<Seg>& segs, const DevMat& W,
-                int BN, int epi, const EpiParams& ep, int w_row0 = 0, int n_cols = -1) {
+                int BN, int epi, const EpiParams& ep, int w_row0 = 0, int n_cols = -1, const GemmDyn* dyn = nullptr) {
     GemmArgs a;
     memset(&a, 0, sizeof(a));
     a.n_seg = (int)segs.size();
@@ -868,6 +876,10 @@ static int gemm(gcpb200_ctx* c, cudaStream_t st, int rows, LevelGeom g, const st
     a.N = n_cols < 0 ? W.N : n_cols;
     a.K = K;
     a.g = g;
+    if (dyn != nullptr) {
+        a.rows_dev = dyn->rows_dev;
+        a.rows_dev_base = dyn->base;
+    }
     a.epi = ep;
     a.epi.bias = W.bias;
     ++c->launches;
@@ -1065,6 +1077,15 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->scratch_ei, 8);
     rc |= dalloc(c, &c->scratch_given, Bp);
     rc |= dalloc(c, &c->frame_node, Bp * 256);
+    if (c->model == GCPB200_MODEL_TREE) {
+        const size_t kept_cap = (size_t)MAX_LEN * Bp + 256;
+        rc |= make_buf(c, &c->latc, kept_cap, NZ_ENC);
+        rc |= dalloc(c, &c->row_cand, kept_cap);
+        rc |= dalloc(c, &c->row_node, kept_cap);
+        rc |= dalloc(c, &c->row_off, Bp + 1);
+        rc |= dalloc(c, &c->n_rows, 1);
+        rc |= dalloc(c, &c->frame_sq, 256 * Bp);
+    }
     rc |= dalloc(c, &c->refit_part, (size_t)REFIT_SPLITS * N_NODES * NZ_VAE * 2, false);
     if (rc) {
         gcpb200_destroy(c);
@@ -1303,7 +1324,7 @@ static int decoder_prepare(gcpb200_ctx* c, cudaStream_t st, int images_shared, i
 // the slot-major latents, then the tail kernel writes image node = slot - 1 of every candidate.  step 2 needs the
 // tcgen05 tail kernel (the SIMT verification kernel only takes contiguous ranges).
 static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int first, int step, int count,
-                         float* images, int n_layout, const float* I_0, const float* I_g) {
+                         float* images, int n_layout, const float* I_0, const float* I_g, const float* l2_goal = nullptr) {
     const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;   // pixel-copy head: needs the start / goal images
     const LevelGeom flat = {Bp, 0, DEPTH};
     if (step != 1 && ((step != 2 && step != 4) || c->use_ref)) {
@@ -1363,6 +1384,10 @@ static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int
             a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
             a.images = images; a.Bp = Bp; a.n_cand = B; a.slot0 = s0; a.n_slots = ns; a.n_nodes = n_layout;
             a.slot_extra = step - 1;
+            if (l2_goal != nullptr) {       // fused L2 image cost: per-image sums of squares, [cand][node]
+                a.frame_sq = c->frame_sq;
+                a.l2_goal = l2_goal;
+            }
             // one persistent CTA per SM; each takes a contiguous run of (candidate, slot) images
             const long long n_img = (long long)B * ns;
             a.src0 = I_0; a.srcg = I_g; a.src_stride = images_shared ? 0 : 3072;
@@ -1378,6 +1403,69 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
                        int n_layout, const float* I_0 = nullptr, const float* I_g = nullptr) {
     CHECK(decoder_prepare(c, st, images_shared, B, Bp));
     return decoder_slots(c, st, images_shared, B, Bp, 1, 1, n_dec, images, n_layout, I_0, I_g);
+}
+
+// Planner mode: decodes only the nodes balanced pruning keeps (DecoderModule.decode_seq restricted to the frames
+// GCPImageSimulator.rollout hands to the cost, cem_simulator.py:29-61).  The kept (candidate, frame) pairs are compacted
+// into consecutive latent rows (candidate-major); the number of rows is known to the device only, so the GEMMs and the tail
+// kernel are launched for the capacity of a chunk and read the live row count from c->n_rows.  Needs c->frame_node
+// (compute_frame_map) and the finished tree.
+static int decoder_kept(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, float* images, const float* l2_goal) {
+    const LevelGeom flat = {Bp, 0, DEPTH};
+    kept_offsets_kernel<<<1, 1024, 0, st>>>(c->end_ind, B, 1, c->row_off, c->n_rows);
+    LAUNCH_CHECK();
+    {
+        const size_t n = (size_t)B * MAX_LEN * 16;
+        gather_kept_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat.p, c->frame_node, c->end_ind, c->row_off, B, Bp,
+                                                                           MAX_LEN, 1, c->latc.p, c->row_cand, c->row_node);
+        LAUNCH_CHECK();
+    }
+    CHECK(decoder_prepare(c, st, images_shared, B, Bp));
+    const int chunk_rows = c->slot_chunk * Bp;
+    const int cap = MAX_LEN * B;                 // at most 200 kept frames per candidate
+    for (int r0 = 0; r0 < cap; r0 += chunk_rows) {
+        const int rows = std::min(chunk_rows, (cap - r0 + 255) / 256 * 256);
+        {
+            ProfScope dsc(c, st, 2);
+            GemmDyn dyn = {c->n_rows, r0};
+            CHECK(gemm(c, st, rows, flat, {seg(c->latc, 0, NZ_ENC, ROW_LEVEL, r0)}, c->dec1, 256, EPI_LINEAR,
+                       epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024), 0, -1, &dyn));
+            {
+                EpiParams e = epi_linear(ACT_RELU, c->x2.p, 2048, nullptr, 0, 2048);
+                e.rowbias = c->rowbias2;
+                e.rowbias_ld = images_shared ? 0 : 2048;
+                e.rowbias_idx = images_shared ? nullptr : c->row_cand + r0;
+                CHECK(gemm(c, st, rows, flat, {seg(c->x1, 0, 1024)}, c->dec2x, 256, EPI_LINEAR, e, 0, -1, &dyn));
+            }
+            Seg a3 = seg(c->x2, 0, 1024);
+            a3.group_cols = 256;
+            for (int q = 0; q < 16; ++q) a3.group_col[q] = dec3_window_row0(q & 7) * 256;
+            CHECK(gemm(c, st, rows, flat, {a3}, c->dec3, 256, EPI_LINEAR, epi_linear(ACT_RELU, c->x3.p, 4096, nullptr, 0, 4096), 0, -1,
+                       &dyn));
+        }
+        ProfScope tsc(c, st, 3);
+        DecTail3Args a;
+        memset(&a, 0, sizeof(a));
+        a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = images_shared ? 0 : 256 * 64;
+        a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
+        a.images = images; a.Bp = Bp; a.n_cand = B; a.n_slots = c->slot_chunk; a.n_nodes = N_NODES;
+        a.n_img_dev = c->n_rows; a.row_cand = c->row_cand; a.row_node = c->row_node; a.img_base = r0;
+        if (l2_goal != nullptr) {
+            a.frame_sq = c->frame_sq;
+            a.l2_goal = l2_goal;
+        }
+        const long long n_img = (long long)rows;
+        dec_tail3_kernel<<<(unsigned)(n_img < c->sms ? n_img : c->sms), D3_THREADS, D3_SMEM_BYTES, st>>>(a);
+        LAUNCH_CHECK();
+        if (c->profile) ++c->prof_tail_launches;
+    }
+    if (c->profile) {       // measurement aid only: the live row count is on the device
+        int n = 0;
+        GCP_CUDA_CHECK(cudaMemcpyAsync(&n, c->n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GCP_CUDA_CHECK(cudaStreamSynchronize(st));
+        c->prof_tail_images += n;
+    }
+    return 0;
 }
 
 // Inverse model on consecutive rows of the zero-padded latent sequence seq [B][200][128] and state regressor on every
@@ -1535,6 +1623,17 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         gcp_set_error("gcpb200_rollout: I_0, I_g and z are required");
         return -1;
     }
+    const bool fused_l2 = io->l2_cost != nullptr;
+    if ((io->decode_kept_only || fused_l2) && (adaptive || c->use_ref)) {
+        gcp_set_error("decode_kept_only / l2_cost need the balanced GCPB200_MODEL_TREE model");
+        return -1;
+    }
+    if (fused_l2 && !io->l2_goal) {
+        gcp_set_error("l2_cost needs l2_goal");
+        return -1;
+    }
+    const bool kept_only = io->decode_kept_only != 0 && (io->images_df != nullptr || fused_l2);
+    const bool decode_all = !kept_only && (io->images_df != nullptr || fused_l2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = io->B, Bp = (B + 127) / 128 * 128;
     const LevelGeom flat = {Bp, 0, DEPTH};
@@ -1592,7 +1691,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     // levels 0-5 (63 nodes) before tree level 6, level 6 (64 nodes) before tree level 7, level 7 (128 nodes) after it.
     // Same work in total; with host-resident noise it puts 2 ms of tensor-bound work in front of each of the two big
     // uploads (level 6: 67 MB, level 7: 133 MB at 1024 candidates) instead of stalling the recursion on PCIe.
-    const bool level_ordered = io->images_df != nullptr && !c->use_ref;
+    const bool level_ordered = decode_all && !c->use_ref;
+    const float* l2_goal = fused_l2 ? io->l2_goal : nullptr;
     float* e_df = io->e_df ? io->e_df : c->e_df;
     for (int l = 0; l < DEPTH; ++l) {
         if (level_ordered && l >= DEPTH - 2) {
@@ -1601,9 +1701,9 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             scope = nullptr;
             if (l == DEPTH - 2) {
                 CHECK(decoder_prepare(c, st, io->images_shared, B, Bp));
-                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, 63, io->images_df, N_NODES, io->I_0, io->I_g));
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, 63, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
             } else {
-                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 64, io->images_df, N_NODES, io->I_0, io->I_g));
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 64, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
             }
             scope = new ProfScope(c, st, 1);
             trace_mark(st, l == DEPTH - 2 ? "dec_l0-5_end" : "dec_l6_end");
@@ -1633,10 +1733,19 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = nullptr;
     // ---- 5. decoder over all 255 node latents
+    const bool need_map = kept_only || fused_l2 || io->model_enc_seq || io->actions || io->regressed_state;
+    if (need_map) CHECK(compute_frame_map(c, c->end_ind, B, st));
     if (level_ordered)      // level 7 = the odd slots
-        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, N_NODES / 2 + 1, io->images_df, N_NODES, io->I_0, io->I_g));
+        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, N_NODES / 2 + 1, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
+    else if (kept_only)
+        CHECK(decoder_kept(c, st, io->images_shared, B, Bp, io->images_df, l2_goal));
     else if (io->images_df)
         CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES, io->I_0, io->I_g));
+    if (fused_l2) {
+        cost_from_frames_kernel<<<B, 32, 0, st>>>(c->frame_sq, kept_only ? nullptr : c->frame_node, c->row_off, c->end_ind, N_NODES,
+                                                  MAX_LEN, io->l2_dense, io->l2_final_step_weight, 1, io->l2_cost);
+        LAUNCH_CHECK();
+    }
     if (adaptive && (io->distances || io->pruned_nodes || io->pruned_len)) {
         // AdaptiveBinding.prune_sequence: distance predictor on consecutive depth-first latents, then compaction
         ProfScope dsc(c, st, 4);
@@ -1663,7 +1772,6 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     ProfScope asc(c, st, 4);
     // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
     if (io->model_enc_seq || io->actions || io->regressed_state) {
-        CHECK(compute_frame_map(c, c->end_ind, B, st));
         float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
         const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
         gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,

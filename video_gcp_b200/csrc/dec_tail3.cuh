@@ -71,6 +71,19 @@ struct DecTail3Args {
     const float* src0;     // [n_cand or 1][3][32][32] start image
     const float* srcg;     // goal image
     int src_stride;        // elements between candidates (0: shared)
+    // ---- list mode (planner mode "decode only the nodes balanced pruning keeps"): image i of this launch is x3 row i,
+    // its (candidate, node) come from row_cand / row_node at index img_base + i, and the number of images is known to the
+    // device only: min(n_slots * Bp, max(0, *n_img_dev - img_base)).  n_cand / slot0 / slot_extra are unused.
+    const int* n_img_dev;
+    const int* row_cand;
+    const int* row_node;
+    int img_base;
+    // ---- fused L2 image cost (HEAD 0; L2ImageCost._compute, gcp/planning/cem/cost_fcn.py:65-72): sum over the image's 3072
+    // sub-pixels of (image - goal)^2, reduced in a fixed order (thread: 24 values; warp butterfly; 4 warps in order) and
+    // written to frame_sq[img_base + i] (list mode) or frame_sq[cand * n_nodes + node]; images may then be NULL (no image
+    // is written at all).
+    float* frame_sq;
+    const float* l2_goal;  // [3][32][32] in [-1,1]
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -176,7 +189,8 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
 
     // this CTA's contiguous run of images; image index = cand * n_slots + slot_local (candidate-major, so
     // a per-candidate skip term is reloaded rarely)
-    const int n_total = a.n_cand * a.n_slots;
+    const bool list = a.row_cand != nullptr;
+    const int n_total = list ? min(a.n_slots * a.Bp, max(__ldg(a.n_img_dev) - a.img_base, 0)) : a.n_cand * a.n_slots;
     const int per = (n_total + gridDim.x - 1) / gridDim.x;
     const int img0 = blockIdx.x * per;
     const int img1 = min(img0 + per, n_total);
@@ -190,7 +204,7 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
         if (bt == 0 && img0 < img1) {
             const int cand = img0 / a.n_slots, sl = img0 - cand * a.n_slots;
             mbar_arrive_expect_tx(x3_full, D3_X3_BYTES);
-            bulk_load_1d(x3s, a.x3 + ((size_t)sl * a.Bp + cand) * 4096, D3_X3_BYTES, x3_full);
+            bulk_load_1d(x3s, a.x3 + (list ? (size_t)img0 : (size_t)sl * a.Bp + cand) * 4096, D3_X3_BYTES, x3_full);
         }
         uint32_t n = 0;
         for (int img = img0; img < img1; ++img, ++n) {
@@ -243,7 +257,7 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
             if (bt == 0 && img + 1 < img1) {
                 const int ni = img + 1, cand = ni / a.n_slots, sl = ni - cand * a.n_slots;
                 mbar_arrive_expect_tx(x3_full, D3_X3_BYTES);
-                bulk_load_1d(x3s, a.x3 + ((size_t)sl * a.Bp + cand) * 4096, D3_X3_BYTES, x3_full);
+                bulk_load_1d(x3s, a.x3 + (list ? (size_t)ni : (size_t)sl * a.Bp + cand) * 4096, D3_X3_BYTES, x3_full);
             }
             mbar_arrive(&in4_full[buf]);
             pc[1] += D3_T() - t1;
@@ -327,8 +341,7 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
         uint4 sk[8];
         int loaded_cand = -1;
         for (int n = 0; n < n_img; ++n) {
-            const int cand = (img0 + n) / a.n_slots;
-            const int want = a.s4_stride == 0 ? 0 : cand;
+            const int want = a.s4_stride == 0 ? 0 : (list ? __ldg(a.row_cand + a.img_base + img0 + n) : (img0 + n) / a.n_slots);
             if (want != loaded_cand) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.s4 + (size_t)want * a.s4_stride + (size_t)(T * 128 + m) * 64);
 #pragma unroll
@@ -392,11 +405,34 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
         float bh[NCH];
 #pragma unroll
         for (int i = 0; i < NCH; ++i) bh[i] = bias5[i];
+        // fused L2 cost: this thread always owns the same 4-pixel quad of each of the two tiles -> its 24 goal values
+        // stay in registers; per-warp partial sums meet in shared memory (two slots, alternating by image)
+        const bool l2 = HEAD == 0 && a.frame_sq != nullptr;
+        float gl[2][3][4];
+        float* sq_part = reinterpret_cast<float*>(smem + D3_OFF_BAR + 208);          // 8 floats behind the barriers / TMEM holder
+        if (l2) {
+#pragma unroll
+            for (int T = 0; T < 2; ++T)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(a.l2_goal + k * 1024 + (16 * T + (m >> 3)) * 32 + 4 * (m & 7)));
+                    gl[T][k][0] = g.x; gl[T][k][1] = g.y; gl[T][k][2] = g.z; gl[T][k][3] = g.w;
+                }
+        }
         for (int n = 0; n < n_img; ++n) {
             const int img = img0 + n;
-            const int cand = img / a.n_slots, sl = img - cand * a.n_slots;
-            const int node = a.slot0 + sl * (1 + a.slot_extra) - 1;
-            float* out = a.images + ((size_t)cand * a.n_nodes + max(node, 0)) * 3072;
+            int cand, sl, node;
+            if (list) {
+                cand = __ldg(a.row_cand + a.img_base + img);
+                node = __ldg(a.row_node + a.img_base + img);
+                sl = 0;
+            } else {
+                cand = img / a.n_slots;
+                sl = img - cand * a.n_slots;
+                node = a.slot0 + sl * (1 + a.slot_extra) - 1;
+            }
+            float* out = a.images != nullptr ? a.images + ((size_t)cand * a.n_nodes + max(node, 0)) * 3072 : nullptr;
+            float sq = 0.f;
             const float* src0 = HEAD == 1 ? a.src0 + (size_t)cand * a.src_stride : nullptr;
             const float* srcg = HEAD == 1 ? a.srcg + (size_t)cand * a.src_stride : nullptr;
             for (int T = 0; T < 2; ++T, ++n5) {
@@ -464,12 +500,32 @@ __device__ __forceinline__ void dec_tail3_body(const DecTail3Args& a) {
                         rgb[k][3] += mk[0][3] * p0.w + mk[1][3] * pg.w;
                     }
                 }
-                if (node >= 0) {
+                if (node >= 0 && out != nullptr) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         *reinterpret_cast<float4*>(out + k * 1024 + oy * 32 + 4 * c) = make_float4(rgb[k][0], rgb[k][1], rgb[k][2], rgb[k][3]);
                 }
+                if (l2) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const float d = rgb[k][x] - (T == 0 ? gl[0][k][x] : gl[1][k][x]);
+                            sq = fmaf(d, d, sq);
+                        }
+                }
                 pc[1] += D3_T() - w1;
+            }
+            if (l2) {
+                // fixed-order reduction: butterfly inside the warp, then the four warps in order
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                float* slot = sq_part + 4 * (n & 1);
+                if (lane == 0) slot[q] = sq;
+                named_bar_sync(2, 128);
+                if (m == 0 && node >= 0)
+                    a.frame_sq[list ? (size_t)(a.img_base + img) : (size_t)cand * a.n_nodes + node] =
+                        ((slot[0] + slot[1]) + slot[2]) + slot[3];
             }
         }
         if (prof_on) { atomicAdd(a.prof + 8, (unsigned long long)pc[0]); atomicAdd(a.prof + 9, (unsigned long long)pc[1]); }

@@ -50,6 +50,8 @@ struct EpiParams {
     const float* bias;      // [N] in packed column order (may be null)
     const float* rowbias;   // per-candidate additive term [Bp][rowbias_ld] (may be null)
     int rowbias_ld;
+    const int* rowbias_idx; // non-null: the candidate of output row r is rowbias_idx[r] (compacted rows of the pruned
+                            // decoder) instead of r % Bp
     const float* gn_gamma;  // EPI_GN
     const float* gn_beta;
     int gn_group;           // channels per group (16 or 4)
@@ -87,6 +89,11 @@ struct GemmArgs {
     const bf16* w;   // packed weights [N][K] (K contiguous)
     int w_ld;
     int rows, N, K;  // rows % 128 == 0, N % BN == 0, K % 64 == 0
+    // Device-side row count (pruned decoder: the number of kept node rows is known to the device only): if non-null, the
+    // kernel processes min(rows, max(0, *rows_dev - rows_dev_base)) rows, rounded up to whole (cluster x 128)-row groups
+    // (the caller zero-fills the padding rows of the A operand).
+    const int* rows_dev;
+    int rows_dev_base;
     LevelGeom g;
     EpiParams epi;
 };
@@ -270,7 +277,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         if (col0 >= p.n_valid) return;
         const int nvalid = min(32, p.n_valid - col0);
         if (p.rowbias != nullptr) {
-            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)cand * p.rowbias_ld + col0);
+            const int rc = p.rowbias_idx != nullptr ? __ldg(p.rowbias_idx + row) : cand;
+            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)rc * p.rowbias_ld + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = __ldg(rb + i);
@@ -448,7 +456,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_n = args.N / BN;
-    const int tiles_m = args.rows / GEMM_BM;
     const int num_kb = args.K / GEMM_BK;
     // Thread-block clusters of C CTAs along M share the weight tile: every CTA fetches 1/C of it and TMA
     // multicasts the slice into all C shared memories, cutting L2->SM operand traffic (the bound of this
@@ -456,7 +463,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const uint32_t C = cluster_nctarank();
     const uint32_t crank = cluster_ctarank();
     const uint16_t cmask = (uint16_t)((1u << C) - 1u);
-    const int n_work = (tiles_m / (int)C) * tiles_n;          // work item = (tile_n, group of C consecutive tile_m)
     const int work0 = blockIdx.x / (int)C, work_stride = gridDim.x / (int)C;
 
     if (warp == 0 && lane == 0) {
@@ -482,6 +488,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // the previous kernel in the stream; nothing below may run before that kernel's writes are visible.
     pdl_launch_dependents();
     pdl_wait();
+    int rows = args.rows;
+    if (args.rows_dev != nullptr) {           // produced by an earlier kernel of the stream: read only after pdl_wait()
+        const int grp = GEMM_BM * (int)C;
+        const int left = max(__ldg(args.rows_dev) - args.rows_dev_base, 0);
+        rows = min(rows, (left + grp - 1) / grp * grp);
+    }
+    const int tiles_m = rows / GEMM_BM;
+    const int n_work = (tiles_m / (int)C) * tiles_n;          // work item = (tile_n, group of C consecutive tile_m)
 
     if (warp == 0) {
         if (lane == 0) {

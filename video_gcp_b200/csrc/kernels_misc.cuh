@@ -265,6 +265,87 @@ __global__ void __launch_bounds__(256) cost_l2_kernel(const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Planner mode "decode only what balanced pruning keeps": the kept (candidate, frame) pairs are compacted into
+// consecutive rows, candidate-major, frame order inside a candidate: row_off[c] = sum_{c' < c} n(c'),
+// n(c) = max(end_ind[c], min_last) + 1 (the frames the cost reads, cem_simulator.py:31), row_off[B] = *n_rows.
+// One CTA; B is a few thousand at most.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) kept_offsets_kernel(const long long* __restrict__ end_ind, int n_cand, int min_last,
+                                                            int* __restrict__ row_off, int* __restrict__ n_rows) {
+    __shared__ int wsum[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n_cand; c0 += 1024) {
+        const int c = c0 + tid;
+        const int v = c < n_cand ? max((int)end_ind[c], min_last) + 1 : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (c < n_cand) row_off[c] = off + inc - v;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += wsum[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        row_off[n_cand] = s_base;
+        *n_rows = s_base;
+    }
+}
+
+// latc[row_off[c] + t][:] = lat[(frame_node[c][t] + 1) * Bp + c][:] (bf16 rows of 128 = 16 x 16 B), + the row's
+// (candidate, node).  Thread per 16-byte piece.
+__global__ void gather_kept_rows_kernel(const bf16* __restrict__ lat, const int* __restrict__ frame_node,
+                                        const long long* __restrict__ end_ind, const int* __restrict__ row_off, int n_cand,
+                                        int Bp, int lcap, int min_last, bf16* __restrict__ latc, int* __restrict__ row_cand,
+                                        int* __restrict__ row_node) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_cand * lcap * 16) return;
+    const int k = idx & 15;
+    const int t = (idx >> 4) % lcap;
+    const int c = idx / ((size_t)16 * lcap);
+    if (t > max((int)end_ind[c], min_last)) return;
+    const int node = frame_node[c * lcap + t];
+    const int r = row_off[c] + t;
+    reinterpret_cast<uint4*>(latc)[(size_t)r * 16 + k] = __ldg(reinterpret_cast<const uint4*>(lat) + ((size_t)(node + 1) * Bp + c) * 16 + k);
+    if (k == 0) {
+        row_cand[r] = c;
+        row_node[r] = node;
+    }
+}
+
+// cost[c] = sum over the kept frames t of sqrt(frame_sq[..]) (last frame weighted; dense = 0: last frame only), from the
+// per-image sums of squares the decoder tail wrote (dec_tail3.cuh, fused L2 cost).  frame_node != null: frame_sq is
+// [c][n_nodes] (all nodes decoded); null: compact rows row_off[c] + t.  One warp per candidate, lanes stride the frames,
+// then the butterfly: the same order in both layouts, so the two decode modes give bit-identical costs.
+__global__ void cost_from_frames_kernel(const float* __restrict__ frame_sq, const int* __restrict__ frame_node,
+                                        const int* __restrict__ row_off, const long long* __restrict__ end_ind, int n_nodes,
+                                        int lcap, int dense, float final_w, int min_last, float* __restrict__ cost) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const int last = max((int)end_ind[c], min_last);
+    float s = 0.f;
+    for (int t = lane; t <= last; t += 32) {
+        if (!dense && t != last) continue;
+        const float q = frame_node != nullptr ? frame_sq[(size_t)c * n_nodes + frame_node[c * lcap + t]] : frame_sq[row_off[c] + t];
+        s += sqrtf(q) * (t == last ? final_w : 1.f);
+    }
+    s = warp_sum(s);
+    if (lane == 0) cost[c] = s;
+}
+
 // Pair rows for the learned pairwise networks from two row tables: pairs[r] = cat(a[ia[r]], b[ib[r]]) (a null index
 // list means row r itself).  Used by gcpb200_cost_pairs (LearnedCostEstimate ndarray branch, cost_fcn.py:84-87) and
 // gcpb200_infer_action (InverseModel.run_single, inverse_mdl.py:221-224).  Rows >= n are zero padding.

@@ -94,12 +94,18 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
                 want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False,
-                prune_threshold=0.5):
+                prune_threshold=0.5, decode_kept_only=False, l2_goal=None, l2_dense=True, l2_final_step_weight=1.0,
+                l2_out=None):
         """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32, either on the device or a PINNED host
         tensor; a host tensor is uploaded by the library level by level on its own copy stream, overlapped with
         the encoder and the upper tree levels (out["z"] is the device copy, valid in stream order after the call).
         Outputs live in persistent buffers owned by the engine (overwritten by the next rollout) unless
-        fresh=True."""
+        fresh=True.
+
+        Planner mode: decode_kept_only=True decodes only the nodes balanced pruning keeps (out["images_df"] then holds
+        exactly those nodes' images, the other entries keep whatever the buffer held); l2_goal ([3,32,32] in [-1,1]) adds
+        out["l2_cost"] ([B], written to `l2_out` if given), the L2 image cost reduced inside the decoder-tail kernel --
+        with want_images=False no image is written at all."""
         dev = self.device
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
@@ -140,13 +146,19 @@ class Engine:
             out["regressed_state"] = mk("regressed_state", (B, MAX_LEN, 2))
         if end_ind is not None:
             end_ind = end_ind.to(device=dev, dtype=torch.int64).contiguous()
+        if l2_goal is not None:
+            l2_goal = l2_goal.to(**f32).contiguous()
+            assert l2_goal.numel() == 3072
+            out["l2_cost"] = self._cost_out(l2_out, B) if l2_out is not None else mk("l2_cost", (B,))
+            self._l2_goal_ref = l2_goal
         io = _C.RolloutIO(
             _ptr(I_0), _ptr(I_g), int(images_shared), _ptr(z), _ptr(z_host), _ptr(end_ind), int(seed), int(B),
             _ptr(out["e_0"]), _ptr(out["e_g"]), _ptr(out.get("seq_len_logits")), _ptr(out["end_ind"]),
             _ptr(out["e_df"]), _ptr(out.get("mu_df")), _ptr(out.get("log_sigma_df")), _ptr(out.get("images_df")),
             _ptr(out.get("existence")), _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")),
             _ptr(out.get("regressed_state")), _ptr(out.get("distances")), _ptr(out.get("pruned_nodes")),
-            _ptr(out.get("pruned_len")), float(prune_threshold))
+            _ptr(out.get("pruned_len")), float(prune_threshold), int(bool(decode_kept_only)), _ptr(l2_goal),
+            _ptr(out.get("l2_cost")), int(bool(l2_dense)), float(l2_final_step_weight))
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
         return out

@@ -412,10 +412,23 @@ class TreeModel(_GCPModelBase):
         inputs.reference_tensor = inputs.I_0
         if "start_ind" not in inputs:
             inputs.start_ind = torch.zeros(B, dtype=torch.long, device=dev)
+        # planner mode (optional `inputs.planner_mode`, set by GCPImageSimulator.rollout_device for the CEM planner): decode
+        # only the nodes balanced pruning keeps, and / or reduce the L2 image cost inside the decoder
+        pm = inputs.get("planner_mode", None)
+        kw, want_images = {}, self.return_images
+        if pm is not None and self.ENGINE_KIND == "tree":
+            want_images = want_images and bool(pm.get("images", True))
+            kw = dict(decode_kept_only=bool(pm.get("kept_only", True)))
+            if pm.get("l2", None) is not None:
+                kw.update(l2_goal=inputs.I_g[0], l2_dense=bool(pm["l2"][0]), l2_final_step_weight=float(pm["l2"][1]),
+                          l2_out=pm.get("l2_out", None))
         res = eng.rollout(inputs.I_0, inputs.I_g, z, end_ind=inject, seed=self.seed, images_shared=shared,
-                          want_images=self.return_images, want_prior=self.return_prior,
-                          prune_threshold=self._hp.learned_pruning_threshold)
+                          want_images=want_images, want_prior=self.return_prior,
+                          prune_threshold=self._hp.learned_pruning_threshold, **kw)
         self.seed += 1
+        if "l2_cost" in res:
+            outputs.l2_cost = res["l2_cost"]
+            outputs.l2_spec = (bool(pm["l2"][0]), float(pm["l2"][1]))
         inputs.e_0 = res["e_0"][..., None, None]
         inputs.e_g = res["e_g"][..., None, None]
         outputs.seq_len_logits = res["seq_len_logits"]

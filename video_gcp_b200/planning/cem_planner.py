@@ -35,10 +35,23 @@ class CEMPlanner:
             sampler=FlatCEMSampler, sampler_clip_val=float("Inf"), initial_std=3e-1,
             verbose=False, dump_planning_data=False, use_delta_state_actions=False, use_inferred_actions=True,
             max_seq_len=None, seed=0,
+            # True: roll out in planner mode -- only the nodes balanced pruning keeps are decoded (the planner never reads
+            # the others) and an L2 image cost is reduced inside the decoder, so CEM iterations write no images at all;
+            # costs / elites / plans are identical to False, which decodes all 255 nodes of every candidate as the
+            # reference does (cem_simulator.py:29-61 then discards them)
+            prune_before_decode=True,
         )
 
     def _build_cost(self):
         return self._hp.cost_fcn(self._hp.dense_cost, self._hp.final_step_cost_weight)
+
+    def _planner_mode(self, images, l2_out=None):
+        """rollout_device kwargs for a rollout whose frames are / are not needed beyond the cost."""
+        if not self._hp.prune_before_decode:
+            return {}
+        spec = self._cost_fcn.fused_spec() if hasattr(self._cost_fcn, "fused_spec") else None
+        latent_cost = hasattr(self._cost_fcn, "pairs_device")       # learned latent-space cost: reads no image at all
+        return dict(planner_mode=dict(kept_only=True, images=images or (spec is None and not latent_cost), l2=spec, l2_out=l2_out))
 
     def _build_sampler(self):
         return self._hp.sampler(self._hp.sampler_clip_val, self._hp.max_seq_len, self._hp.action_dim, self._hp.initial_std)
@@ -67,7 +80,8 @@ class CEMPlanner:
             raise NotImplementedError("%s needs all candidates in one rollout (raise max_rollout_bs)" % type(self._cost_fcn).__name__)
         z_dev = []
         for s, e in chunks:
-            ro = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len)
+            ro = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len,
+                                                **self._planner_mode(images=False, l2_out=cost[s:e]))
             self._cost_fcn.device_cost(ro, out=cost[s:e])
             if not z.is_cuda:
                 z_dev.append(ro.z if len(chunks) == 1 else ro.z.clone())    # device copy of host-resident samples
@@ -111,7 +125,8 @@ class CEMPlanner:
         """Final rollout of the best samples (cem_planner.py:81-82), joined over chunks, as host lists."""
         out = None
         for s, e in self._chunks(z.shape[0]):
-            part = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len).to_host(self._simulator._append_latent)
+            part = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len,
+                                                  **self._planner_mode(images=True)).to_host(self._simulator._append_latent)
             if out is None:
                 out = part
             else:
@@ -131,9 +146,11 @@ class CEMPlanner:
         final = self._rollout_host(state, goal_state, best)
         self._sampler.sync_host()
         scores = val.cpu().numpy()
-        logs.append(AttrDict(elite_rollouts=copy.deepcopy(self._maybe_split_image(final.predictions)),
+        # (the reference deep-copies the elite rollouts into its log, cem_planner.py:83-89; these arrays are fresh host
+        # copies that nothing else writes, so the log holds them as they are)
+        logs.append(AttrDict(elite_rollouts=self._maybe_split_image(final.predictions),
                              elite_scores=scores, dists=self._sampler.get_dists(), goal_state=goal_state,
-                             elite_states=copy.deepcopy(final.states)))
+                             elite_states=final.states))
         self._logs.append(logs)
         best_actions = self._get_action_plan(final, best)
         return final.predictions[0], best_actions[0], final.latents[0], float(scores[0])

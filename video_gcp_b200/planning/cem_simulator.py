@@ -17,6 +17,8 @@ class DeviceRollouts:
         self.model, self.inputs, self.outputs, self.goal_chw = model, inputs, outputs, goal_chw
         self.end_ind = torch.max(outputs.end_ind, torch.ones_like(outputs.end_ind))   # cem_simulator.py:31
         self.z = outputs.z_device          # device copy of the noise that was rolled out
+        self.l2_cost = outputs.get("l2_cost", None)     # planner mode: L2 image cost reduced inside the decoder
+        self.l2_spec = outputs.get("l2_spec", None)     # (dense_cost, final_step_weight) it was computed with
         self.sequential = "tree" not in outputs
         if self.sequential:
             # sequential model: frames / latents are stored in time order (frame 0 = start image, latent 0 = e_0)
@@ -30,28 +32,39 @@ class DeviceRollouts:
         return int(self.end_ind.shape[0])
 
     def to_host(self, append_latent, idx=None):
-        """AttrDict(predictions, actions, states, latents) of numpy lists, for candidates `idx` (default all)."""
+        """AttrDict(predictions, actions, states, latents) of numpy lists, for candidates `idx` (default all).
+        One device-side gather per field, one D2H copy per field into pinned host memory (a pageable destination costs
+        ~10x the copy time at 250 MB of elite frames); the per-candidate arrays are views of those host blocks, which stay
+        alive as long as any of the arrays does."""
         eng = self.model.engine
         ends = self.end_ind.tolist()
-        sel = list(range(len(ends))) if idx is None else [int(i) for i in idx]
-        sel_t = torch.as_tensor(sel, device=self.end_ind.device)
-        end_sel = self.end_ind[sel_t]
+        n_all = len(ends)
+        sel = list(range(n_all)) if idx is None else [int(i) for i in idx]
+        take = (lambda t: t) if idx is None else (lambda t, i=torch.as_tensor(sel, device=self.end_ind.device): t[i])
+        end_sel = take(self.end_ind)
         if self.sequential:
             # cem_simulator.py:45-58 with SequentialRecModule.get_sample_with_len (sequential.py:78-94); `latents`
             # is inputs.model_enc_seq capped to the predicted length (cem_simulator.py:41)
-            img = self.images_seq[sel_t].reshape(len(sel), self.images_seq.shape[1], -1)
-            lat = torch.cat([self.inputs.e_0[sel_t][:, None, :, 0, 0], self.enc_seq[sel_t]], 1)
+            img = take(self.images_seq).reshape(len(sel), self.images_seq.shape[1], -1)
+            lat = torch.cat([take(self.inputs.e_0)[:, None, :, 0, 0], take(self.enc_seq)], 1)
         else:
-            img = eng.prune_gather(self.images_df[sel_t], end_sel)
-            lat = eng.prune_gather(self.e_df[sel_t], end_sel)
+            img = eng.prune_gather(take(self.images_df), end_sel)
+            lat = eng.prune_gather(take(self.e_df), end_sel)
         if append_latent:
             img = torch.cat([img, lat], -1)
-        img, lat = img.cpu().numpy(), lat.cpu().numpy()
         # the reference pads these two to the longest sequence of the batch (pad_sequence, base_gcp.py:242): actions
         # [B, lmax - 1], states [B, lmax]; the device buffers are full length when the length sync was deferred
         lmax = self.outputs["_lmax"]()
-        act = self.outputs.actions[sel_t][:, :lmax - 1].cpu().numpy()
-        sta = self.outputs.regressed_state[sel_t][:, :lmax].cpu().numpy()
+        act = take(self.outputs.actions)[:, :lmax - 1]
+        sta = take(self.outputs.regressed_state)[:, :lmax]
+
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        img, lat, act, sta = pinned(img), pinned(lat), pinned(act), pinned(sta)
+        torch.cuda.current_stream(self.end_ind.device).synchronize()
+        img, lat, act, sta = img.numpy(), lat.numpy(), act.numpy(), sta.numpy()
         out = AttrDict(predictions=[], actions=[], states=[], latents=[])
         for n, i in enumerate(sel):
             L = ends[i] + 1
@@ -73,8 +86,11 @@ class GCPSimulator:
     def _postprocess_inputs(self, input_dict):
         return input_dict
 
-    def rollout_device(self, state, goal_state, samples, rollout_len):
+    def rollout_device(self, state, goal_state, samples, rollout_len, planner_mode=None):
         """samples: numpy [B,255,256] ([B,199,256] for the sequential model) or a CUDA tensor (kept on device).
+        planner_mode (tree model): dict(kept_only=True, images=True/False, l2=(dense_cost, final_step_weight) or None,
+        l2_out=[B] destination or None) -- decode only the frames the planner reads and fold the L2 image cost into the
+        decoder (see gcpb200_rollout_io.decode_kept_only).  None = the reference behaviour, every node decoded.
         Returns DeviceRollouts."""
         dev = self._model.engine.device
         B = samples.shape[0]
@@ -91,6 +107,8 @@ class GCPSimulator:
             start_ind=torch.zeros(B, dtype=torch.long, device=dev),
             end_ind=torch.full((B,), rollout_len - 1, dtype=torch.long, device=dev),
             z=z, images_shared=True)
+        if planner_mode is not None:
+            input_dict.planner_mode = planner_mode
         input_dict = self._postprocess_inputs(input_dict)
         input_dict.I_0 = input_dict.I_0.to(dev, non_blocking=True)
         input_dict.I_g = input_dict.I_g.to(dev, non_blocking=True)

@@ -51,9 +51,20 @@ class L2ImageCost(CostFcn, ImageCost):
         super().__init__(dense_cost, final_step_weight)
         self.engine = engine
 
+    def fused_spec(self):
+        """(dense_cost, final_step_weight): what the rollout needs to reduce this cost inside the decoder-tail kernel."""
+        return (bool(self._dense_cost), float(self._final_step_weight))
+
     def device_cost(self, ro, out=None):
         """[B] costs of a DeviceRollouts; `out`: caller-owned destination (else an engine buffer that the next cost
-        call overwrites)."""
+        call overwrites).  A rollout made in planner mode already carries the cost (same bits as the kernel below gives on
+        its frames up to summation order, identical between the two decode modes)."""
+        if getattr(ro, "l2_cost", None) is not None and ro.l2_spec == self.fused_spec():
+            if out is None:
+                return ro.l2_cost
+            if out.data_ptr() != ro.l2_cost.data_ptr():
+                out.copy_(ro.l2_cost)
+            return out
         if ro.sequential:
             return ro.model.engine.cost_l2_seq(ro.images_seq, ro.end_ind, ro.goal_chw, self._dense_cost,
                                                self._final_step_weight, out=out)

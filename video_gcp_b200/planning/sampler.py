@@ -62,7 +62,7 @@ class FlatCEMSampler(CEMSampler):
         seed = (self.seed * 1000003 + self._draws) & 0xFFFFFFFFFFFFFFFF
         self._draws += 1
         self._last_seed = seed
-        self._last_dist = (self._mean_d, self._std_d)      # the distribution this draw is taken from (regenerate uses it)
+        self._last_dist = (getattr(self, "_mean_d", None), getattr(self, "_std_d", None))    # distribution of this draw
         return seed
 
     def sample_device(self, n_samples, first_id=0, out=None):
