@@ -46,10 +46,12 @@ class CEMPlanner:
         return self._hp.cost_fcn(self._hp.dense_cost, self._hp.final_step_cost_weight)
 
     def _planner_mode(self, images, l2_out=None):
-        """rollout_device kwargs for a rollout whose frames are / are not needed beyond the cost."""
-        if not self._hp.prune_before_decode:
-            return {}
+        """rollout_device kwargs for a rollout whose frames are / are not needed beyond the cost.  Either way an L2 image
+        cost is reduced inside the decoder (same bits in both modes); prune_before_decode decides whether the decoder
+        visits the kept nodes only (and skips the image writes the caller does not need) or all 255 nodes."""
         spec = self._cost_fcn.fused_spec() if hasattr(self._cost_fcn, "fused_spec") else None
+        if not self._hp.prune_before_decode:
+            return dict(planner_mode=dict(kept_only=False, images=True, l2=spec, l2_out=l2_out))
         latent_cost = hasattr(self._cost_fcn, "pairs_device")       # learned latent-space cost: reads no image at all
         return dict(planner_mode=dict(kept_only=True, images=images or (spec is None and not latent_cost), l2=spec, l2_out=l2_out))
 
@@ -121,12 +123,15 @@ class CEMPlanner:
         z, z_elite = packed
         return z_elite if z_elite is not None else z[idx.long()]
 
-    def _rollout_host(self, state, goal_state, z):
-        """Final rollout of the best samples (cem_planner.py:81-82), joined over chunks, as host lists."""
+    def _rollout_host(self, state, goal_state, z, only_best=False):
+        """Final rollout of the best samples (cem_planner.py:81-82), joined over chunks, as host lists.  only_best: all
+        elites are rolled out, but only elite 0 -- the plan -- is copied to the host."""
         out = None
         for s, e in self._chunks(z.shape[0]):
-            part = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len,
-                                                  **self._planner_mode(images=True)).to_host(self._simulator._append_latent)
+            ro = self._simulator.rollout_device(state, goal_state, z[s:e], self._hp.max_seq_len, **self._planner_mode(images=True))
+            if only_best and s > 0:
+                continue
+            part = ro.to_host(self._simulator._append_latent, idx=[0] if only_best else None)
             if out is None:
                 out = part
             else:
@@ -138,20 +143,21 @@ class CEMPlanner:
         self._sampler.init()
         logs = []
         best = val = None
+        # the reference logs every elite rollout of every call (cem_planner.py:71-89); that is 100+ MB of frames per plan,
+        # so they are only brought to the host when something will read them (log_verbose with verbose / dump_planning_data)
+        full_logs = bool(self._hp.verbose or self._hp.dump_planning_data)
         for _ in range(self._hp.n_iters):
             cost, idx, val, packed = self.cem_iteration(state, goal_state)
             best = self._elite_samples(packed, idx)
-            logs.append(AttrDict(elite_scores=val.cpu().numpy(), goal_state=goal_state))
+            logs.append(AttrDict(elite_scores=val if not full_logs else val.cpu().numpy(), goal_state=goal_state))
         # final rollout of the elites with the best samples (cem_planner.py:81-96)
-        final = self._rollout_host(state, goal_state, best)
-        self._sampler.sync_host()
+        final = self._rollout_host(state, goal_state, best, only_best=not full_logs)
         scores = val.cpu().numpy()
-        # (the reference deep-copies the elite rollouts into its log, cem_planner.py:83-89; these arrays are fresh host
-        # copies that nothing else writes, so the log holds them as they are)
-        logs.append(AttrDict(elite_rollouts=self._maybe_split_image(final.predictions),
-                             elite_scores=scores, dists=self._sampler.get_dists(), goal_state=goal_state,
-                             elite_states=final.states))
-        self._logs.append(logs)
+        if full_logs:
+            self._sampler.sync_host()
+            logs.append(AttrDict(elite_rollouts=self._maybe_split_image(final.predictions), elite_scores=scores,
+                                 dists=self._sampler.get_dists(), goal_state=goal_state, elite_states=final.states))
+            self._logs.append(logs)
         best_actions = self._get_action_plan(final, best)
         return final.predictions[0], best_actions[0], final.latents[0], float(scores[0])
 
@@ -165,7 +171,7 @@ class CEMPlanner:
             return [b[1:] - b[:-1] for b in final_rollouts.states]
         elif self._hp.use_inferred_actions:
             return final_rollouts.actions
-        return best_samples.cpu().numpy()
+        return best_samples[:1].cpu().numpy()
 
     def log_verbose(self, logger, step, phase, i_tr, dump_dir):
         self._logs = []

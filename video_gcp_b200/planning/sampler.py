@@ -51,6 +51,7 @@ class FlatCEMSampler(CEMSampler):
         self._mean_d = self._std_d = None
 
     def get_dists(self):
+        self.sync_host()
         return AttrDict(mean=self.mean, std=self.std)
 
     # ---- device path ----
@@ -81,9 +82,11 @@ class FlatCEMSampler(CEMSampler):
         self._mean_d, self._std_d = self.engine.refit(z, elite_idx)
 
     def sync_host(self):
-        if self._mean_d is not None:
+        """Brings the host copies of mean / std up to date with the device refit (lazily: get_dists() calls it)."""
+        if self._mean_d is not None and getattr(self, "_synced", None) is not self._mean_d:
             self.mean = self._mean_d.double().cpu().numpy()
             self.std = self._std_d.double().cpu().numpy()
+            self._synced = self._mean_d
 
 
 class SimpleTreeCEMSampler(FlatCEMSampler):
