@@ -196,8 +196,18 @@ def run_reference(args):
 
 
 def timed(fn, steps, warmup, world, dev, dist):
+    import gc
     for _ in range(warmup):
         fn()
+    gc.collect()
+    gc.disable()              # a generation-2 collection inside the K timed steps would be charged to the step
+    try:
+        return _timed(fn, steps, world, dev, dist)
+    finally:
+        gc.enable()
+
+
+def _timed(fn, steps, world, dev, dist):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -287,9 +297,16 @@ def main():
     def step_value():
         return planner.cem_iteration(state_t, goal_t)
 
+    trace = os.environ.get("BENCH_TRACE") == "1"      # per-call host wall times on stderr (diagnostic)
+
     def step_e2e():
+        t0 = time.perf_counter()
         cost, idx, val, _ = planner.cem_iteration(state_t, goal_t)
-        return cost.cpu(), idx.cpu()
+        t1 = time.perf_counter()
+        out = cost.cpu(), idx.cpu()
+        if trace:
+            print("[e2e] enqueue %.2f ms, read-back wait %.2f ms" % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3), file=sys.stderr)
+        return out
 
     clocks = ClockSampler(local)
     if rank == 0:

@@ -301,6 +301,42 @@ int main() {
         report("T5 projections s_c (f32)", d, ma, 1e-4);
     }
 
+    // ---------------- T1b: CTA-pair MMA (cta_group::2, M = 256), linear epilogue, 2 K-segments, several tiles per pair -----
+    {
+        const int rows = 2048, N = 1024, K1 = 128, K2 = 192, K = K1 + K2;
+        bf16* A1 = dev_bf16((size_t)rows * K1, 1.f);
+        bf16* A2 = dev_bf16((size_t)rows * 256, 1.f);
+        bf16* Wd = dev_bf16((size_t)N * K, 0.1f);
+        float* bias = dev_f32(N, 0.5f);
+        float* o_tc = dev_zero<float>((size_t)rows * N);
+        float* o_ref = dev_zero<float>((size_t)rows * N);
+        bf16* b_tc = dev_zero<bf16>((size_t)rows * N);
+        bf16* b_ref = dev_zero<bf16>((size_t)rows * N);
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_seg = 2;
+        a.seg[0] = {A1, K1, 0, K1, ROW_LEVEL, 0, 0, {0}};
+        a.seg[1] = {A2, 256, 64, K2, ROW_LEVEL, 0, 0, {0}};
+        if (make_tmap_bf16(&a.a_map[0], A1, rows, K1, K1, 128)) return 2;
+        if (make_tmap_bf16(&a.a_map[1], A2, rows, 256, 256, 128)) return 2;
+        a.w = Wd; a.w_ld = K; a.rows = rows; a.N = N; a.K = K;
+        a.g = {128, 0, 8};
+        a.epi.bias = bias; a.epi.act = ACT_LRELU; a.epi.n_valid = N;
+        a.epi.out_f32_ld = N; a.epi.out_bf16_ld = N;
+        a.epi.out_f32 = o_tc; a.epi.out_bf16 = b_tc;
+        if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 128)) return 2;
+        for (int rep = 0; rep < 3; ++rep)            // repeated launches: barrier phases / TMEM reuse across launches
+            if (launch_gemm(a, 256, EPI_LINEAR, false, 0, 8 /* few CTAs: 4 pairs, 8 work items each */, 2)) return 2;
+        a.epi.out_f32 = o_ref; a.epi.out_bf16 = b_ref;
+        if (make_tmap_bf16(&a.w_map, Wd, N, K, K, 256)) return 2;
+        if (launch_gemm(a, 256, EPI_LINEAR, true, 0, sms)) return 2;
+        CK(cudaDeviceSynchronize());
+        double ma, d = max_diff_f32(o_tc, o_ref, (size_t)rows * N, &ma);
+        report("T1b CTA-pair linear f32 (cluster 2)", d, ma, 1e-4);
+        d = max_diff_bf16(b_tc, b_ref, (size_t)rows * N, &ma);
+        report("T1b CTA-pair linear bf16 (cluster 2)", d, ma, 1e-2);
+    }
+
     // ---------------- T4b: cluster multicast of the weight tile (clusters of 2, 4, 8 CTAs along M) ---------
     for (int cl : {2, 4, 8}) {
         const int Bp = 1024, level = 0, depth = 8, H = 512;

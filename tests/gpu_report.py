@@ -41,7 +41,7 @@ def main():
     outs = {}
     for mode in ("ref", "tc"):
         print("== %s kernels ==" % mode)
-        from tests.verify_lib import verify_engine
+        from verify_lib import verify_engine
         eng = verify_engine(dev, max_candidates=128, attach_cost_mdl=True) if mode == "ref" else \
             Engine(dev, max_candidates=128, attach_cost_mdl=True)
         eng.load_weights(sd)

@@ -37,7 +37,7 @@ def main():
     print("oracle (CPU, %d threads) B=%d: %.2f s" % (torch.get_num_threads(), B, time.time() - t0))
     dev = torch.device("cuda:0")
     for use_ref in (True, False):
-        from tests.verify_lib import verify_engine
+        from verify_lib import verify_engine
         eng = verify_engine(dev, max_candidates=max(B, 128), model="sequential") if use_ref else \
             Engine(dev, max_candidates=max(B, 128), model="sequential")
         eng.load_weights(sd)

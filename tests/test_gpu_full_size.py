@@ -117,10 +117,10 @@ def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
         "import sys, hashlib, torch\n"
-        "sys.path.insert(0, %r)\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')\n"
         "from video_gcp_b200 import hparams\n"
         "from video_gcp_b200.engine import Engine\n"
-        "from tests.verify_lib import verify_engine\n"
+        "from verify_lib import verify_engine\n"
         "from video_gcp_b200.synthetic import synthetic_rollout_inputs, synthetic_state_dict\n"
         "dev = torch.device('cuda:0')\n"
         "hp = hparams.build_hparams(hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True))\n"
@@ -134,7 +134,7 @@ def test_fused_row_mlp_is_bit_identical_to_the_layerwise_path(dev):
         "h = hashlib.sha256()\n"
         "for k in ('e_df', 'mu_df', 'log_sigma_df', 'images_df', 'existence', 'actions', 'regressed_state', 'seq_len_logits'):\n"
         "    h.update(out[k].cpu().numpy().tobytes())\n"
-        "print('HASH', h.hexdigest(), eng.launch_count())\n" % root)
+        "print('HASH', h.hexdigest(), eng.launch_count())\n" % (root, root))
     res = {}
     for name, env in (("shipped", {}), ("fused", {}), ("layerwise", {"GCPB200_NO_FUSED_MLP": "1"}), ("no_pdl", {"GCPB200_NO_PDL": "1"})):
         p = subprocess.run([sys.executable, "-c", code, name], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)

@@ -175,7 +175,7 @@ def test_tc_kernels_match_simt_verification_kernels(dev, sd):
     from video_gcp_b200.engine import Engine
     inp = synthetic_rollout_inputs(5, seed=33, shared_images=True)
     outs = []
-    from tests.verify_lib import verify_engine
+    from verify_lib import verify_engine
     for use_ref in (True, False):
         # SIMT cross-check kernels live in the separately built verification library, not in the shipped one
         eng = verify_engine(dev, max_candidates=128, attach_cost_mdl=True) if use_ref else \

@@ -133,7 +133,7 @@ def test_adaptive_tc_kernels_match_simt_verification_kernels(dev, ada_sd):
     from video_gcp_b200.engine import Engine
     inp = synthetic_rollout_inputs(4, seed=37, shared_images=True)
     outs = []
-    from tests.verify_lib import verify_engine
+    from verify_lib import verify_engine
     for use_ref in (True, False):
         eng = verify_engine(dev, max_candidates=128, model="tree_adaptive") if use_ref else \
             Engine(dev, max_candidates=128, model="tree_adaptive")

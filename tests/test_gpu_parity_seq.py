@@ -128,7 +128,7 @@ def test_seq_tc_kernels_match_simt_verification_kernels(dev, seq_sd):
     from video_gcp_b200.engine import Engine
     inp = synthetic_seq_inputs(3, seed=35, shared_images=True)
     outs = []
-    from tests.verify_lib import verify_engine
+    from verify_lib import verify_engine
     for use_ref in (True, False):
         eng = verify_engine(dev, max_candidates=128, model="sequential") if use_ref else \
             Engine(dev, max_candidates=128, model="sequential")

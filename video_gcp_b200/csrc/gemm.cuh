@@ -422,20 +422,22 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
 // ---------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+// PAIR: the CTAs of a 2-CTA cluster run one M = 256 MMA (tcgen05 cta_group::2, see common.cuh): a CTA stages its own 128
+// rows of A and half of the B tile, so a stage is 32 KB instead of 48 KB at BN = 256 and six of them fit.
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256 && !PAIR) ? 4 : 6;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STORE_STAGE_BYTES = GEMM_EPI_WARPS * 2048;   // per-warp transpose tile of the bf16 store path
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STORE_STAGE_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -470,15 +472,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tma_prefetch_desc(&args.w_map);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], C);       // released by the UMMA issuer of every CTA in the cluster
+            mbar_init(&empty_bar[s], PAIR ? 1 : C);   // released by the UMMA issuer of every CTA in the cluster (PAIR: the leader's)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 32 * GEMM_EPI_WARPS);
+            // PAIR: one arrival per epilogue warp of BOTH CTAs, on the leader's barrier
+            mbar_init(&tmem_empty[s], PAIR ? 2 * GEMM_EPI_WARPS : 32 * GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(tmem_holder, Cfg::TMEM_COLS);
+        else tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     if (C > 1) cluster_sync_all();             // peers' barriers are initialised before any remote arrive
@@ -514,6 +520,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     for (int kk = 0; kk < sg.k_len; kk += GEMM_BK, ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                        if (PAIR) {
+                            // both CTAs' bytes are counted on the LEADER's barrier: it expects two stages' worth
+                            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                            tma_load_2d_pair(sa, &args.a_map[s], lead_bar, c0 + kk, row0);
+                            tma_load_2d_pair(sa + Cfg::A_BYTES, &args.w_map, lead_bar, kb * GEMM_BK, tile_n * BN + (int)crank * (BN / 2));
+                            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         tma_load_2d(sa, &args.a_map[s], &full_bar[stage], c0 + kk, row0);
                         if (C == 1)
@@ -527,9 +542,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== UMMA issuer (single thread) =====
-            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+        if (lane == 0 && (!PAIR || crank == 0)) {
+            // ===== UMMA issuer (single thread; PAIR: of the leader CTA, for both) =====
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -545,13 +560,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    if (C == 1) umma_commit(&empty_bar[stage]);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        if (PAIR) umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (PAIR) umma_commit_pair(&empty_bar[stage], 3);
+                    else if (C == 1) umma_commit(&empty_bar[stage]);
                     else umma_commit_mcast(&empty_bar[stage], cmask);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[as]);
+                if (PAIR) umma_commit_pair(&tmem_full[as], 3);
+                else umma_commit(&tmem_full[as]);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -581,7 +600,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 __syncwarp();
                 tmem_ld32_pair(t0 + ch0 * 32, t0 + (ch0 + 1) * 32, a0, a1);
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[as]);
+                if (PAIR) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                } else {
+                    mbar_arrive(&tmem_empty[as]);
+                }
                 const int c0 = tile_n * BN + ch0 * 32;
                 epilogue_math_fast<EPI>(args.epi, c0, a0, gn_sm);
                 epilogue_math_fast<EPI>(args.epi, c0 + 32, a1, gn_sm);
@@ -602,7 +626,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                     (EPI == EPI_GN && args.N <= 256) ? gn_sm : nullptr);
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            if (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+            } else {
+                mbar_arrive(&tmem_empty[as]);
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
@@ -612,7 +641,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

@@ -79,9 +79,24 @@ inline bool gemm_pdl_enabled() {
 #endif
 }
 
-template <int BN, int EPI>
+// CTA-pair MMAs for the BN = 256 GEMMs whose launch uses 2-CTA clusters (GCPB200_NO_PAIR=1 in the verification build
+// switches back to two independent M = 128 CTAs with a multicast weight tile, for A/B measurements).
+inline bool gemm_pair_enabled() {
+#ifdef GCPB200_VERIFY
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GCPB200_NO_PAIR");
+        on = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+#else
+    return true;
+#endif
+}
+
+template <int BN, int EPI, bool PAIR = false>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, PAIR>;
     // function attributes and occupancy are per device: one slot per device ordinal (a process normally drives one GPU,
     // but nothing here should break when it owns several contexts)
     static bool configured_dev[64] = {false};
@@ -91,7 +106,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster)
     dev &= 63;
     int* max_clusters = max_clusters_dev[dev];
     if (!configured_dev[dev]) {
-        GCP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GCP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES));
         configured_dev[dev] = true;
     }
@@ -116,13 +131,13 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, int cluster)
     if (max_clusters[cluster] == 0) {
         cfg.gridDim = dim3(num_sms / cluster * cluster);
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, EPI>, &cfg) != cudaSuccess || n <= 0) n = num_sms / cluster;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, EPI, PAIR>, &cfg) != cudaSuccess || n <= 0) n = num_sms / cluster;
         max_clusters[cluster] = n;
     }
     const int n_work = (a.rows / GEMM_BM / cluster) * (a.N / BN);
     const int n_clusters = n_work < max_clusters[cluster] ? n_work : max_clusters[cluster];
     cfg.gridDim = dim3(n_clusters * cluster);
-    GCP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, a));
+    GCP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, PAIR>, a));
     return 0;
 }
 
@@ -155,6 +170,14 @@ inline int launch_gemm(const GemmArgs& a, int BN, int epi, bool use_ref, cudaStr
             case EPI_GN: return launch_gemm_tc<128, EPI_GN>(a, st, num_sms, cluster);
         }
     } else if (BN == 256) {
+        if (cluster == 2 && gemm_pair_enabled()) {
+            // an even number of 128-row tiles: CTA pairs run M = 256 MMAs (cta_group::2)
+            switch (epi) {
+                case EPI_LINEAR: return launch_gemm_tc<256, EPI_LINEAR, true>(a, st, num_sms, cluster);
+                case EPI_REPARAM: return launch_gemm_tc<256, EPI_REPARAM, true>(a, st, num_sms, cluster);
+                case EPI_LSTM: return launch_gemm_tc<256, EPI_LSTM, true>(a, st, num_sms, cluster);
+            }
+        }
         switch (epi) {
             case EPI_LINEAR: return launch_gemm_tc<256, EPI_LINEAR>(a, st, num_sms, cluster);
             case EPI_REPARAM: return launch_gemm_tc<256, EPI_REPARAM>(a, st, num_sms, cluster);
