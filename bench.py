@@ -415,11 +415,7 @@ def main():
             other = world - 1
             ids = torch.arange(other * B, (other + 1) * B, device=dev, dtype=torch.int32)
             model.seed = seed0
-            c2 = torch.empty(B, device=dev)
-            for s, e in planner._chunks(B):
-                z2 = planner._sampler.regenerate(ids[s:e])
-                ro = sim.rollout_device(state_t, goal_t, z2, 200)
-                planner._cost_fcn.device_cost(ro, out=c2[s:e])
+            c2, _ = planner._rollout_costs(state_t, goal_t, planner._sampler.regenerate(ids))
             reroll = bool(torch.equal(c2, cost[other * B:(other + 1) * B]))
         flag = torch.tensor([1.0 if (same and reroll) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -329,7 +329,7 @@ def test_sharded_planner_nccl_two_ranks(dev, sd):
         cost = torch.empty(N, device=dev)
         for s, e in pl._chunks(N):
             model.seed = it
-            ro = pl._simulator.rollout_device(state, goal, z[s:e], 200)
+            ro = pl._simulator.rollout_device(state, goal, z[s:e], 200, **pl._planner_mode(images=False, l2_out=cost[s:e]))
             pl._cost_fcn.device_cost(ro, out=cost[s:e])
         idx, val = model.engine.topk(cost, int(N * 0.1))
         pl._sampler.fit_device(z, idx)
