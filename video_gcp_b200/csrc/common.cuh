@@ -291,6 +291,11 @@ __device__ __forceinline__ float tanhf_(float x) {
     // tanh(x) = 1 - 2 / (1 + e^{2x})
     return 1.0f - 2.0f * fast_rcp(1.0f + fast_ex2(2.8853900817779268f * x));
 }
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float lrelu_(float x) { return x > 0.f ? x : 0.2f * x; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

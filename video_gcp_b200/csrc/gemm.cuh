@@ -390,15 +390,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
                 cprev[2 * i + 1] = t.y;
             }
         }
+        // One MUFU op per gate (tanh.approx.f32; sigmoid(x) = 0.5 * tanh(x / 2) + 0.5) instead of ex2 + rcp: the cell update
+        // is MUFU-bound (5 instead of 10 ops per hidden unit), and a gate GEMM tile's epilogue is as long as its MMAs.
+        // tanh.approx: max relative error 2^-11, below the bf16 rounding (2^-9) of the h / c that leave this epilogue.
         float h[8], c[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float ig = sigmoidf_(acc[u]);
-            const float fg = sigmoidf_(acc[8 + u]);
-            const float gg = tanhf_(acc[16 + u]);
-            const float og = sigmoidf_(acc[24 + u]);
+            const float ig = fmaf(0.5f, tanh_mufu(0.5f * acc[u]), 0.5f);
+            const float fg = fmaf(0.5f, tanh_mufu(0.5f * acc[8 + u]), 0.5f);
+            const float gg = tanh_mufu(acc[16 + u]);
+            const float og = fmaf(0.5f, tanh_mufu(0.5f * acc[24 + u]), 0.5f);
             c[u] = fg * cprev[u] + ig * gg;
-            h[u] = og * tanhf_(c[u]);
+            h[u] = og * tanh_mufu(c[u]);
         }
         uint4 hv, cv;
         hv.x = pack_bf16x2(h[0], h[1]); hv.y = pack_bf16x2(h[2], h[3]);
