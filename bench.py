@@ -48,11 +48,11 @@ TAIL_FLOP_PER_IMAGE = 2 * (8.388608e6 + 7.8643e6)   # the two full-resolution de
 TAIL_EXECUTED_FLOP_PER_IMAGE = 2 * 2 * 28 * (2 * 128 * 64 * 16)
 ELITE_FRAC = 0.1
 # DRAM traffic of one decoder-tail launch at 1024 candidates: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture, profiles/r1k_dec_tail3_ncu_full.txt.  With level-ordered decoding the four launches of a step
-# decode 63, 64, 64 and 64 slots x 1024 candidates; the figure is their mean (63-slot launch 529.0 + 747.0 MB, 64-slot
-# launches 537.4 + 758.7 MB).  Algorithmic I/O of a 64-slot launch is 536.9 MB read (bf16 layer-3 maps) + 805.3 MB written
-# (fp32 images; the last 6 % drain from L2 after the kernel window): no re-reads.
-TAIL_TRAFFIC_BYTES_B1024 = (528.97e6 + 746.97e6 + 3 * (537.36e6 + 758.71e6)) / 4
+# `ncu --set full` capture, profiles/r2o_dec_tail3_ncu_full.txt (round 2, tail kernel with the fused L2 epilogue).  With
+# level-ordered decoding the four launches of a step decode 63, 64, 64 and 64 slots x 1024 candidates; the figure is their
+# mean (63-slot launch 529.6 + 746.8 MB, 64-slot launches 538.1 + 757.8 MB).  Algorithmic I/O of a 64-slot launch is 536.9 MB
+# read (bf16 layer-3 maps) + 805.3 MB written (fp32 images; the last 6 % drain from L2 after the kernel window): no re-reads.
+TAIL_TRAFFIC_BYTES_B1024 = (529.59e6 + 746.79e6 + 3 * (538.09e6 + 757.79e6)) / 4
 
 
 def workload(cands, config="tree"):
@@ -464,7 +464,7 @@ def main():
                                   "note": "tcgen05 FLOPs actually issued (29.36 MFLOP/image vs 32.51 canonical: shared "
                                           "skip half + unused mixture-scale channels are not computed)"},
                      "traffic": TAIL_TRAFFIC_BYTES_B1024 if chunk == 1024 else None,
-                     "traffic_note": "bytes per launch, ncu dram read+write (profiles/r1k_dec_tail3_ncu_full.txt)",
+                     "traffic_note": "bytes per launch, ncu dram read+write (profiles/r2o_dec_tail3_ncu_full.txt)",
                      "peak_source": peak_src,
                      "ms_per_launch": tail_ms, "images_per_launch": tail_imgs},
         "roofline_step": {"bound": "tensor", "achieved": value / world * FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf,
