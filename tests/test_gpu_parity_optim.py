@@ -84,3 +84,47 @@ def test_full_model_step_bandwidth(engine):
     gbs = n * (28 + 4) / ms / 1e6          # + 4 B: the gradient is read once more for the norm
     print("RAdam + clipping over %d parameters: %.3f ms per step = %.0f GB/s algorithmic" % (n, ms, gbs))
     assert torch.isfinite(p).all() and gbs > 2000
+
+
+def test_step_then_forward_uses_new_weights(sd):
+    """the engine computes with its own packed copy of the weights, so a forward after `optimizer.step()` must
+    see the update.  `ClippedOptimizer(model=...)` marks the model dirty; the next `model.engine` access repacks.  The
+    rollout after the step equals the rollout of a fresh model loaded with the updated state dict, and differs from the
+    rollout before it."""
+    from video_gcp_b200 import hparams
+    from video_gcp_b200.model import TreeModel
+    from video_gcp_b200.optim import get_clipped_optimizer
+    from video_gcp_b200.synthetic import synthetic_rollout_inputs
+    dev = torch.device("cuda:0")
+    cfg = hparams.gcp_tree_25room_config(batch_size=1, attach_cost_mdl=True)
+
+    def build(state):
+        m = TreeModel(cfg, None, max_candidates=128)
+        m.load_state_dict(state, strict=True)
+        m.to(dev)
+        m.device = dev
+        m.eval()
+        return m
+
+    inp = synthetic_rollout_inputs(8, seed=3, shared_images=True)
+    I0, Ig, z, ei = inp["I_0"][:1].to(dev), inp["I_g"][:1].to(dev), inp["z"].to(dev), inp["end_ind"].to(dev)
+    run = lambda m: {k: v.clone() for k, v in m.engine.rollout(I0, Ig, z, end_ind=ei, images_shared=True).items()
+                     if k in ("e_df", "images_df", "actions")}
+    model = build(sd)
+    before = run(model)
+    names = ["decoder.net.gen_head.conv.weight", "tree_module.tree_modules.0.subgoal_pred.lstm.0.weight_ih", "encoder.net.net.input.conv.weight"]
+    params = dict(model.named_parameters())
+    ps = [params[n] for n in names]
+    opt = get_clipped_optimizer(ps, model.engine, optimizer_type="adam", lr=5e-2, gradient_clip=None, model=model)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for p in ps:
+        p.grad = torch.randn(p.shape, generator=g).to(dev)
+    opt.step()
+    torch.cuda.synchronize()
+    assert model._dirty
+    after = run(model)
+    assert not model._dirty
+    fresh = run(build({k: v.detach().cpu() for k, v in model.state_dict().items()}))
+    for k in after:
+        assert torch.equal(after[k], fresh[k]), k
+        assert not torch.equal(after[k], before[k]), k
