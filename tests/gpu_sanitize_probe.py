@@ -20,6 +20,26 @@ for z in (inp["z"].to(dev), inp["z"].pin_memory()):
     idx, _ = eng.topk(cost, 2)
     eng.refit(out["z"], idx)
 torch.cuda.synchronize()
+# round 2: planner mode (kept nodes only + fused L2 cost, with and without image writes), full decode with the fused cost,
+# radix-select top-k with NaN / ties, refit split over elites, a 256-row rollout (CTA-pair GEMMs from level 1 on)
+goal = inp["I_g"][0].to(dev)
+for kw in (dict(decode_kept_only=True), dict(decode_kept_only=True, want_images=False), dict()):
+    o2 = eng.rollout(inp["I_0"].to(dev), inp["I_g"].to(dev), inp["z"].to(dev), end_ind=inp["end_ind"].to(dev), l2_goal=goal,
+                     l2_dense=True, l2_final_step_weight=1.0, **kw)
+    assert torch.isfinite(o2["l2_cost"]).all()
+c = torch.randn(5000, device=dev)
+c[::7] = float("nan")
+c[1::11] = c[3]
+idx, val = eng.topk(c, 500)
+big = synthetic_rollout_inputs(200, seed=12, shared_images=True)
+eng2 = Engine(dev, max_candidates=256, attach_cost_mdl=True)
+eng2.load_weights(synthetic_state_dict(hp, 1))
+o3 = eng2.rollout(big["I_0"][:1].to(dev), big["I_g"][:1].to(dev), big["z"].to(dev), images_shared=True, decode_kept_only=True,
+                  want_images=False, l2_goal=goal)
+i3, _ = eng2.topk(o3["l2_cost"], 20)
+eng2.refit(o3["z"], i3)
+torch.cuda.synchronize()
+eng2.close()
 batch = synthetic_train_batch(2, seed=5, end_ind=[61, 198])
 ei = batch["end_ind"].numpy()
 d = {k: v.to(dev) for k, v in batch.items() if isinstance(v, torch.Tensor)}

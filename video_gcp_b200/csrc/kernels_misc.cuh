@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(TOPK_SELECT_THREADS) topk_select_kernel(const 
                 if (lane >= o) inc += t;
             }
             const int krem = s_krem, before = inc - tot;
+            __syncwarp();                  // every lane has read s_krem / s_prefix before the selecting lane rewrites them
             if (before < krem && krem <= inc) {
                 int cum = before;
 #pragma unroll
