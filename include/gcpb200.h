@@ -57,6 +57,13 @@ typedef struct {
     int model;           /* GCPB200_MODEL_TREE (0), _SEQUENTIAL (1) or _TREE_ADAPTIVE (2): which reference model the context
                             holds (TreeModel, gcp/prediction/models/tree/tree.py:14; SequentialModel,
                             gcp/prediction/models/sequential.py:104) */
+    /* Tree shape; 0 = the 25-room values.  The 9-room planner config (experiments/control/9room/gcp_tree/mod_hyper.py:33-54)
+     * is hierarchy_levels 7, max_seq_len 100, tied_layers 1. */
+    int hierarchy_levels; /* tree depth d in [2,8]: 2^d - 1 nodes per candidate (default 8) */
+    int max_seq_len;      /* frames per sequence, a multiple of 4, <= 2^d - 1 for the tree models (default 200); every
+                             [B,200,..] / [B,255,..] extent in this header scales with these two */
+    int tied_layers;      /* 1: one TreeModule for all levels (untied_layers False: state-dict keys tree_module.*, not
+                             tree_module.tree_modules.<level>.*; gcp/prediction/models/tree/tree.py:18-21) */
 } gcpb200_config;
 
 #define GCPB200_MODEL_TREE 0

@@ -115,10 +115,17 @@ def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
     return h2, c2
 
 
-def df_index(level, j):
-    """In-order (depth-first) index of node j of `level` in a depth-8 tree
+def df_index(level, j, depth=DEPTH):
+    """In-order (depth-first) index of node j of `level` in a tree of `depth` levels
     (gcp/prediction/utils/tree_utils.py:222-232 depthfirst2layers, inverted)."""
-    return (2 * j + 1) * 2 ** (DEPTH - 1 - level) - 1
+    return (2 * j + 1) * 2 ** (depth - 1 - level) - 1
+
+
+def tree_module_prefix(sd, level):
+    """State-dict prefix of the TreeModule that predicts `level`: one module per level with untied_layers
+    (UntiedLayersTree, gcp/prediction/models/tree/untied_layers_tree.py:9-17), else a single `tree_module.`
+    (gcp/prediction/models/tree/tree.py:18-21; the 9-room config)."""
+    return "tree_module.tree_modules.%d." % level if "tree_module.tree_modules.0.prior.input.conv.weight" in sd else "tree_module."
 
 
 def interleave(a, b):
@@ -131,20 +138,23 @@ def tree_rollout(sd, e0, eg, z):
     (gcp/prediction/utils/tree_utils.py:21-44; gcp/prediction/models/tree/tree_module.py:67-114;
     gcp/prediction/models/tree/tree_lstm.py:30-49; blox/torch/recurrent_modules.py:195-223,286-295).
 
-    e0, eg [B,128]; z [B,255,256] (depth-first node order).
-    Returns dict of depth-first tensors: e [B,255,128], mu/log_sigma [B,255,256], hidden [B,255,3072].
+    e0, eg [B,128]; z [B,2^depth - 1,256] (depth-first node order; the tree depth is read off z: 255 nodes = 8 levels).
+    Returns dict of depth-first tensors: e [B,n,128], mu/log_sigma [B,n,256], hidden [B,n,3072].
     """
     B = e0.shape[0]
+    n_nodes = z.shape[1]
+    depth = int(np.log2(n_nodes + 1))
+    assert 2 ** depth - 1 == n_nodes
     eL, eR = e0[:, None], eg[:, None]
     hL = hR = None
-    e_df = torch.zeros(B, N_NODES, 128)
-    mu_df = torch.zeros(B, N_NODES, 256)
-    ls_df = torch.zeros(B, N_NODES, 256)
-    h_df = torch.zeros(B, N_NODES, 3072)
-    for lvl in range(DEPTH):
+    e_df = torch.zeros(B, n_nodes, 128)
+    mu_df = torch.zeros(B, n_nodes, 256)
+    ls_df = torch.zeros(B, n_nodes, 256)
+    h_df = torch.zeros(B, n_nodes, 3072)
+    for lvl in range(depth):
         n = 2 ** lvl
-        tm = "tree_module.tree_modules.%d." % lvl
-        idx = [df_index(lvl, j) for j in range(n)]
+        tm = tree_module_prefix(sd, lvl)
+        idx = [df_index(lvl, j, depth) for j in range(n)]
         eps = z[:, idx].reshape(B * n, 256)
         el, er = eL.reshape(B * n, 128), eR.reshape(B * n, 128)
         pz = mlp(sd, tm + "prior", torch.cat([el, er], 1))
@@ -186,7 +196,7 @@ def tree_rollout(sd, e0, eg, z):
 # --------------------------------------------------------------------------------------------------
 # integer part: balanced pruning
 # --------------------------------------------------------------------------------------------------
-def balanced_keep_mask(end_ind):
+def balanced_keep_mask(end_ind, depth=DEPTH):
     """BalancedEvalBinding.get_all_samples + BalancedBinding.__call__/comp_timestep/get_init_inds
     (gcp/evaluation/evaluation_matching.py:192-206; gcp/prediction/models/tree/frame_binding.py:42-65).
 
@@ -194,14 +204,14 @@ def balanced_keep_mask(end_ind):
     division, torch-1.3 semantics); the node is kept iff t != l and t != r; children get (l, t), (t, r).
     Returns keep [255] bool and timestep [255] int64, both in depth-first node order.
     """
-    keep = np.zeros(N_NODES, dtype=bool)
-    tstep = np.zeros(N_NODES, dtype=np.int64)
+    keep = np.zeros(2 ** depth - 1, dtype=bool)
+    tstep = np.zeros(2 ** depth - 1, dtype=np.int64)
 
     def rec(l, r, lvl, j):
-        if lvl == DEPTH:
+        if lvl == depth:
             return
         t = int((l + r) / 2)            # C-style truncation toward zero
-        i = df_index(lvl, j)
+        i = df_index(lvl, j, depth)
         tstep[i] = t
         keep[i] = (t != l) and (t != r)
         rec(l, t, lvl + 1, 2 * j)
@@ -211,9 +221,9 @@ def balanced_keep_mask(end_ind):
     return keep, tstep
 
 
-def prune_indices(end_ind):
+def prune_indices(end_ind, depth=DEPTH):
     """Depth-first indices of the kept nodes, in order: exactly end_ind + 1 of them."""
-    keep, _ = balanced_keep_mask(end_ind)
+    keep, _ = balanced_keep_mask(end_ind, depth)
     return np.nonzero(keep)[0]
 
 
@@ -237,15 +247,17 @@ def rollout(sd, I_0, I_g, z, end_ind, decode=True):
     tree = tree_rollout(sd, e0, eg, z)
     out["tree"] = tree
     B = e0.shape[0]
+    n_nodes = z.shape[1]
+    depth = int(np.log2(n_nodes + 1))
     if decode:
-        lat = tree["e"].reshape(B * N_NODES, 128)
-        imgs = decoder(sd, lat, s0.repeat_interleave(N_NODES, 0), s2.repeat_interleave(N_NODES, 0))
-        out["images_df"] = imgs.reshape(B, N_NODES, 3, 32, 32)
+        lat = tree["e"].reshape(B * n_nodes, 128)
+        imgs = decoder(sd, lat, s0.repeat_interleave(n_nodes, 0), s2.repeat_interleave(n_nodes, 0))
+        out["images_df"] = imgs.reshape(B, n_nodes, 3, 32, 32)
     # existence predictor (gcp/prediction/models/tree/frame_binding.py:67-78); result unused by pruning
-    ex = mlp(sd, "tree_module.tree_modules.0.binding.existence_predictor", tree["e"].reshape(-1, 128))
-    out["existence"] = ex.reshape(B, N_NODES)
+    ex = mlp(sd, tree_module_prefix(sd, 0) + "binding.existence_predictor", tree["e"].reshape(-1, 128))
+    out["existence"] = ex.reshape(B, n_nodes)
     # balanced pruning with the (injected) predicted length
-    idxs = [prune_indices(int(t)) for t in end_ind]
+    idxs = [prune_indices(int(t), depth) for t in end_ind]
     out["prune_idx"] = idxs
     if decode:
         out["pruned_images"] = [out["images_df"][b, torch.as_tensor(ix)] for b, ix in enumerate(idxs)]

@@ -47,7 +47,11 @@ def test_model_state_dict_and_modes(golden_dir):
     with pytest.raises(NotImplementedError):
         m(AttrDict(I_0=torch.zeros(1, 3, 32, 32)))           # training-time path is out of scope
     with pytest.raises(NotImplementedError):
-        TreeModel(hparams.gcp_tree_25room_config(batch_size=1, hierarchy_levels=7))
+        TreeModel(hparams.gcp_tree_25room_config(batch_size=1, hierarchy_levels=7))      # 200 frames need 8 levels
+    m9 = TreeModel(hparams.gcp_tree_9room_config(batch_size=1))                          # 7 levels, 100 frames, tied layers
+    sd9 = m9.state_dict()
+    assert "tree_module.prior.input.conv.weight" in sd9 and not any(k.startswith("tree_module.tree_modules.") for k in sd9)
+    assert sd9["length_pred.p.head.conv.weight"].shape[0] == 100
 
 
 def test_env2planner_and_sampler_host_contract():

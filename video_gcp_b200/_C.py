@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgcpb200.
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("max_candidates", C.c_int), ("attach_cost_mdl", C.c_int),
-                ("reserved0", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int)]
+                ("reserved0", C.c_int), ("decoder_slot_chunk", C.c_int), ("model", C.c_int),
+                ("hierarchy_levels", C.c_int), ("max_seq_len", C.c_int), ("tied_layers", C.c_int)]
 
 
 MODEL_TREE, MODEL_SEQUENTIAL, MODEL_TREE_ADAPTIVE = 0, 1, 2

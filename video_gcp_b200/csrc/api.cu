@@ -48,7 +48,7 @@ extern "C" const char* gcpb200_version(void) { return "gcpb200 0.1.0 (sm_100a)";
     } while (0)
 
 // model dimensions of the 25-room GCP-tree (experiments/control/25room/gcp_tree/mod_hyper.py:33-54)
-static const int DEPTH = 8, N_NODES = 255, N_SLOTS = 257;
+static const int DEPTH = 8, N_NODES = 255;        // 25-room defaults (and the maxima); the context carries the live values
 static const int NZ_ENC = 128, NZ_VAE = 256, NZ_MID = 128, HID = 512, N_LSTM = 3, STATE = 3072;
 static const int MAX_LEN = 200, INIT_MID = 32;
 static const int REFIT_SPLITS = 16;
@@ -106,6 +106,10 @@ struct gcpb200_ctx {
     LevelW lvl[8];
     SeqW seqw;
     int model = 0, n_slots = 257, lstm_hid = 512;
+    // tree shape (gcpb200_config.hierarchy_levels / max_seq_len / tied_layers): 25-room = 8 levels, 255 nodes, 200 frames, one
+    // TreeModule per level; 9-room = 7 levels, 127 nodes, 100 frames, ONE TreeModule for all levels
+    int depth = 8, n_nodes = 255, max_len = 200;
+    bool tied = false;
     DevBuf hs[2];            // sequential: bf16 h state [Bp][3 * 1024], ping-pong by step parity
     float* cs = nullptr;     // sequential: fp32 c state [Bp][3 * 1024]
     // sequential: the 199-step recurrence (~2000 dependent launches) is captured once per (noise buffer, prior output
@@ -699,7 +703,8 @@ static int pack_lstm_cell(gcpb200_ctx* c, const WStore& ws, const std::string& l
 
 static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     LevelW& L = c->lvl[l];
-    const std::string tm = "tree_module.tree_modules." + std::to_string(l) + ".";
+    // untied_layers (UntiedLayersTree, untied_layers_tree.py:9-17): one TreeModule per level; otherwise a single one
+    const std::string tm = c->tied ? std::string("tree_module.") : "tree_module.tree_modules." + std::to_string(l) + ".";
     // prior head: packed row p = tile*256 + chunk*32 + part*16 + u  <->  part*256 + tile*128 + chunk*16 + u
     auto reparam_perm = [](int p) {
         const int tile = p >> 8, chunk = (p >> 5) & 7, part = (p >> 4) & 1, u = p & 15;
@@ -1029,14 +1034,25 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         return -1;
     }
     const bool is_seq = c->model == GCPB200_MODEL_SEQUENTIAL;
-    // latent rows are [slot][candidate]: tree = start, 255 in-order nodes, goal; sequential = frames 0..199, goal
-    c->n_slots = is_seq ? MAX_LEN + 1 : N_SLOTS;
+    c->depth = cfg->hierarchy_levels > 0 ? cfg->hierarchy_levels : DEPTH;
+    c->max_len = cfg->max_seq_len > 0 ? cfg->max_seq_len : MAX_LEN;
+    c->tied = cfg->tied_layers != 0;
+    c->n_nodes = (1 << c->depth) - 1;
+    if (c->depth < 2 || c->depth > DEPTH || c->max_len < 3 || c->max_len > 256 || c->max_len % 4 != 0 ||
+        (!is_seq && c->max_len > c->n_nodes)) {
+        gcp_set_error("gcpb200_create: unsupported tree shape (hierarchy_levels %d in [2,8], max_seq_len %d a multiple of 4, <= 256 "
+                      "and <= 2^levels - 1)", c->depth, c->max_len);
+        delete c;
+        return -1;
+    }
+    // latent rows are [slot][candidate]: tree = start, the in-order nodes, goal; sequential = frames 0..max_len-1, goal
+    c->n_slots = is_seq ? c->max_len + 1 : c->n_nodes + 2;
     c->lstm_hid = is_seq ? 2 * HID : HID;
 #if GCP_VERIFY
     if (const char* e = getenv("GCPB200_GEMM_CLUSTER")) c->max_cluster = atoi(e) > 0 ? atoi(e) : 1;
     if (const char* e = getenv("GCPB200_SEQ_GRAPH")) c->seq_graph_on = atoi(e) != 0;
 #endif
-    const size_t Bp = c->Bp_max, NL = is_seq ? Bp : 128 * Bp, NS = (size_t)c->n_slots * Bp, ND = 256 * Bp;
+    const size_t Bp = c->Bp_max, NL = is_seq ? Bp : ((size_t)1 << (c->depth - 1)) * Bp, NS = (size_t)c->n_slots * Bp, ND = 256 * Bp;
     int rc = 0;
     rc |= dalloc(c, &c->lat_f32, NS * NZ_ENC);
     rc |= make_buf(c, &c->lat, NS, NZ_ENC);
@@ -1058,9 +1074,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= make_buf(c, &c->x1, (size_t)c->slot_chunk * Bp, 1024);
     rc |= make_buf(c, &c->x2, (size_t)c->slot_chunk * Bp, 2048);
     rc |= make_buf(c, &c->x3, (size_t)c->slot_chunk * Bp, 4096);
-    c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? N_NODES : MAX_LEN + 1) * Bp + 256);
+    c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? c->n_nodes : c->max_len + 1) * Bp + 256);
     rc |= make_buf(c, &c->pairs, (size_t)c->pair_rows, 256);
-    rc |= make_buf(c, &c->seqb, (size_t)(MAX_LEN + 1) * Bp + 256, NZ_ENC);
+    rc |= make_buf(c, &c->seqb, (size_t)(c->max_len + 1) * Bp + 256, NZ_ENC);
     rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
@@ -1069,8 +1085,8 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->skip_up, Bp * 2 * DT_PSTRIDE * 8);
     rc |= dalloc(c, &c->s4, Bp * 256 * 64);
     rc |= dalloc(c, &c->exist_slot, ND);
-    rc |= dalloc(c, &c->e_df, Bp * N_NODES * NZ_ENC);
-    rc |= dalloc(c, &c->seq, Bp * MAX_LEN * NZ_ENC);
+    rc |= dalloc(c, &c->e_df, Bp * c->n_nodes * NZ_ENC);
+    rc |= dalloc(c, &c->seq, Bp * c->max_len * NZ_ENC);
     rc |= dalloc(c, &c->rowcost, (size_t)c->pair_rows * 2);
     rc |= dalloc(c, &c->goal_tail, 256);
     rc |= dalloc(c, &c->end_ind, Bp);
@@ -1078,7 +1094,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     rc |= dalloc(c, &c->scratch_given, Bp);
     rc |= dalloc(c, &c->frame_node, Bp * 256);
     if (c->model == GCPB200_MODEL_TREE) {
-        const size_t kept_cap = (size_t)MAX_LEN * Bp + 256;
+        const size_t kept_cap = (size_t)c->max_len * Bp + 256;
         rc |= make_buf(c, &c->latc, kept_cap, NZ_ENC);
         rc |= dalloc(c, &c->row_cand, kept_cap);
         rc |= dalloc(c, &c->row_node, kept_cap);
@@ -1086,7 +1102,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         rc |= dalloc(c, &c->n_rows, 1);
         rc |= dalloc(c, &c->frame_sq, 256 * Bp);
     }
-    rc |= dalloc(c, &c->refit_part, (size_t)REFIT_SPLITS * N_NODES * NZ_VAE * 2, false);
+    rc |= dalloc(c, &c->refit_part, (size_t)REFIT_SPLITS * c->n_nodes * NZ_VAE * 2, false);
     if (rc) {
         gcpb200_destroy(c);
         return -1;
@@ -1188,21 +1204,22 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
     CHECK(pack_encoder(c, ws));
     CHECK(pack_decoder(c, ws));
     // training-only tensors are optional: planner checkpoints stripped of them still load (forward_loss then refuses)
-    c->has_train = c->model == GCPB200_MODEL_TREE && ws.m.count("inf_encoder.net.input.conv.weight") != 0 &&
+    c->has_train = c->model == GCPB200_MODEL_TREE && !c->tied && c->depth == DEPTH && c->max_len == MAX_LEN &&
+                   ws.m.count("inf_encoder.net.input.conv.weight") != 0 &&
                    ws.m.count("tree_module.tree_modules.0.inference.q.input.conv.weight") != 0;
     if (c->has_train) CHECK(pack_train(c, ws));
     if (c->model == GCPB200_MODEL_SEQUENTIAL) {
         CHECK(pack_sequential(c, ws));
     } else {
-        for (int l = 0; l < DEPTH; ++l) CHECK(pack_level(c, ws, l));
+        for (int l = 0; l < (c->tied ? 1 : c->depth); ++l) CHECK(pack_level(c, ws, l));
         if (c->model == GCPB200_MODEL_TREE_ADAPTIVE)
-            CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.distance_predictor", true, 2 * NZ_ENC, NZ_MID, 1, 128,
+            CHECK(pack_mlp(c, ws, std::string(c->tied ? "tree_module." : "tree_module.tree_modules.0.") + "binding.distance_predictor", true, 2 * NZ_ENC, NZ_MID, 1, 128,
                            nullptr, &c->distance_pred));
         else
-            CHECK(pack_mlp(c, ws, "tree_module.tree_modules.0.binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128,
+            CHECK(pack_mlp(c, ws, std::string(c->tied ? "tree_module." : "tree_module.tree_modules.0.") + "binding.existence_predictor", true, NZ_ENC, NZ_MID, 1, 128,
                            nullptr, &c->existence));
     }
-    CHECK(pack_mlp(c, ws, "length_pred.p", true, 2 * NZ_ENC, NZ_MID, MAX_LEN, 256, nullptr, &c->length_pred));
+    CHECK(pack_mlp(c, ws, "length_pred.p", true, 2 * NZ_ENC, NZ_MID, c->max_len, 256, nullptr, &c->length_pred));
     // auxiliary heads exist only when the model config attaches them (attach_inv_mdl / attach_state_regressor)
     c->has_inv = ws.m.count("inv_mdl.action_pred.input.linear.weight") != 0;
     c->has_state = ws.m.count("state_regressor.input.linear.weight") != 0;
@@ -1240,8 +1257,8 @@ static int check_ready(gcpb200_ctx* c, int B) {
     } while (0)
 
 static int compute_frame_map(gcpb200_ctx* c, const long long* end_ind, int B, cudaStream_t st) {
-    GCP_CUDA_CHECK(cudaMemsetAsync(c->frame_node, 0, (size_t)B * MAX_LEN * sizeof(int), st));
-    prune_map_kernel<<<(B * N_NODES + 255) / 256, 256, 0, st>>>(end_ind, B, DEPTH, MAX_LEN, c->frame_node);
+    GCP_CUDA_CHECK(cudaMemsetAsync(c->frame_node, 0, (size_t)B * c->max_len * sizeof(int), st));
+    prune_map_kernel<<<(B * c->n_nodes + 255) / 256, 256, 0, st>>>(end_ind, B, c->depth, c->max_len, c->frame_node);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1262,7 +1279,7 @@ struct CommonIO {
 static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& in, int Bp, int goal_row0) {
     const CommonIO* io = &in;
     const int B = in.B;
-    const LevelGeom flat = {Bp, 0, DEPTH};
+    const LevelGeom flat = {Bp, 0, c->depth};
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
     encoder_kernel<<<dim3(n_img, 2), ENC_THREADS, 0, st>>>(io->I_0, io->I_g, c->enc, c->lat_f32, c->lat.p, 0, goal_row0, c->s0, c->s2,
@@ -1284,15 +1301,15 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
     if (io->seq_len_logits || !io->end_ind) {
         CHECK(mlp_body(c, st, c->length_pred, Bp, flat, ctx_in));
         CHECK(gemm(c, st, Bp, flat, {seg(c->tb, 0, c->length_pred.mid_k)}, c->length_pred.head, 128, EPI_LINEAR,
-                   epi_linear(ACT_NONE, nullptr, 0, c->logits, 256, MAX_LEN)));
+                   epi_linear(ACT_NONE, nullptr, 0, c->logits, 256, c->max_len)));
         if (io->seq_len_logits)
-            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->seq_len_logits, MAX_LEN * 4, c->logits, 256 * 4, MAX_LEN * 4, B,
+            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->seq_len_logits, c->max_len * 4, c->logits, 256 * 4, c->max_len * 4, B,
                                              cudaMemcpyDeviceToDevice, st));
     }
     if (io->end_ind) {
         GCP_CUDA_CHECK(cudaMemcpyAsync(c->end_ind, io->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     } else {
-        sample_length_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->logits, 256, MAX_LEN, B, io->seed, c->end_ind);
+        sample_length_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->logits, 256, c->max_len, B, io->seed, c->end_ind);
         LAUNCH_CHECK();
     }
     if (io->end_ind_out) GCP_CUDA_CHECK(cudaMemcpyAsync(io->end_ind_out, c->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
@@ -1306,7 +1323,7 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
 // Per-call constants of the decoder: the up-sampled encoder skip, the skip half of the 32->16 tail conv in the quad
 // layout of dec_tail3, and the skip half of the 128->32 conv as a per-candidate row bias (the conv is linear in its input).
 static int decoder_prepare(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp) {
-    const LevelGeom flat = {Bp, 0, DEPTH};
+    const LevelGeom flat = {Bp, 0, c->depth};
     const int n_skip = images_shared ? 1 : B;
     skip_prep_kernel<<<n_skip, 256, 0, st>>>(c->s0, c->skip_up, n_skip);
     LAUNCH_CHECK();
@@ -1326,7 +1343,7 @@ static int decoder_prepare(gcpb200_ctx* c, cudaStream_t st, int images_shared, i
 static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, int first, int step, int count,
                          float* images, int n_layout, const float* I_0, const float* I_g, const float* l2_goal = nullptr) {
     const bool pc = c->model == GCPB200_MODEL_TREE_ADAPTIVE;   // pixel-copy head: needs the start / goal images
-    const LevelGeom flat = {Bp, 0, DEPTH};
+    const LevelGeom flat = {Bp, 0, c->depth};
     if (step != 1 && ((step != 2 && step != 4) || c->use_ref)) {
         gcp_set_error("decoder_slots: unsupported slot step %d", step);
         return -1;
@@ -1343,7 +1360,7 @@ static int decoder_slots(gcpb200_ctx* c, cudaStream_t st, int images_shared, int
             // row block j of the A operand = slot s0 + step * j: the geometry of tree level 7 (step 2) / 6 (step 4) maps
             // j to slot (2j + 1) * step / 2 (ROW_SELF); row_base shifts that to s0
             const int half = step / 2;
-            const LevelGeom gl = {Bp, step == 2 ? DEPTH - 1 : DEPTH - 2, DEPTH};
+            const LevelGeom gl = {Bp, step == 2 ? c->depth - 1 : c->depth - 2, c->depth};
             CHECK(gemm(c, st, rows, gl, {seg(c->lat, 0, NZ_ENC, ROW_SELF, (s0 - half) * Bp)}, c->dec1, 256, EPI_LINEAR,
                        epi_linear(ACT_RELU, c->x1.p, 1024, nullptr, 0, 1024)));
         }
@@ -1411,18 +1428,18 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
 // kernel are launched for the capacity of a chunk and read the live row count from c->n_rows.  Needs c->frame_node
 // (compute_frame_map) and the finished tree.
 static int decoder_kept(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, float* images, const float* l2_goal) {
-    const LevelGeom flat = {Bp, 0, DEPTH};
+    const LevelGeom flat = {Bp, 0, c->depth};
     kept_offsets_kernel<<<1, 1024, 0, st>>>(c->end_ind, B, 1, c->row_off, c->n_rows);
     LAUNCH_CHECK();
     {
-        const size_t n = (size_t)B * MAX_LEN * 16;
+        const size_t n = (size_t)B * c->max_len * 16;
         gather_kept_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat.p, c->frame_node, c->end_ind, c->row_off, B, Bp,
-                                                                           MAX_LEN, 1, c->latc.p, c->row_cand, c->row_node);
+                                                                           c->max_len, 1, c->latc.p, c->row_cand, c->row_node);
         LAUNCH_CHECK();
     }
     CHECK(decoder_prepare(c, st, images_shared, B, Bp));
     const int chunk_rows = c->slot_chunk * Bp;
-    const int cap = MAX_LEN * B;                 // at most 200 kept frames per candidate
+    const int cap = c->max_len * B;                 // at most 200 kept frames per candidate
     for (int r0 = 0; r0 < cap; r0 += chunk_rows) {
         const int rows = std::min(chunk_rows, (cap - r0 + 255) / 256 * 256);
         {
@@ -1448,7 +1465,7 @@ static int decoder_kept(gcpb200_ctx* c, cudaStream_t st, int images_shared, int 
         memset(&a, 0, sizeof(a));
         a.x3 = c->x3.p; a.s4 = c->s4; a.s4_stride = images_shared ? 0 : 256 * 64;
         a.w4 = c->z4; a.w5 = c->z5; a.b5h = c->b5h;
-        a.images = images; a.Bp = Bp; a.n_cand = B; a.n_slots = c->slot_chunk; a.n_nodes = N_NODES;
+        a.images = images; a.Bp = Bp; a.n_cand = B; a.n_slots = c->slot_chunk; a.n_nodes = c->n_nodes;
         a.n_img_dev = c->n_rows; a.row_cand = c->row_cand; a.row_node = c->row_node; a.img_base = r0;
         if (l2_goal != nullptr) {
             a.frame_sq = c->frame_sq;
@@ -1472,10 +1489,10 @@ static int decoder_kept(gcpb200_ctx* c, cudaStream_t st, int images_shared, int 
 // row (InverseModel.full_seq_forward, inverse_mdl.py:110-134; base_gcp.py:252-256).
 static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const long long* end_ind, int B, float* actions,
                           float* regressed_state) {
-    // c->seqb holds the sequences as bf16 rows (cand, t), MAX_LEN + 1 rows per candidate (gather_frames_kernel): the
+    // c->seqb holds the sequences as bf16 rows (cand, t), c->max_len + 1 rows per candidate (gather_frames_kernel): the
     // pair [frame t | frame t + 1] is two row-shifted K segments of the same array, no pair matrix is materialised.
-    const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
-    const int L1 = MAX_LEN + 1;
+    const LevelGeom flat = {(B + 127) / 128 * 128, 0, c->depth};
+    const int L1 = c->max_len + 1;
     const int rows = (B * L1 + 127) / 128 * 128;
     (void)end_ind;
     if ((actions && !c->has_inv) || (regressed_state && !c->has_state)) {
@@ -1490,15 +1507,15 @@ static int run_pair_heads(gcpb200_ctx* c, cudaStream_t st, const long long* end_
         CHECK(mlp_body(c, st, c->inv_mdl, rows, flat, {seg(c->seqb, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->seqb, 0, NZ_ENC, ROW_LEVEL, 1)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->inv_mdl.mid_k)}, c->inv_mdl.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-        GCP_CUDA_CHECK(cudaMemcpy2DAsync(actions, (size_t)MAX_LEN * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4, (size_t)MAX_LEN * 2 * 4, B,
+        GCP_CUDA_CHECK(cudaMemcpy2DAsync(actions, (size_t)c->max_len * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4, (size_t)c->max_len * 2 * 4, B,
                                          cudaMemcpyDeviceToDevice, st));
     }
     if (regressed_state) {
         CHECK(mlp_body(c, st, c->state_reg, rows, flat, {seg(c->seqb, 0, NZ_ENC)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->state_reg.mid_k)}, c->state_reg.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 2, 2)));
-        GCP_CUDA_CHECK(cudaMemcpy2DAsync(regressed_state, (size_t)MAX_LEN * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4,
-                                         (size_t)MAX_LEN * 2 * 4, B, cudaMemcpyDeviceToDevice, st));
+        GCP_CUDA_CHECK(cudaMemcpy2DAsync(regressed_state, (size_t)c->max_len * 2 * 4, c->rowcost, (size_t)L1 * 2 * 4,
+                                         (size_t)c->max_len * 2 * 4, B, cudaMemcpyDeviceToDevice, st));
     }
     return 0;
 }
@@ -1514,12 +1531,12 @@ struct PosteriorArgs {
 // B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
 static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
                       const PosteriorArgs* post, float* e_df = nullptr) {
-    const LevelGeom flat = {Bp, 0, DEPTH};
-    const int goal_row0 = 256 * Bp;
+    const LevelGeom flat = {Bp, 0, c->depth};
+    const int goal_row0 = (c->n_nodes + 1) * Bp;
     const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
     {
-        const LevelW& L = c->lvl[l];
-        const LevelGeom g = {Bp, l, DEPTH};
+        const LevelW& L = c->lvl[c->tied ? 0 : l];
+        const LevelGeom g = {Bp, l, c->depth};
         const int rows = Bp << l;
         // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
         CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
@@ -1538,7 +1555,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             // training phase: z ~ q(z | e_l, e_r, e_tilde), e_tilde = inference encoding of the frame the node is matched
             // to (tree_module.py:86-95, tree/inference.py:16-36); the sample overwrites the prior's in c->zeta
             const size_t n = (size_t)rows * 128;
-            gather_etilde_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(post->inf_seq, post->tstep, g, B, MAX_LEN, c->xb.p, HID);
+            gather_etilde_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(post->inf_seq, post->tstep, g, B, c->max_len, c->xb.p, HID);
             LAUNCH_CHECK();
             CHECK(mlp_body(c, st, L.q, rows, g, {par[0], par[1], seg(c->xb, 0, NZ_ENC)}));
             EpiParams e;
@@ -1586,7 +1603,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             e.c_prev = c->sh.p; e.c_prev_ld = 6 * HID; e.c_prev_col0 = (3 + i) * HID;
             e.out_bf16 = xout->p; e.out_bf16_ld = HID;
             e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
-            e.write_hid = (l < DEPTH - 1);
+            e.write_hid = (l < c->depth - 1);
             CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e));
             std::swap(xin, xout);
         }
@@ -1595,7 +1612,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         EpiParams eo = epi_linear(ACT_NONE, c->lat.p, NZ_ENC, c->lat_f32, NZ_ENC, NZ_ENC, ROW_SELF, ROW_SELF);
         if (e_df != nullptr) {
             eo.out_f32 = e_df;
-            eo.out_f32_df = N_NODES;
+            eo.out_f32_df = c->n_nodes;
             eo.n_cand = B;
         }
         CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR, eo));
@@ -1640,8 +1657,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     const bool decode_all = !kept_only && (io->images_df != nullptr || fused_l2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = io->B, Bp = (B + 127) / 128 * 128;
-    const LevelGeom flat = {Bp, 0, DEPTH};
-    const int goal_row0 = 256 * Bp;
+    const LevelGeom flat = {Bp, 0, c->depth};
+    const int goal_row0 = (c->n_nodes + 1) * Bp;
 
     ProfScope total_scope(c, st, 5);
     if (io->z_host) {
@@ -1650,7 +1667,19 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         trace_mark(st, "start");
         GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy_start, st));       // earlier users of the staging buffer are done
         GCP_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy_start, 0));
-        const int sets[5][3] = {{16, 15, 15}, {16, 7, 16}, {8, 3, 32}, {4, 1, 64}, {2, 0, 128}};   // node = a*k + b, k < cnt
+        // node = a*k + b, k < cnt: set 0 = levels 0 .. depth-5 together, sets 1-4 = levels depth-4 .. depth-1 one by one
+        // (depth 8: {16,15,15}, {16,7,16}, {8,3,32}, {4,1,64}, {2,0,128}); trees of fewer than 5 levels upload everything at once
+        int sets[5][3];
+        const int D = c->depth, n_sets = D >= 5 ? 5 : 1;
+        if (D >= 5) {
+            sets[0][0] = 16; sets[0][1] = 15; sets[0][2] = (1 << (D - 4)) - 1;
+            for (int i = 1; i < 5; ++i) {
+                const int l = D - 5 + i;
+                sets[i][0] = 1 << (D - l); sets[i][1] = (1 << (D - 1 - l)) - 1; sets[i][2] = 1 << l;
+            }
+        } else {
+            sets[0][0] = 1; sets[0][1] = 0; sets[0][2] = c->n_nodes;
+        }
         // Launch shape (measured with GCPB200_TRACE=1, profiles/r1j_upload_interference.txt): PCIe saturates at about
         // 8 k outstanding 16-byte reads.  Reads beyond that queue inside the GPU's memory system and slow the tensor-core
         // kernels of the rollout stream (12-16 k outstanding: GEMMs and decoder 1.5x slower; 19 k: they stall until the
@@ -1670,10 +1699,10 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
 #else
         const int up_grid = 64, up_block = 32;
 #endif
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < n_sets; ++i) {
             upload_rows_kernel<<<up_grid, up_block, 0, c->copy_stream>>>(reinterpret_cast<const float4*>(io->z_host),
                                                                       reinterpret_cast<float4*>(const_cast<float*>(io->z)), B,
-                                                                      N_NODES, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
+                                                                      c->n_nodes, NZ_VAE / 4, sets[i][0], sets[i][1], sets[i][2]);
             LAUNCH_CHECK();
             GCP_CUDA_CHECK(cudaEventRecord(c->ev_copy[i], c->copy_stream));
             static const char* names[5] = {"up_l0-3", "up_l4", "up_l5", "up_l6", "up_l7"};
@@ -1695,24 +1724,25 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     // levels 0-5 (63 nodes) before tree level 6, level 6 (64 nodes) before tree level 7, level 7 (128 nodes) after it.
     // Same work in total; with host-resident noise it puts 2 ms of tensor-bound work in front of each of the two big
     // uploads (level 6: 67 MB, level 7: 133 MB at 1024 candidates) instead of stalling the recursion on PCIe.
-    const bool level_ordered = decode_all && !c->use_ref;
+    const bool level_ordered = decode_all && !c->use_ref && c->depth >= 3;
     const float* l2_goal = fused_l2 ? io->l2_goal : nullptr;
     float* e_df = io->e_df ? io->e_df : c->e_df;
-    for (int l = 0; l < DEPTH; ++l) {
-        if (level_ordered && l >= DEPTH - 2) {
-            trace_mark(st, l == DEPTH - 2 ? "tree_l5_end" : "tree_l6_end");
+    for (int l = 0; l < c->depth; ++l) {
+        if (level_ordered && l >= c->depth - 2) {
+            trace_mark(st, l == c->depth - 2 ? "tree_l5_end" : "tree_l6_end");
             delete scope;
             scope = nullptr;
-            if (l == DEPTH - 2) {
+            if (l == c->depth - 2) {
                 CHECK(decoder_prepare(c, st, io->images_shared, B, Bp));
-                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, 63, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, (1 << (c->depth - 2)) - 1, io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
             } else {
-                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 64, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
+                CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 1 << (c->depth - 2), io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
             }
             scope = new ProfScope(c, st, 1);
-            trace_mark(st, l == DEPTH - 2 ? "dec_l0-5_end" : "dec_l6_end");
+            trace_mark(st, l == c->depth - 2 ? "dec_l0-5_end" : "dec_l6_end");
         }
-        if (io->z_host && (l == 0 || l >= 4)) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_copy[l == 0 ? 0 : l - 3], 0));
+        if (io->z_host && (l == 0 || (c->depth >= 5 && l >= c->depth - 4)))
+            GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_copy[l == 0 ? 0 : l - (c->depth - 5)], 0));
         if ((io->mu_df == nullptr) != (io->log_sigma_df == nullptr)) {
             gcp_set_error("mu_df and log_sigma_df must be given together");
             return -1;
@@ -1725,12 +1755,12 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     scope = new ProfScope(c, st, 4);
     // ---- 4. existence predictor (the depth-first fp32 latents were written by the output GEMM of every level)
     if (io->existence) {
-        const int rows = N_NODES * Bp;
+        const int rows = c->n_nodes * Bp;
         CHECK(mlp_body(c, st, c->existence, rows, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, Bp)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->existence.mid_k)}, c->existence.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->exist_slot + Bp, 1, 1)));
-        const size_t n = (size_t)B * N_NODES;
-        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->exist_slot, Bp, B, N_NODES, 1, 1, io->existence);
+        const size_t n = (size_t)B * c->n_nodes;
+        slot_to_df_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->exist_slot, Bp, B, c->n_nodes, 1, 1, io->existence);
         LAUNCH_CHECK();
     }
 
@@ -1740,14 +1770,14 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     const bool need_map = kept_only || fused_l2 || io->model_enc_seq || io->actions || io->regressed_state;
     if (need_map) CHECK(compute_frame_map(c, c->end_ind, B, st));
     if (level_ordered)      // level 7 = the odd slots
-        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, N_NODES / 2 + 1, io->images_df, N_NODES, io->I_0, io->I_g, l2_goal));
+        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, c->n_nodes / 2 + 1, io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
     else if (kept_only)
         CHECK(decoder_kept(c, st, io->images_shared, B, Bp, io->images_df, l2_goal));
     else if (io->images_df)
-        CHECK(run_decoder(c, st, io->images_shared, B, Bp, N_NODES, io->images_df, N_NODES, io->I_0, io->I_g));
+        CHECK(run_decoder(c, st, io->images_shared, B, Bp, c->n_nodes, io->images_df, c->n_nodes, io->I_0, io->I_g));
     if (fused_l2) {
-        cost_from_frames_kernel<<<B, 32, 0, st>>>(c->frame_sq, kept_only ? nullptr : c->frame_node, c->row_off, c->end_ind, N_NODES,
-                                                  MAX_LEN, io->l2_dense, io->l2_final_step_weight, 1, io->l2_cost);
+        cost_from_frames_kernel<<<B, 32, 0, st>>>(c->frame_sq, kept_only ? nullptr : c->frame_node, c->row_off, c->end_ind, c->n_nodes,
+                                                  c->max_len, io->l2_dense, io->l2_final_step_weight, 1, io->l2_cost);
         LAUNCH_CHECK();
     }
     if (adaptive && (io->distances || io->pruned_nodes || io->pruned_len)) {
@@ -1757,18 +1787,18 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             gcp_set_error("pruned_nodes and pruned_len must be given together");
             return -1;
         }
-        const int rows = (B * N_NODES + 127) / 128 * 128;
-        make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(e_df, c->end_ind, nullptr, B, N_NODES, rows,
+        const int rows = (B * c->n_nodes + 127) / 128 * 128;
+        make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(e_df, c->end_ind, nullptr, B, c->n_nodes, rows,
                                                                                        c->pairs.p);
         LAUNCH_CHECK();
         CHECK(mlp_body(c, st, c->distance_pred, rows, flat, {seg(c->pairs, 0, 256)}));
         CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->distance_pred.mid_k)}, c->distance_pred.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->rowcost, 1, 1)));
         if (io->distances)
-            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->distances, (N_NODES - 1) * 4, c->rowcost, N_NODES * 4, (N_NODES - 1) * 4, B,
+            GCP_CUDA_CHECK(cudaMemcpy2DAsync(io->distances, (c->n_nodes - 1) * 4, c->rowcost, c->n_nodes * 4, (c->n_nodes - 1) * 4, B,
                                              cudaMemcpyDeviceToDevice, st));
         const float thr = io->prune_threshold > 0.f ? io->prune_threshold : 0.5f;
-        adaptive_prune_kernel<<<B, 256, 0, st>>>(c->rowcost, N_NODES, N_NODES, logf(thr / (1.0f - thr)), io->pruned_nodes,
+        adaptive_prune_kernel<<<B, 256, 0, st>>>(c->rowcost, c->n_nodes, c->n_nodes, logf(thr / (1.0f - thr)), io->pruned_nodes,
                                                  io->pruned_len, nullptr);
         LAUNCH_CHECK();
     }
@@ -1777,8 +1807,8 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     // ---- 6. pruned latent sequence + inverse model + state regressor (run_auxilliary_models)
     if (io->model_enc_seq || io->actions || io->regressed_state) {
         float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
-        const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
-        gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, N_NODES, MAX_LEN,
+        const size_t n = (size_t)B * c->max_len * (NZ_ENC / 4);
+        gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, c->end_ind, B, c->n_nodes, c->max_len,
                                                                            NZ_ENC / 4, seq, c->seqb.p);
         LAUNCH_CHECK();
         if (io->actions || io->regressed_state) CHECK(run_pair_heads(c, st, c->end_ind, B, io->actions, io->regressed_state));
@@ -2113,9 +2143,9 @@ extern "C" int gcpb200_seq_rollout(gcpb200_ctx* c, const gcpb200_seq_io* io, voi
         return -1;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int B = io->B, Bp = (B + 127) / 128 * 128, T = GCPB200_SEQ_STEPS, H = c->lstm_hid;
-    const LevelGeom flat = {Bp, 0, DEPTH};
-    const int goal_row0 = MAX_LEN * Bp;
+    const int B = io->B, Bp = (B + 127) / 128 * 128, T = c->max_len - 1, H = c->lstm_hid;
+    const LevelGeom flat = {Bp, 0, c->depth};
+    const int goal_row0 = c->max_len * Bp;
     const SeqW& S = c->seqw;
 
     ProfScope total_scope(c, st, 5);
@@ -2221,26 +2251,26 @@ extern "C" int gcpb200_seq_rollout(gcpb200_ctx* c, const gcpb200_seq_io* io, voi
     delete scope;
     scope = nullptr;
     if (io->images) {
-        copy_frame0_kernel<<<(B * 768 + 255) / 256, 256, 0, st>>>(io->I_0, io->images_shared, B, MAX_LEN, io->images);
+        copy_frame0_kernel<<<(B * 768 + 255) / 256, 256, 0, st>>>(io->I_0, io->images_shared, B, c->max_len, io->images);
         LAUNCH_CHECK();
-        CHECK(run_decoder(c, st, io->images_shared, B, Bp, T, io->images + 3072, MAX_LEN));
+        CHECK(run_decoder(c, st, io->images_shared, B, Bp, T, io->images + 3072, c->max_len));
     }
     ProfScope asc(c, st, 4);
     if (io->model_enc_seq || io->actions || io->regressed_state) {
         // inputs.end_ind decides how much of cat(e_0, encodings) is kept (phase = 'train' branch, base_gcp.py:238-239)
         const long long* given = reinterpret_cast<const long long*>(io->given_end_ind);
         if (given == nullptr) {
-            fill_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(c->scratch_given, MAX_LEN - 1, B);
+            fill_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(c->scratch_given, c->max_len - 1, B);
             LAUNCH_CHECK();
             given = c->scratch_given;
         }
         float* seq = io->model_enc_seq ? io->model_enc_seq : c->seq;
-        const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
-        seq_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, given, Bp, B, MAX_LEN, seq);
+        const size_t n = (size_t)B * c->max_len * (NZ_ENC / 4);
+        seq_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat_f32, given, Bp, B, c->max_len, seq);
         LAUNCH_CHECK();
         if (io->actions || io->regressed_state) {
-            const size_t nq = (size_t)B * MAX_LEN * (NZ_ENC / 4);
-            seq_to_b16_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(seq, B, MAX_LEN, NZ_ENC / 4, c->seqb.p);
+            const size_t nq = (size_t)B * c->max_len * (NZ_ENC / 4);
+            seq_to_b16_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(seq, B, c->max_len, NZ_ENC / 4, c->seqb.p);
             LAUNCH_CHECK();
             CHECK(run_pair_heads(c, st, given, B, io->actions, io->regressed_state));
         }
@@ -2268,8 +2298,8 @@ extern "C" int gcpb200_gather_nodes(gcpb200_ctx* c, const float* src_df, const i
         gcp_set_error("gcpb200_gather_nodes: bad arguments (row_len must be a multiple of 4)");
         return -1;
     }
-    const size_t n = (size_t)B * N_NODES * (row_len / 4);
-    gather_nodes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_df, nodes, len, B, N_NODES,
+    const size_t n = (size_t)B * c->n_nodes * (row_len / 4);
+    gather_nodes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_df, nodes, len, B, c->n_nodes,
                                                                                                       row_len / 4, dst);
     LAUNCH_CHECK();
     return 0;
@@ -2281,7 +2311,7 @@ extern "C" int gcpb200_cost_l2_nodes(gcpb200_ctx* c, const float* images_df, con
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     len_to_end_kernel<<<(B + 255) / 256, 256, 0, st>>>(len, c->scratch_given, B);
     LAUNCH_CHECK();
-    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, nodes, c->scratch_given, goal, N_NODES, N_NODES, dense, final_step_weight, cost, 0);
+    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, nodes, c->scratch_given, goal, c->n_nodes, c->n_nodes, dense, final_step_weight, cost, 0);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2296,8 +2326,8 @@ extern "C" int gcpb200_prune_gather(gcpb200_ctx* c, const float* src_df, const i
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long* ei = reinterpret_cast<const long long*>(end_ind);
     CHECK(compute_frame_map(c, ei, B, st));
-    const size_t n = (size_t)B * MAX_LEN * (row_len / 4);
-    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src_df, c->frame_node, ei, B, N_NODES, MAX_LEN, row_len / 4, dst);
+    const size_t n = (size_t)B * c->max_len * (row_len / 4);
+    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src_df, c->frame_node, ei, B, c->n_nodes, c->max_len, row_len / 4, dst);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2308,7 +2338,7 @@ extern "C" int gcpb200_cost_l2(gcpb200_ctx* c, const float* images_df, const int
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long* ei = reinterpret_cast<const long long*>(end_ind);
     CHECK(compute_frame_map(c, ei, B, st));
-    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, c->frame_node, ei, goal, N_NODES, MAX_LEN, dense, final_step_weight, cost);
+    cost_l2_kernel<<<B, 256, 0, st>>>(images_df, c->frame_node, ei, goal, c->n_nodes, c->max_len, dense, final_step_weight, cost);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2320,20 +2350,20 @@ extern "C" int gcpb200_cost_learned(gcpb200_ctx* c, const float* e_df, const int
         gcp_set_error("learned cost needs attach_cost_mdl=1 and cost_mdl.cost_pred.* weights");
         return -1;
     }
-    if (Lg < 1 || Lg > MAX_LEN) {
-        gcp_set_error("goal sequence length %d outside [1,%d]", Lg, MAX_LEN);
+    if (Lg < 1 || Lg > c->max_len) {
+        gcp_set_error("goal sequence length %d outside [1,%d]", Lg, c->max_len);
         return -1;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long* ei = reinterpret_cast<const long long*>(end_ind);
-    const LevelGeom flat = {(B + 127) / 128 * 128, 0, DEPTH};
+    const LevelGeom flat = {(B + 127) / 128 * 128, 0, c->depth};
     CHECK(compute_frame_map(c, ei, B, st));
-    const size_t n = (size_t)B * MAX_LEN * (NZ_ENC / 4);
-    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, ei, B, N_NODES, MAX_LEN, NZ_ENC / 4, c->seq);
+    const size_t n = (size_t)B * c->max_len * (NZ_ENC / 4);
+    gather_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e_df, c->frame_node, ei, B, c->n_nodes, c->max_len, NZ_ENC / 4, c->seq);
     LAUNCH_CHECK();
     // pairs inside each candidate's sequence, the pair bridging into the goal sequence, then the goal's own pairs
-    const int rows = (B * MAX_LEN + 127) / 128 * 128;
-    make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(c->seq, ei, goal_seq, B, MAX_LEN, rows, c->pairs.p);
+    const int rows = (B * c->max_len + 127) / 128 * 128;
+    make_pairs_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(c->seq, ei, goal_seq, B, c->max_len, rows, c->pairs.p);
     LAUNCH_CHECK();
     CHECK(mlp_body(c, st, c->cost_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
     CHECK(gemm(c, st, rows, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
@@ -2344,16 +2374,16 @@ extern "C" int gcpb200_cost_learned(gcpb200_ctx* c, const float* e_df, const int
         long long* e1 = c->scratch_ei;   // [Lg-1] as "end_ind" of a single pseudo-candidate
         const long long hv = Lg - 1;
         GCP_CUDA_CHECK(cudaMemcpyAsync(e1, &hv, 8, cudaMemcpyHostToDevice, st));
-        GCP_CUDA_CHECK(cudaMemsetAsync(c->seq, 0, (size_t)MAX_LEN * NZ_ENC * 4, st));
+        GCP_CUDA_CHECK(cudaMemsetAsync(c->seq, 0, (size_t)c->max_len * NZ_ENC * 4, st));
         GCP_CUDA_CHECK(cudaMemcpyAsync(c->seq, goal_seq, (size_t)Lg * NZ_ENC * 4, cudaMemcpyDeviceToDevice, st));
-        make_pairs_kernel<<<(256 * 256 + 255) / 256, 256, 0, st>>>(c->seq, e1, nullptr, 1, MAX_LEN, 256, c->pairs.p);
+        make_pairs_kernel<<<(256 * 256 + 255) / 256, 256, 0, st>>>(c->seq, e1, nullptr, 1, c->max_len, 256, c->pairs.p);
         LAUNCH_CHECK();
         CHECK(mlp_body(c, st, c->cost_mdl, 256, flat, {seg(c->pairs, 0, 256)}));
         CHECK(gemm(c, st, 256, flat, {seg(c->tb, 0, c->cost_mdl.mid_k)}, c->cost_mdl.head, 128, EPI_LINEAR,
                    epi_linear(ACT_NONE, nullptr, 0, c->goal_tail, 1, 1)));
         n_tail = Lg - 1;
     }
-    cost_sum_kernel<<<B, 32, 0, st>>>(c->rowcost, ei, MAX_LEN, c->goal_tail, n_tail, cost);
+    cost_sum_kernel<<<B, 32, 0, st>>>(c->rowcost, ei, c->max_len, c->goal_tail, n_tail, cost);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2375,7 +2405,7 @@ extern "C" int gcpb200_cost_pairs(gcpb200_ctx* c, const float* lat, const int32_
         return -1;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const LevelGeom flat = {rows, 0, DEPTH};
+    const LevelGeom flat = {rows, 0, c->depth};
     make_pairs_idx_kernel<<<(unsigned)(((size_t)rows * 256 + 255) / 256), 256, 0, st>>>(lat, idx1, lat, idx2, n, rows, c->pairs.p);
     LAUNCH_CHECK();
     CHECK(mlp_body(c, st, c->cost_mdl, rows, flat, {seg(c->pairs, 0, 256)}));
@@ -2399,7 +2429,7 @@ extern "C" int gcpb200_infer_action(gcpb200_ctx* c, const float* img, const floa
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int rows = (n + 127) / 128 * 128;
-    const LevelGeom flat = {rows, 0, DEPTH};
+    const LevelGeom flat = {rows, 0, c->depth};
     // encoder on the current image(s): latent rows 0..n-1 of the workspace (the skip maps it also writes are scratch
     // that every rollout recomputes)
     encoder_kernel<<<dim3(n, 1), ENC_THREADS, 0, st>>>(img, img, c->enc, c->lat_f32, c->lat.p, 0, 0, c->s0, c->s2, c->s2b.p);
@@ -2444,7 +2474,7 @@ extern "C" int gcpb200_refit(gcpb200_ctx* c, const float* z, const int32_t* elit
         return -1;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int per = N_NODES * NZ_VAE;
+    const int per = c->n_nodes * NZ_VAE;
     const int S = std::max(1, std::min(REFIT_SPLITS, k / 8));
     refit_partial_kernel<<<dim3((per / 4 + 127) / 128, S), 128, 0, st>>>(z, elite_idx, k, per, c->refit_part);
     LAUNCH_CHECK();
@@ -2459,7 +2489,7 @@ extern "C" int gcpb200_sample_noise(gcpb200_ctx* c, const float* mean, const flo
         gcp_set_error("gcpb200_sample_noise: bad arguments");
         return -1;
     }
-    const int per = N_NODES * NZ_VAE;
+    const int per = c->n_nodes * NZ_VAE;
     const size_t n = (size_t)B * (per / 4);
     sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mean, stdv, std_scalar, seed, first_candidate_id, nullptr, B, per, clip, z);
@@ -2473,7 +2503,7 @@ extern "C" int gcpb200_sample_noise_ids(gcpb200_ctx* c, const float* mean, const
         gcp_set_error("gcpb200_sample_noise_ids: bad arguments");
         return -1;
     }
-    const int per = N_NODES * NZ_VAE;
+    const int per = c->n_nodes * NZ_VAE;
     const size_t n = (size_t)B * (per / 4);
     sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mean, stdv, std_scalar, seed, 0ULL, ids, B, per, clip, z);

@@ -25,7 +25,7 @@ class Engine:
     """One context = one device.  Not thread-safe (same as the reference model object)."""
 
     def __init__(self, device, max_candidates=1024, attach_cost_mdl=False, decoder_slot_chunk=0, model="tree",
-                 lib=None, reserved0=0):
+                 lib=None, reserved0=0, hierarchy_levels=8, max_seq_len=200, tied_layers=False):
         """lib / reserved0: test hooks -- tests/verify_lib.py passes the separately built verification library
         (tests/cuda/libgcpb200_verify.so) and its SIMT cross-check switch; the product never sets them."""
         if not torch.cuda.is_available():
@@ -39,8 +39,12 @@ class Engine:
         self.attach_cost_mdl = bool(attach_cost_mdl)
         self.model = model
         kind = {"tree": _C.MODEL_TREE, "sequential": _C.MODEL_SEQUENTIAL, "tree_adaptive": _C.MODEL_TREE_ADAPTIVE}[model]
+        # tree shape: 25-room = 8 levels / 200 frames / one TreeModule per level; 9-room = 7 / 100 / tied
+        self.depth, self.max_len, self.tied = int(hierarchy_levels), int(max_seq_len), bool(tied_layers)
+        self.n_nodes = (1 << self.depth) - 1 if model != "sequential" else N_NODES
+        self.seq_steps = self.max_len - 1
         cfg = _C.Config(self.index, self.max_candidates, int(attach_cost_mdl), int(reserved0),
-                        int(decoder_slot_chunk), kind)
+                        int(decoder_slot_chunk), kind, self.depth if model != "sequential" else 0, self.max_len, int(self.tied))
         h = C.c_void_p()
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_create(C.byref(h), C.byref(cfg)))
@@ -109,12 +113,12 @@ class Engine:
         dev = self.device
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
-        assert z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (N_NODES, NZ_VAE)
+        assert z.dtype == torch.float32 and z.is_contiguous() and tuple(z.shape[1:]) == (self.n_nodes, NZ_VAE)
         z_host = None
         if not z.is_cuda:
             if not z.is_pinned():
                 z = z.pin_memory()
-            z_host, z = z, self._buf("z_dev", (B, N_NODES, NZ_VAE))
+            z_host, z = z, self._buf("z_dev", (B, self.n_nodes, NZ_VAE))
             self._z_host_ref = z_host          # keep the host buffer alive until the next call
         I_0 = I_0.to(**f32).contiguous()
         I_g = I_g.to(**f32).contiguous()
@@ -123,27 +127,27 @@ class Engine:
         else:
             mk = self._buf
         out = dict(z=z, e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
-                   e_df=mk("e_df", (B, N_NODES, NZ_ENC)))
+                   e_df=mk("e_df", (B, self.n_nodes, NZ_ENC)))
         if want_logits:
-            out["seq_len_logits"] = mk("seq_len_logits", (B, MAX_LEN))
+            out["seq_len_logits"] = mk("seq_len_logits", (B, self.max_len))
         if want_prior:
-            out["mu_df"] = mk("mu_df", (B, N_NODES, NZ_VAE))
-            out["log_sigma_df"] = mk("log_sigma_df", (B, N_NODES, NZ_VAE))
+            out["mu_df"] = mk("mu_df", (B, self.n_nodes, NZ_VAE))
+            out["log_sigma_df"] = mk("log_sigma_df", (B, self.n_nodes, NZ_VAE))
         if want_images:
-            out["images_df"] = mk("images_df", (B, N_NODES, 3, 32, 32))
+            out["images_df"] = mk("images_df", (B, self.n_nodes, 3, 32, 32))
         adaptive = self.model == "tree_adaptive"
         if adaptive:
             # AdaptiveBinding: distance-predictor logits + the kept (depth-first) node list per candidate
             want_existence = want_aux = False
-            out["distances"] = mk("distances", (B, N_NODES - 1))
-            out["pruned_nodes"] = mk("pruned_nodes", (B, N_NODES), torch.int32)
+            out["distances"] = mk("distances", (B, self.n_nodes - 1))
+            out["pruned_nodes"] = mk("pruned_nodes", (B, self.n_nodes), torch.int32)
             out["pruned_len"] = mk("pruned_len", (B,), torch.int32)
         if want_existence:
-            out["existence"] = mk("existence", (B, N_NODES))
+            out["existence"] = mk("existence", (B, self.n_nodes))
         if want_aux:
-            out["model_enc_seq"] = mk("model_enc_seq", (B, MAX_LEN, NZ_ENC))
-            out["actions"] = mk("actions", (B, MAX_LEN, 2))
-            out["regressed_state"] = mk("regressed_state", (B, MAX_LEN, 2))
+            out["model_enc_seq"] = mk("model_enc_seq", (B, self.max_len, NZ_ENC))
+            out["actions"] = mk("actions", (B, self.max_len, 2))
+            out["regressed_state"] = mk("regressed_state", (B, self.max_len, 2))
         if end_ind is not None:
             end_ind = end_ind.to(device=dev, dtype=torch.int64).contiguous()
         if l2_goal is not None:
@@ -171,7 +175,7 @@ class Engine:
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
         z = z.to(**f32).contiguous()
-        assert tuple(z.shape[1:]) == (SEQ_STEPS, NZ_VAE)
+        assert tuple(z.shape[1:]) == (self.seq_steps, NZ_VAE)
         I_0 = I_0.to(**f32).contiguous()
         I_g = I_g.to(**f32).contiguous()
         if fresh:
@@ -179,18 +183,18 @@ class Engine:
         else:
             mk = self._buf
         out = dict(z=z, e_0=mk("e_0", (B, NZ_ENC)), e_g=mk("e_g", (B, NZ_ENC)), end_ind=mk("end_ind", (B,), torch.int64),
-                   encodings=mk("encodings", (B, SEQ_STEPS, NZ_ENC)))
+                   encodings=mk("encodings", (B, self.seq_steps, NZ_ENC)))
         if want_logits:
-            out["seq_len_logits"] = mk("seq_len_logits", (B, MAX_LEN))
+            out["seq_len_logits"] = mk("seq_len_logits", (B, self.max_len))
         if want_prior:
-            out["mu"] = mk("seq_mu", (B, SEQ_STEPS, NZ_VAE))
-            out["log_sigma"] = mk("seq_log_sigma", (B, SEQ_STEPS, NZ_VAE))
+            out["mu"] = mk("seq_mu", (B, self.seq_steps, NZ_VAE))
+            out["log_sigma"] = mk("seq_log_sigma", (B, self.seq_steps, NZ_VAE))
         if want_images:
-            out["images"] = mk("seq_images", (B, MAX_LEN, 3, 32, 32))
+            out["images"] = mk("seq_images", (B, self.max_len, 3, 32, 32))
         if want_aux:
-            out["model_enc_seq"] = mk("model_enc_seq", (B, MAX_LEN, NZ_ENC))
-            out["actions"] = mk("actions", (B, MAX_LEN, 2))
-            out["regressed_state"] = mk("regressed_state", (B, MAX_LEN, 2))
+            out["model_enc_seq"] = mk("model_enc_seq", (B, self.max_len, NZ_ENC))
+            out["actions"] = mk("actions", (B, self.max_len, 2))
+            out["regressed_state"] = mk("regressed_state", (B, self.max_len, 2))
         i64 = lambda t: None if t is None else t.to(device=dev, dtype=torch.int64).contiguous()
         end_ind, given_end_ind = i64(end_ind), i64(given_end_ind)
         io = _C.SeqIO(
@@ -223,9 +227,9 @@ class Engine:
     def gather_nodes(self, src_df, nodes, length):
         """src_df [B,255,D...] -> [B,255,D] with rows nodes[c,:length[c]] in order, zeros after (adaptive pruning)."""
         B = src_df.shape[0]
-        flat = src_df.reshape(B, N_NODES, -1).contiguous()
+        flat = src_df.reshape(B, self.n_nodes, -1).contiguous()
         D = flat.shape[2]
-        dst = torch.empty(B, N_NODES, D, device=self.device, dtype=torch.float32)
+        dst = torch.empty(B, self.n_nodes, D, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_gather_nodes(self.h, _ptr(flat), _ptr(nodes.contiguous()), _ptr(length.contiguous()), B, D,
                                                    _ptr(dst), _stream()))
@@ -243,9 +247,9 @@ class Engine:
     def prune_gather(self, src_df, end_ind):
         """src_df [B,255,D...] -> [B,200,D] with frames 0..end_ind in order, zeros after."""
         B = src_df.shape[0]
-        flat = src_df.reshape(B, N_NODES, -1).contiguous()
+        flat = src_df.reshape(B, self.n_nodes, -1).contiguous()
         D = flat.shape[2]
-        dst = torch.empty(B, MAX_LEN, D, device=self.device, dtype=torch.float32)
+        dst = torch.empty(B, self.max_len, D, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_prune_gather(self.h, _ptr(flat), _ptr(end_ind.contiguous()), B, D, _ptr(dst), _stream()))
         return dst
@@ -308,8 +312,8 @@ class Engine:
         return idx, val
 
     def refit(self, z, elite_idx):
-        mean = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
-        std = torch.empty(N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        mean = torch.empty(self.n_nodes, NZ_VAE, device=self.device, dtype=torch.float32)
+        std = torch.empty(self.n_nodes, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_refit(self.h, _ptr(z), _ptr(elite_idx.contiguous()), elite_idx.shape[0], _ptr(mean),
                                             _ptr(std), _stream()))
@@ -317,7 +321,7 @@ class Engine:
 
     def sample_noise(self, n, mean=None, std=None, std_scalar=1.0, seed=0, first_candidate_id=0, clip=float("inf"),
                      out=None):
-        z = out if out is not None else torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        z = out if out is not None else torch.empty(n, self.n_nodes, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_sample_noise(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
                                                    int(first_candidate_id), int(n), float(min(clip, 3.0e38)), _ptr(z),
@@ -327,7 +331,7 @@ class Engine:
     def sample_noise_ids(self, ids, mean=None, std=None, std_scalar=1.0, seed=0, clip=float("inf")):
         """Noise of the global candidate ids in `ids` (int32 cuda tensor)."""
         n = ids.shape[0]
-        z = torch.empty(n, N_NODES, NZ_VAE, device=self.device, dtype=torch.float32)
+        z = torch.empty(n, self.n_nodes, NZ_VAE, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_sample_noise_ids(self.h, _ptr(mean), _ptr(std), float(std_scalar), int(seed),
                                                        _ptr(ids.contiguous()), int(n), float(min(clip, 3.0e38)), _ptr(z),
@@ -345,7 +349,7 @@ class Engine:
         f32 = dict(device=dev, dtype=torch.float32)
         i64 = dict(device=dev, dtype=torch.int64)
         B, T = traj_seq.shape[:2]
-        assert T == MAX_LEN and tuple(traj_seq.shape[2:]) == (3, 32, 32)
+        assert T == self.max_len and tuple(traj_seq.shape[2:]) == (3, 32, 32)
         traj_seq = traj_seq.to(**f32).contiguous()
         end_ind = torch.as_tensor(end_ind).to(**i64).contiguous()
         if I_0 is None:
@@ -359,13 +363,13 @@ class Engine:
                    cost_start=torch.as_tensor(cost_start).to(**i64).contiguous(),
                    cost_end=torch.as_tensor(cost_end).to(**i64).contiguous(),
                    cost_target=None if cost_target is None else torch.as_tensor(cost_target).to(**f32).reshape(-1).contiguous())
-        assert tuple(ins["eps"].shape) == (B, N_NODES, NZ_VAE)
+        assert tuple(ins["eps"].shape) == (B, self.n_nodes, NZ_VAE)
         assert ins["cost_target"] is None or ins["cost_target"].numel() == B
         shapes = dict(nll_per_frame=(B, T), kl_per_seq=(B,), e_0=(B, NZ_ENC), e_g=(B, NZ_ENC), enc_traj_seq=(B, T, NZ_ENC),
-                      inf_enc_seq=(B, T, NZ_ENC), seq_len_logits=(B, T), e_df=(B, N_NODES, NZ_ENC),
-                      p_mu=(B, N_NODES, NZ_VAE), p_log_sigma=(B, N_NODES, NZ_VAE), q_mu=(B, N_NODES, NZ_VAE),
-                      q_log_sigma=(B, N_NODES, NZ_VAE), match_timesteps=(B, N_NODES), images_df=(B, N_NODES, 3, 32, 32),
-                      existence=(B, N_NODES), model_enc_seq=(B, T, NZ_ENC), regressed_state=(B, T, 2), inv_actions=(B, 2),
+                      inf_enc_seq=(B, T, NZ_ENC), seq_len_logits=(B, T), e_df=(B, self.n_nodes, NZ_ENC),
+                      p_mu=(B, self.n_nodes, NZ_VAE), p_log_sigma=(B, self.n_nodes, NZ_VAE), q_mu=(B, self.n_nodes, NZ_VAE),
+                      q_log_sigma=(B, self.n_nodes, NZ_VAE), match_timesteps=(B, self.n_nodes), images_df=(B, self.n_nodes, 3, 32, 32),
+                      existence=(B, self.n_nodes), model_enc_seq=(B, T, NZ_ENC), regressed_state=(B, T, 2), inv_actions=(B, 2),
                       cost_pred=(B,))
         out = dict(losses=self._buf("train_losses", (len(_C.LOSS_NAMES),)))
         for name in want:

@@ -67,6 +67,16 @@ def gcp_tree_25room_config(**extra):
     return cfg
 
 
+def gcp_tree_9room_config(**extra):
+    """experiments/control/9room/gcp_tree/mod_hyper.py:33-54: the 9-room planner model -- 7 levels (127 nodes), 100
+    frames, and `untied_layers` left at its default False (ONE TreeModule for all levels)."""
+    cfg = gcp_tree_25room_config()
+    cfg.update(max_seq_len=100, hierarchy_levels=7)
+    cfg.pop("untied_layers")            # the 9-room experiment leaves it at the default (False)
+    cfg.update(extra)
+    return cfg
+
+
 def gcp_adaptive_25room_config(**extra):
     """The adaptive-binding GCP-tree model with the 25-room network sizes (config 4): experiments/prediction/
     base_configs/gcp_adaptive.py:6-11 over base_tree.py:11-20, sizes of experiments/prediction/25room/gcp_tree/conf.py.

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import spec
-from .engine import Engine, MAX_LEN, N_NODES
+from .engine import Engine
 from .hparams import build_hparams
 from .types import AttrDict
 
@@ -193,7 +193,8 @@ class _GCPModelBase(nn.Module):
             if dev.type != "cuda":
                 dev = next(self.parameters()).device
             self._engine = Engine(dev, self._max_candidates, attach_cost_mdl=self._hp.attach_cost_mdl,
-                                  model=self.ENGINE_KIND)
+                                  model=self.ENGINE_KIND, hierarchy_levels=max(int(self._hp.hierarchy_levels), 2),
+                                  max_seq_len=int(self._hp.max_seq_len), tied_layers=not self._hp.untied_layers)
             self._dirty = True
         if self._dirty:
             sd = {k: v for k, v in nn.Module.state_dict(self).items() if k in set(self._canonical_keys)}
@@ -251,13 +252,19 @@ class TreeModel(_GCPModelBase):
                 and hp.lstm_init == "mlp" and hp.use_skips and not hp.attach_inv_mdl and not hp.attach_state_regressor):
             self.ENGINE_KIND = "tree_adaptive"
             return
-        if not (hp.hierarchy_levels == 8 and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
+        # network sizes are those of the shipped GCP-tree configurations; tree depth, sequence length and tied / untied
+        # layers are context parameters: 25-room = 8 levels, 200 frames, untied (experiments/control/25room/gcp_tree/
+        # mod_hyper.py:33-54), 9-room = 7 levels, 100 frames, tied (experiments/control/9room/gcp_tree/mod_hyper.py:33-54)
+        shape_ok = (2 <= hp.hierarchy_levels <= 8 and hp.max_seq_len % 4 == 0 and 4 <= hp.max_seq_len <= 256
+                    and hp.max_seq_len <= 2 ** hp.hierarchy_levels - 1)
+        if not (shape_ok and hp.nz_enc == 128 and hp.nz_vae == 256 and hp.nz_mid == 128
                 and hp.nz_mid_lstm == 512 and hp.n_lstm_layers == 3 and hp.ngf == 16 and hp.img_sz == 32
-                and hp.max_seq_len == 200 and hp.untied_layers and hp.tree_lstm == "split_linear"
+                and hp.tree_lstm == "split_linear"
                 and hp.lstm_init == "mlp" and hp.matching_type == "balanced" and hp.use_skips
                 and hp.decoder_distribution == "discrete_logistic_mixture" and not hp.add_weighted_pixel_copy):
-            raise NotImplementedError("libgcpb200 is specialised to the 25-room GCP-tree configuration "
-                                      "(experiments/control/25room/gcp_tree/mod_hyper.py)")
+            raise NotImplementedError("libgcpb200 is specialised to the network sizes of the shipped GCP-tree configurations "
+                                      "(experiments/control/{25room,9room}/gcp_tree/mod_hyper.py); tree depth 2..8 and "
+                                      "max_seq_len (a multiple of 4, <= 2^depth - 1) are free")
 
     def _make_dense_rec(self):
         return TreeDenseRec(self)
@@ -268,7 +275,8 @@ class TreeModel(_GCPModelBase):
         hp = self._hp
         if self.ENGINE_KIND != "tree":
             raise NotImplementedError("the training-phase forward is implemented for the balanced 25-room GCP-tree only")
-        ok = (hp.attach_inv_mdl and hp.attach_state_regressor and hp.attach_cost_mdl and hp.get("run_cost_mdl", True)
+        ok = (hp.hierarchy_levels == 8 and hp.max_seq_len == 200 and hp.untied_layers
+              and hp.attach_inv_mdl and hp.attach_state_regressor and hp.attach_cost_mdl and hp.get("run_cost_mdl", True)
               and hp.regress_length and hp.get("seq_enc", "conv") == "conv"
               and not hp.get("supervised_decoder", False) and not hp.get("train_inv_mdl_full_seq", False)
               and hp.kl_weight == 1.0 and hp.length_pred_weight == 1.0 and hp.dense_img_rec_weight == 1.0
@@ -400,7 +408,7 @@ class TreeModel(_GCPModelBase):
     def forward(self, inputs, phase="train"):
         if not self._val_mode and "traj_seq" in inputs:
             return self._forward_train(inputs, phase)
-        z, inject = self._rollout_args(inputs, N_NODES)
+        z, inject = self._rollout_args(inputs, 2 ** self._hp.hierarchy_levels - 1)
         eng = self.engine
         dev = eng.device
         if z.is_cuda or not (z.dtype == torch.float32 and z.is_pinned()):
@@ -452,7 +460,7 @@ class TreeModel(_GCPModelBase):
             return outputs
         outputs.existence_predictor = AttrDict(existence=res["existence"])
         outputs["_lmax"] = lambda e=res["end_ind"]: int(e.max()) + 1      # length the reference pads to (host sync)
-        lmax = MAX_LEN if self.defer_length_sync else outputs["_lmax"]()
+        lmax = self._hp.max_seq_len if self.defer_length_sync else outputs["_lmax"]()
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
         outputs.actions = res["actions"][:, :lmax - 1]
         outputs.regressed_state = res["regressed_state"][:, :lmax]
@@ -503,7 +511,7 @@ class SequentialModel(_GCPModelBase):
         return SequentialDenseRec(self)
 
     def forward(self, inputs, phase="train"):
-        z, inject = self._rollout_args(inputs, MAX_LEN - 1)
+        z, inject = self._rollout_args(inputs, self._hp.max_seq_len - 1)
         eng = self.engine
         dev = eng.device
         z = z.to(device=dev, dtype=torch.float32).contiguous()
@@ -533,8 +541,8 @@ class SequentialModel(_GCPModelBase):
         outputs.dense_rec = dr
         if phase != "train":
             raise NotImplementedError("only the simulator's default phase='train' aux path is implemented")
-        outputs["_lmax"] = (lambda e=given: int(e.max()) + 1) if given is not None else (lambda: MAX_LEN)
-        lmax = MAX_LEN if self.defer_length_sync else outputs["_lmax"]()
+        outputs["_lmax"] = (lambda e=given: int(e.max()) + 1) if given is not None else (lambda: self._hp.max_seq_len)
+        lmax = self._hp.max_seq_len if self.defer_length_sync else outputs["_lmax"]()
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
         outputs.actions = res["actions"][:, :lmax - 1]
         outputs.regressed_state = res["regressed_state"][:, :lmax]

@@ -7,9 +7,9 @@ from .cem_simulator import DeviceRollouts
 
 
 def _lists_to_device(engine, seqs, width):
-    """Pack per-candidate [L_i, width] arrays into [B,200,width] + end_ind on the device."""
+    """Pack per-candidate [L_i, width] arrays into [B,max_seq_len,width] + end_ind on the device."""
     B = len(seqs)
-    buf = np.zeros((B, 200, width), dtype=np.float32)
+    buf = np.zeros((B, engine.max_len, width), dtype=np.float32)
     end = np.zeros((B,), dtype=np.int64)
     for i, s in enumerate(seqs):
         s = np.asarray(s, dtype=np.float32).reshape(len(s), -1)
@@ -89,10 +89,10 @@ def _as_df(engine, seq, end):
     """Scatter ordered frames [B,200,D] into a depth-first [B,255,D] array at the balanced-pruning
     positions, so the device cost kernels (which gather through the pruning map) see them unchanged."""
     B, _, D = seq.shape
-    df = torch.zeros(B, 255, D, device=seq.device)
+    df = torch.zeros(B, engine.n_nodes, D, device=seq.device)
     from ..pruning import frame_nodes
     for i, e in enumerate(end.tolist()):
-        nodes = torch.as_tensor(frame_nodes(e), device=seq.device)
+        nodes = torch.as_tensor(frame_nodes(e, engine.depth), device=seq.device)
         df[i, nodes] = seq[i, :e + 1]
     return df, end
 
