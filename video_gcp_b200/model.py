@@ -423,10 +423,11 @@ class TreeModel(_GCPModelBase):
         # planner mode (optional `inputs.planner_mode`, set by GCPImageSimulator.rollout_device for the CEM planner): decode
         # only the nodes balanced pruning keeps, and / or reduce the L2 image cost inside the decoder
         pm = inputs.get("planner_mode", None)
-        kw, want_images = {}, self.return_images
+        kw, want_images, want_heads = {}, self.return_images, True
         if pm is not None and self.ENGINE_KIND == "tree":
             want_images = want_images and bool(pm.get("images", True))
-            kw = dict(decode_kept_only=bool(pm.get("kept_only", True)))
+            want_heads = bool(pm.get("heads", True))     # False: a cost-only rollout (no existence / action / state heads)
+            kw = dict(decode_kept_only=bool(pm.get("kept_only", True)), want_existence=want_heads, want_aux=want_heads)
             if pm.get("l2", None) is not None:
                 kw.update(l2_goal=inputs.I_g[0], l2_dense=bool(pm["l2"][0]), l2_final_step_weight=float(pm["l2"][1]),
                           l2_out=pm.get("l2_out", None))
@@ -458,8 +459,10 @@ class TreeModel(_GCPModelBase):
             if "images_df" in res:
                 outputs.pruned_prediction = _LazyNodePruned(self, outputs, res["images_df"])
             return outputs
-        outputs.existence_predictor = AttrDict(existence=res["existence"])
         outputs["_lmax"] = lambda e=res["end_ind"]: int(e.max()) + 1      # length the reference pads to (host sync)
+        if not want_heads:
+            return outputs
+        outputs.existence_predictor = AttrDict(existence=res["existence"])
         lmax = self._hp.max_seq_len if self.defer_length_sync else outputs["_lmax"]()
         inputs.model_enc_seq = res["model_enc_seq"][:, :lmax]
         outputs.actions = res["actions"][:, :lmax - 1]

@@ -53,7 +53,11 @@ class CEMPlanner:
         if not self._hp.prune_before_decode:
             return dict(planner_mode=dict(kept_only=False, images=True, l2=spec, l2_out=l2_out))
         latent_cost = hasattr(self._cost_fcn, "pairs_device")       # learned latent-space cost: reads no image at all
-        return dict(planner_mode=dict(kept_only=True, images=images or (spec is None and not latent_cost), l2=spec, l2_out=l2_out))
+        # CEM iterations of an image-space cost read nothing but the cost: the existence / inverse-model / state heads are
+        # left to the final rollout of the elites (which returns actions and states); a latent-space cost needs the pruned
+        # latent sequence the heads' path produces
+        return dict(planner_mode=dict(kept_only=True, images=images or (spec is None and not latent_cost), l2=spec, l2_out=l2_out,
+                                      heads=images or latent_cost or spec is None))
 
     def _build_sampler(self):
         return self._hp.sampler(self._hp.sampler_clip_val, self._hp.max_seq_len, self._hp.action_dim, self._hp.initial_std)

@@ -26,6 +26,7 @@ class DeviceRollouts:
             self.enc_seq = outputs.dense_rec.encodings[..., 0, 0]
             return
         self.images_df = outputs.tree.df.images if "images" in outputs.tree._fields else None
+        self.has_heads = "actions" in outputs      # False: a cost-only rollout, to_host() is not available
         self.e_df = outputs.tree.df.e_g_prime[..., 0, 0]
 
     def __len__(self):
@@ -36,6 +37,8 @@ class DeviceRollouts:
         One device-side gather per field, one D2H copy per field into pinned host memory (a pageable destination costs
         ~10x the copy time at 250 MB of elite frames); the per-candidate arrays are views of those host blocks, which stay
         alive as long as any of the arrays does."""
+        if not getattr(self, "has_heads", True):
+            raise RuntimeError("this rollout was made cost-only (planner_mode heads=False): it carries no frames / actions / states")
         eng = self.model.engine
         ends = self.end_ind.tolist()
         n_all = len(ends)
