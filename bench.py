@@ -278,11 +278,11 @@ def main():
     eng = model.engine
     sim = GCPImageSimulator(model, append_latent=False)
 
-    def make_planner(n_iters=1, seed=7, pruned=False):
+    def make_planner(n_iters=1, seed=7, pruned=False, sort_lengths=None):
         return ImageCEMPlanner(dict(batch_size=N, n_iters=n_iters, elite_frac=ELITE_FRAC, cost_fcn=L2ImageCost, dense_cost=True,
                                     final_step_cost_weight=1.0, sampler=partial(SimpleTreeCEMSampler, n_level_hierarchy=8),
                                     max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=chunk, seed=seed,
-                                    prune_before_decode=pruned), sim)
+                                    prune_before_decode=pruned, sort_lengths=sort_lengths), sim)
 
     # `value` / `e2e`: the canonical workload, all 255 nodes of every candidate decoded (what the reference computes)
     planner = make_planner()
@@ -351,7 +351,8 @@ def main():
         plp._sampler.init()
         ms_p = timed(lambda: plp.cem_iteration(state_t, goal_t), args.steps, args.warmup, world, dev, dist)
         # same candidates, same rollout seeds -> the two modes must agree bit for bit (checked outside the timed region)
-        pa, pb = make_planner(seed=31), make_planner(seed=31, pruned=True)
+        # (the full-decode side also takes the sampled lengths in descending order, so both see the same lengths)
+        pa, pb = make_planner(seed=31, sort_lengths=True), make_planner(seed=31, pruned=True)
         pa._sampler.init(), pb._sampler.init()
         model.seed = 1000
         ca, ia, va, _ = pa.cem_iteration(state_t, goal_t)
@@ -361,15 +362,18 @@ def main():
         same = bool(torch.equal(ia, ib) and torch.equal(pa._sampler._mean_d, pb._sampler._mean_d)
                     and torch.equal(pa._sampler._std_d, pb._sampler._std_d))
         same = same and bool(torch.equal(ca, cb))
-        DEC_FLOP_PER_NODE = 0.69 * FLOP_PER_ROLLOUT / 255          # decoder = 69 % of the canonical work
-        executed = None if kept is None else FLOP_PER_ROLLOUT - DEC_FLOP_PER_NODE * (255 - kept)
+        # decoder = 69 %, tree recursion = 31 % of the canonical work, both per node; the tree is pruned
+        # at (node, 128-candidate tile) granularity, so the executed figure is a lower bound
+        NODE_FLOP = FLOP_PER_ROLLOUT / 255
+        executed = None if kept is None else NODE_FLOP * kept
         extras["value_pruned"] = {
             "value": N * args.steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / args.steps,
             "speedup_vs_value": ms / ms_p, "kept_nodes_mean": kept, "executed_flop_per_rollout": executed,
             "same_costs_elites_refit_as_full_decode": same,
             "note": "ImageCEMPlanner(prune_before_decode=True).cem_iteration: only the end_ind+1 nodes balanced pruning keeps "
-                    "are decoded, the L2 cost is reduced in the decoder-tail epilogue, no image is written; `value` (all 255 "
-                    "nodes, canonical FLOPs) stays the headline"}
+                    "are decoded AND computed by the tree recursion (sampled lengths handed out in descending order so that "
+                    "128-candidate tiles share a length class), the L2 cost is reduced in the decoder-tail epilogue, no image "
+                    "is written, no existence / action / state heads; `value` (all 255 nodes, canonical FLOPs) stays the headline"}
 
         # ---- a whole planner call: n_iters iterations + final rollout of the elites + the plan on the host
         if B <= chunk:

@@ -127,6 +127,16 @@ typedef struct {
     float* l2_cost;          /* [B] L2ImageCost of every candidate (cost_fcn.py:9-22,65-72); same bits in both decode modes */
     int l2_dense;            /* dense_cost: sum over frames (1) or last frame only (0) */
     float l2_final_step_weight;
+    int tree_kept_only;      /* 1 (needs decode_kept_only, no existence output): the TREE recursion, too, visits only the (node,
+                                128-candidate tile) pairs some candidate keeps -- level 7 is half of the recursion and a tenth
+                                of its nodes is kept on average.  e_df / mu_df / log_sigma_df then hold valid entries for
+                                kept nodes only; costs, pruned frames and the pruned-sequence heads are bit-identical.  Most
+                                effective when neighbouring candidates have similar lengths */
+    int sort_sampled_lengths; /* 1 (images_shared, end_ind == NULL): the sampled rollout lengths are handed to the candidates in
+                                descending order.  Every candidate's length is an i.i.d. draw from the same predictor output and
+                                independent of its noise, so the joint law of (noise, length) over the batch -- hence costs,
+                                elites and refit of a CEM iteration -- is unchanged; candidate tiles become homogeneous in
+                                length, which is what tree_kept_only needs to skip work */
 } gcpb200_rollout_io;
 
 /* I/O of the sequential GCP rollout (SequentialModel forward in val_mode with injected z, default phase as the

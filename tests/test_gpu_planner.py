@@ -405,7 +405,7 @@ def test_planner_pruned_mode_equals_full_decode(dev, sd):
         pl = ImageCEMPlanner(dict(batch_size=N, n_iters=2, elite_frac=0.1, cost_fcn=L2ImageCost, dense_cost=True,
                                   final_step_cost_weight=1.0, sampler=partial(SimpleTreeCEMSampler, n_level_hierarchy=8),
                                   max_seq_len=200, action_dim=256, initial_std=0.3, max_rollout_bs=128, seed=13,
-                                  prune_before_decode=pruned), GCPImageSimulator(model, append_latent=True))
+                                  prune_before_decode=pruned, sort_lengths=True), GCPImageSimulator(model, append_latent=True))
         model.seed = 50
         frames, actions, latents, score = pl(state, goal)
         res.append((frames.copy(), actions.copy(), latents.copy(), score, pl._sampler.get_dists()))
@@ -414,3 +414,51 @@ def test_planner_pruned_mode_equals_full_decode(dev, sd):
     assert abs(a[3] - b[3]) <= 2e-6 * abs(a[3])
     assert np.array_equal(a[4].mean, b[4].mean) and np.array_equal(a[4].std, b[4].std)
     model.engine.close()
+
+
+@pytest.mark.parametrize("order", ["sorted", "random"])
+def test_tree_pruning_is_bit_identical(dev, sd, order):
+    """gcpb200_rollout_io.tree_kept_only: the recursion visits only the (node, candidate tile) pairs some candidate keeps.
+    Everything the planner reads -- fused cost, pruned frames, pruned latent sequence, actions, states -- is the same bits
+    as with the whole tree computed, and the latents of kept nodes are identical; with lengths in descending order the deep
+    levels' work lists are short (checked through the launch-independent row counts the library keeps), with random
+    lengths the lists are long but the result is the same."""
+    from video_gcp_b200.engine import Engine
+    from video_gcp_b200.pruning import frame_nodes
+    from video_gcp_b200.synthetic import synthetic_rollout_inputs
+    B = 300
+    eng = Engine(dev, max_candidates=384, attach_cost_mdl=True)
+    eng.load_weights(sd)
+    inp = synthetic_rollout_inputs(B, seed=9, shared_images=True)
+    end = np.random.default_rng(4).integers(1, 200, size=B)
+    end[:3] = (199, 128, 127)
+    if order == "sorted":
+        end = np.sort(end)[::-1].copy()
+    ei = torch.as_tensor(end).to(dev)
+    I0, Ig, z = inp["I_0"][:1].to(dev), inp["I_g"][:1].to(dev), inp["z"].to(dev)
+    kw = dict(end_ind=ei, images_shared=True, decode_kept_only=True, l2_goal=Ig[0], want_existence=False, fresh=True)
+    a = eng.rollout(I0, Ig, z, **kw)
+    b = eng.rollout(I0, Ig, z, tree_kept_only=True, **kw)
+    assert torch.equal(a["l2_cost"], b["l2_cost"])
+    for k in ("model_enc_seq", "actions", "regressed_state", "seq_len_logits"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(eng.prune_gather(a["images_df"], a["end_ind"]), eng.prune_gather(b["images_df"], b["end_ind"]))
+    for c in (0, 1, 2, 150, B - 1):
+        nodes = torch.as_tensor(frame_nodes(int(end[c])))
+        assert torch.equal(a["e_df"][c].cpu()[nodes], b["e_df"][c].cpu()[nodes])
+    eng.close()
+
+
+def test_sorted_sampled_lengths(dev, sd):
+    """sort_sampled_lengths: the same draws as without it (same seed), handed out in descending order."""
+    from video_gcp_b200.engine import Engine
+    from video_gcp_b200.synthetic import synthetic_rollout_inputs
+    eng = Engine(dev, max_candidates=1024, attach_cost_mdl=True)
+    eng.load_weights(sd)
+    inp = synthetic_rollout_inputs(1000, seed=3, shared_images=True)
+    I0, Ig, z = inp["I_0"][:1].to(dev), inp["I_g"][:1].to(dev), inp["z"].to(dev)
+    kw = dict(end_ind=None, seed=77, images_shared=True, want_images=False, want_aux=False, want_existence=False)
+    plain = eng.rollout(I0, Ig, z, **kw)["end_ind"].cpu().numpy().copy()
+    srt = eng.rollout(I0, Ig, z, sort_sampled_lengths=True, **kw)["end_ind"].cpu().numpy().copy()
+    assert np.array_equal(srt, np.sort(plain)[::-1]) and (np.diff(srt) <= 0).all() and srt.min() >= 2
+    eng.close()

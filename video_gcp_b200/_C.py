@@ -33,7 +33,8 @@ class RolloutIO(C.Structure):
                 ("distances", C.c_void_p), ("pruned_nodes", C.c_void_p), ("pruned_len", C.c_void_p),
                 ("prune_threshold", C.c_float),
                 ("decode_kept_only", C.c_int), ("l2_goal", C.c_void_p), ("l2_cost", C.c_void_p), ("l2_dense", C.c_int),
-                ("l2_final_step_weight", C.c_float)]
+                ("l2_final_step_weight", C.c_float), ("tree_kept_only", C.c_int),
+                ("sort_sampled_lengths", C.c_int)]
 
 
 class SeqIO(C.Structure):

@@ -144,6 +144,7 @@ struct gcpb200_ctx {
     DevBuf latc;
     int *row_cand = nullptr, *row_node = nullptr, *row_off = nullptr, *n_rows = nullptr;
     float* frame_sq = nullptr;
+    int *tree_tiles = nullptr, *tree_rows = nullptr;   // per-level work lists of the pruned recursion (tree_worklists_kernel)
     unsigned long long* topk_sel = nullptr;   // elite selection: the k selected composite keys (grown on demand)
     int topk_cap = 0;
     double* refit_part = nullptr;             // refit: per-split (sum, sum of squares) [REFIT_SPLITS][255*256][2]
@@ -916,7 +917,8 @@ static bool fused_mlp_enabled() {
     return true;
 #endif
 }
-static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
+static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in,
+                          const GemmDyn* dyn = nullptr) {
     static bool configured_dev[64] = {false};     // function attributes are per device
     int dev = 0;
     GCP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -950,6 +952,10 @@ static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int row
     ia.N = 128;
     ia.K = K;
     ia.g = g;
+    if (dyn != nullptr) {
+        ia.rows_dev = dyn->rows_dev;
+        ia.rows_dev_base = dyn->base;
+    }
     for (int l = 0; l < 3; ++l) {
         a.w_mid[l] = m.mid[l].map_box[3];
         a.gam[l] = m.gam[l];
@@ -976,13 +982,14 @@ static int mlp_body_fused(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int row
 }
 
 // runs in -> mid x3; the last activation ends in c->tb (K = m.mid_k columns valid)
-static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in) {
+static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, LevelGeom g, const std::vector<Seg>& in,
+                    const GemmDyn* dyn = nullptr) {
     bool plain = in.size() <= GEMM_MAX_SEGS;
     for (const Seg& s : in) plain = plain && s.group_cols == 0 && s.k_len % GEMM_BK == 0;
     if (!c->use_ref && fused_mlp_enabled() && plain && m.n_mid == 3 && m.mid_valid == 128 && m.mid_k == 128 &&
         m.gn_group == 16 && m.in.N == 128 && c->tb.ld == 128)
-        return mlp_body_fused(c, st, m, rows, g, in);
-    CHECK(gemm(c, st, rows, g, in, m.in, 128, EPI_LINEAR, epi_linear(ACT_LRELU, c->ta.p, c->ta.ld, nullptr, 0, m.mid_valid)));
+        return mlp_body_fused(c, st, m, rows, g, in, dyn);
+    CHECK(gemm(c, st, rows, g, in, m.in, 128, EPI_LINEAR, epi_linear(ACT_LRELU, c->ta.p, c->ta.ld, nullptr, 0, m.mid_valid), 0, -1, dyn));
     DevBuf* src = &c->ta;
     DevBuf* dst = &c->tb;
     LevelGeom flat = g;
@@ -991,7 +998,7 @@ static int mlp_body(gcpb200_ctx* c, cudaStream_t st, const Mlp& m, int rows, Lev
         e.gn_gamma = m.gam[i];
         e.gn_beta = m.bet[i];
         e.gn_group = m.gn_group;
-        CHECK(gemm(c, st, rows, flat, {seg(*src, 0, m.mid_k)}, m.mid[i], 128, EPI_GN, e));
+        CHECK(gemm(c, st, rows, flat, {seg(*src, 0, m.mid_k)}, m.mid[i], 128, EPI_GN, e, 0, -1, dyn));
         std::swap(src, dst);
     }
     // after an odd number of swaps the result is in `src` == tb
@@ -1101,6 +1108,8 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         rc |= dalloc(c, &c->row_off, Bp + 1);
         rc |= dalloc(c, &c->n_rows, 1);
         rc |= dalloc(c, &c->frame_sq, 256 * Bp);
+        rc |= dalloc(c, &c->tree_tiles, (size_t)c->n_nodes * (Bp >> 7) + 2 * DEPTH + 2);
+        rc |= dalloc(c, &c->tree_rows, DEPTH);
     }
     rc |= dalloc(c, &c->refit_part, (size_t)REFIT_SPLITS * c->n_nodes * NZ_VAE * 2, false);
     if (rc) {
@@ -1271,6 +1280,7 @@ struct CommonIO {
     int B;
     float *e_0, *e_g, *seq_len_logits;
     int64_t* end_ind_out;
+    int sort_lengths;
 };
 
 // Encoder on the start / goal images (latent slots 0 and goal_row0 / Bp, decoder skips of I_0) and the rollout length
@@ -1311,6 +1321,10 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
     } else {
         sample_length_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->logits, 256, c->max_len, B, io->seed, c->end_ind);
         LAUNCH_CHECK();
+        if (io->sort_lengths && io->images_shared) {
+            sort_lengths_desc_kernel<<<1, 1024, 0, st>>>(c->end_ind, B);
+            LAUNCH_CHECK();
+        }
     }
     if (io->end_ind_out) GCP_CUDA_CHECK(cudaMemcpyAsync(io->end_ind_out, c->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
 
@@ -1530,26 +1544,30 @@ struct PosteriorArgs {
 // One level of SubgoalTreeLayer.produce_tree (gcp/prediction/utils/tree_utils.py:21-44) = TreeModule.produce_subgoal on all
 // B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
 static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
-                      const PosteriorArgs* post, float* e_df = nullptr) {
+                      const PosteriorArgs* post, float* e_df = nullptr, bool pruned = false) {
     const LevelGeom flat = {Bp, 0, c->depth};
     const int goal_row0 = (c->n_nodes + 1) * Bp;
     const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
     {
         const LevelW& L = c->lvl[c->tied ? 0 : l];
-        const LevelGeom g = {Bp, l, c->depth};
+        // planner mode: only the (node, candidate tile) pairs of this level's work list; the launches are shaped for the whole
+        // level and read the live row count (c->tree_rows[l]) on the device
+        const LevelGeom g = {Bp, l, c->depth, pruned ? c->tree_tiles + tree_tiles_offset(l, Bp >> 7) : nullptr};
+        const GemmDyn dynv = {c->tree_rows + l, 0};
+        const GemmDyn* dyn = pruned ? &dynv : nullptr;
         const int rows = Bp << l;
         // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
         CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
         // prior p(z | e_l, e_r) and reparametrisation
         const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
-        CHECK(mlp_body(c, st, L.prior, rows, g, par));
+        CHECK(mlp_body(c, st, L.prior, rows, g, par, dyn));
         {
             EpiParams e;
             memset(&e, 0, sizeof(e));
             e.z = z; e.n_cand = B; e.nz = NZ_VAE;
             e.out_bf16 = c->zeta.p; e.out_bf16_ld = NZ_VAE;
             e.mu_out = mu_df; e.ls_out = ls_df;
-            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.prior.mid_k)}, L.prior.head, 256, EPI_REPARAM, e));
+            CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.prior.mid_k)}, L.prior.head, 256, EPI_REPARAM, e, 0, -1, dyn));
         }
         if (post != nullptr) {
             // training phase: z ~ q(z | e_l, e_r, e_tilde), e_tilde = inference encoding of the frame the node is matched
@@ -1568,11 +1586,11 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         const std::vector<Seg> par_z = {par[0], par[1], seg(c->zeta, 0, NZ_VAE)};
         if (l == 0) {
             // MLPLSTMCellInitializer: hidden states of the two root parents (slots 0 and 256)
-            CHECK(mlp_body(c, st, L.init, rows, g, par_z));
+            CHECK(mlp_body(c, st, L.init, rows, g, par_z, dyn));
             CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init.head, 256, EPI_LINEAR,
-                       epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE)));
+                       epi_linear(ACT_NONE, c->hid.p, STATE, nullptr, 0, STATE), 0, -1, dyn));
             CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 256, EPI_LINEAR,
-                       epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE)));
+                       epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE), 0, -1, dyn));
         }
         // split-linear projections of the parents' LSTM state
         {
@@ -1585,14 +1603,14 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             // (max-rel 7.5e-3 either way: it is the bf16 rounding of the GEMM OPERANDS, which the SIMT cross-check kernels
             // with fp32 accumulation reproduce) and costs 1.2 ms per 1024-candidate rollout in extra HBM traffic.
             EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
-            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e));
+            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e, 0, -1, dyn));
         }
         // embed
         {
             EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
             e.rowbias = c->ctxb;
             e.rowbias_ld = HID;
-            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e));
+            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e, 0, -1, dyn));
         }
         // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
         DevBuf* xin = &c->xa;
@@ -1604,7 +1622,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             e.out_bf16 = xout->p; e.out_bf16_ld = HID;
             e.hid = c->hid.p; e.hid_ld = STATE; e.hid_col0 = 2 * HID * i; e.hidden = HID;
             e.write_hid = (l < c->depth - 1);
-            CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e));
+            CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID), seg(c->sh, i * HID, HID)}, L.lstm[i], 256, EPI_LSTM, e, 0, -1, dyn));
             std::swap(xin, xout);
         }
         // output linear -> node latent e' (raw, no activation) at the node's slot
@@ -1615,7 +1633,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             eo.out_f32_df = c->n_nodes;
             eo.n_cand = B;
         }
-        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR, eo));
+        CHECK(gemm(c, st, rows, g, {seg(*xin, 0, HID)}, L.out, 128, EPI_LINEAR, eo, 0, -1, dyn));
     }
 
     return 0;
@@ -1654,6 +1672,11 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         return -1;
     }
     const bool kept_only = io->decode_kept_only != 0 && (io->images_df != nullptr || fused_l2);
+    if (io->tree_kept_only && (!io->decode_kept_only || io->existence)) {
+        gcp_set_error("tree_kept_only needs decode_kept_only and no existence output (pruned-away nodes are not computed)");
+        return -1;
+    }
+    const bool tree_pruned = io->tree_kept_only != 0 && !adaptive && !c->use_ref;
     const bool decode_all = !kept_only && (io->images_df != nullptr || fused_l2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int B = io->B, Bp = (B + 127) / 128 * 128;
@@ -1712,7 +1735,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     ProfScope* scope = new ProfScope(c, st, 0);
     {
         CommonIO cio = {io->I_0, io->I_g, io->images_shared, io->end_ind, io->seed, B, io->e_0, io->e_g, io->seq_len_logits,
-                        io->end_ind_out};
+                        io->end_ind_out, io->sort_sampled_lengths};
         CHECK(run_encoder_length(c, st, cio, Bp, goal_row0));
     }
     const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
@@ -1747,7 +1770,12 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             gcp_set_error("mu_df and log_sigma_df must be given together");
             return -1;
         }
-        CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr, e_df));
+        if (tree_pruned && l == 0) {
+            // the rollout length is known (sampled / injected in run_encoder_length): work lists of every level
+            tree_worklists_kernel<<<c->depth, 1024, 0, st>>>(c->end_ind, B, Bp, 1, c->tree_tiles, c->tree_rows);
+            LAUNCH_CHECK();
+        }
+        CHECK(tree_level(c, st, l, B, Bp, io->z, io->mu_df, io->log_sigma_df, nullptr, e_df, tree_pruned));
     }
 
     trace_mark(st, "tree_l7_end");

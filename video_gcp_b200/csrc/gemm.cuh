@@ -33,6 +33,12 @@ struct LevelGeom {
     int Bp;     // candidates padded to a multiple of 128
     int level;  // tree level 0..depth-1 (0 for plain GEMMs)
     int depth;  // 8
+    // Work list of a pruned tree level (planner mode): tiles[i] = the 128-row tile (node j, candidate tile) = j * (Bp / 128) +
+    // ctile that the i-th tile of this launch stands for; null = every tile in order.  Slot-addressed operands / outputs
+    // (ROW_LEFT / ROW_RIGHT / ROW_SELF, the candidate index, the node of a row) use the LISTED tile, level-row scratch
+    // arrays (ROW_LEVEL) are addressed compactly by the launch's own tile index, so a level's kernels only touch and
+    // compute the (node, candidate tile) pairs some candidate keeps.
+    const int* tiles;
 };
 
 struct ASeg {
@@ -121,6 +127,13 @@ __device__ __forceinline__ int map_row(const LevelGeom& g, int mode, int row) {
     const int j = row / g.Bp;
     const int c = row - j * g.Bp;
     return slot_of(g, j, mode) * g.Bp + c;
+}
+__device__ __forceinline__ int listed_tile(const LevelGeom& g, int tile_m) {
+    return g.tiles != nullptr ? __ldg(g.tiles + tile_m) : tile_m;
+}
+// array row of the launch's row `row` (compact) whose listed ("logical") row is `lrow`
+__device__ __forceinline__ int map_row2(const LevelGeom& g, int mode, int row, int lrow) {
+    return mode == ROW_LEVEL ? row : map_row(g, mode, lrow);
 }
 __device__ __forceinline__ int seg_col0(const ASeg& s, int n0) {
     return s.col0 + (s.group_cols > 0 ? s.group_col[n0 / s.group_cols] : 0);
@@ -261,10 +274,11 @@ __device__ __forceinline__ void epilogue_math_fast(const EpiParams& p, int col0,
     }
 }
 
+// row: row of this launch (compact when the level is pruned); lrow: the row it stands for in the full level
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int col0,
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int lrow, int col0,
                                                float (&acc)[32], uint4* stage = nullptr, const float* gn_sm = nullptr) {
-    const int cand = row % g.Bp;
+    const int cand = lrow % g.Bp;
     if (p.bias != nullptr) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -303,18 +317,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
         }
         if (p.split_col > 0) {
             if (col0 < p.split_col) {
-                const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
+                const size_t r = (size_t)map_row2(g, p.out_bf16_mode, row, lrow);
                 if (stage != nullptr && nvalid >= 32)
                     store_bf16x32_staged(stage, p.out_bf16 + (r - (threadIdx.x & 31)) * p.out_bf16_ld + col0, p.out_bf16_ld, acc);
                 else
                     store_bf16x32(p.out_bf16 + r * p.out_bf16_ld + col0, acc, nvalid);
             } else {
-                const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
+                const size_t r = (size_t)map_row2(g, p.out_f32_mode, row, lrow);
                 store_f32x32(p.out_f32 + r * p.out_f32_ld + (col0 - p.split_col), acc, nvalid);
             }
         } else {
             if (p.out_bf16 != nullptr) {
-                const size_t r = (size_t)map_row(g, p.out_bf16_mode, row);
+                const size_t r = (size_t)map_row2(g, p.out_bf16_mode, row, lrow);
                 if (stage != nullptr && nvalid >= 32)
                     store_bf16x32_staged(stage, p.out_bf16 + (r - (threadIdx.x & 31)) * p.out_bf16_ld + col0, p.out_bf16_ld, acc);
                 else
@@ -323,11 +337,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
             if (p.out_f32 != nullptr) {
                 if (p.out_f32_df > 0) {
                     if (cand < p.n_cand) {
-                        const size_t r = (size_t)cand * p.out_f32_df + slot_of(g, row / g.Bp, ROW_SELF) - 1;
+                        const size_t r = (size_t)cand * p.out_f32_df + slot_of(g, lrow / g.Bp, ROW_SELF) - 1;
                         store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
                     }
                 } else {
-                    const size_t r = (size_t)map_row(g, p.out_f32_mode, row);
+                    const size_t r = (size_t)map_row2(g, p.out_f32_mode, row, lrow);
                     store_f32x32(p.out_f32 + r * p.out_f32_ld + col0, acc, nvalid);
                 }
             }
@@ -335,7 +349,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
     } else if (EPI == EPI_REPARAM) {
         // packed columns: [mu(16) | log_sigma(16)] for latent dims d0 .. d0+15
         const int d0 = col0 >> 1;
-        const int j = row / g.Bp;
+        const int j = lrow / g.Bp;
         const int node = p.z_nodes > 0 ? p.z_node : slot_of(g, j, ROW_SELF) - 1;  // depth-first node index / time step
         const int n_nodes = p.z_nodes > 0 ? p.z_nodes : (1 << g.depth) - 1;
         float zeta[16];
@@ -414,7 +428,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
             cf[1] = make_float4(c[4], c[5], c[6], c[7]);
         }
         if (p.write_hid) {
-            const size_t r = (size_t)map_row(g, ROW_SELF, row);
+            const size_t r = (size_t)map_row(g, ROW_SELF, lrow);
             bf16* hrow = p.hid + r * p.hid_ld + p.hid_col0 + u0;
             *reinterpret_cast<uint4*>(hrow) = hv;
             *reinterpret_cast<uint4*>(hrow + p.hidden) = cv;
@@ -518,7 +532,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 int kb = 0;
                 for (int s = 0; s < args.n_seg; ++s) {
                     const ASeg& sg = args.seg[s];
-                    const int row0 = tile_row0(args.g, sg.row_mode, tile_m) + sg.row_base;
+                    const int row0 = tile_row0(args.g, sg.row_mode, sg.row_mode == ROW_LEVEL ? tile_m : listed_tile(args.g, tile_m)) + sg.row_base;
                     const int c0 = seg_col0(sg, tile_n * BN);
                     for (int kk = 0; kk < sg.k_len; kk += GEMM_BK, ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -595,6 +609,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const int row = tile_m * GEMM_BM + row_in_tile;
+            const int lrow = listed_tile(args.g, tile_m) * GEMM_BM + row_in_tile;
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
             if (kPair && pair_fast) {
                 // both chunks of this thread at once; the accumulator buffer is released as soon as they are in registers
@@ -612,7 +627,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const int c0 = tile_n * BN + ch0 * 32;
                 epilogue_math_fast<EPI>(args.epi, c0, a0, gn_sm);
                 epilogue_math_fast<EPI>(args.epi, c0 + 32, a1, gn_sm);
-                const size_t r = (size_t)map_row(args.g, args.epi.out_bf16_mode, row);
+                const size_t r = (size_t)map_row2(args.g, args.epi.out_bf16_mode, row, lrow);
                 bf16* orow = args.epi.out_bf16 + (r - lane) * args.epi.out_bf16_ld + c0;
                 uint4* stg = store_stage + (warp - 2) * 128;
                 store_bf16x32_staged(stg, orow, args.epi.out_bf16_ld, a0);
@@ -625,7 +640,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 float acc[32];
                 __syncwarp();
                 tmem_ld32(t0 + ch * 32, acc);
-                epilogue_chunk<EPI>(args.epi, args.g, row, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128,
+                epilogue_chunk<EPI>(args.epi, args.g, row, lrow, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128,
                                     (EPI == EPI_GN && args.N <= 256) ? gn_sm : nullptr);
             }
             tc_fence_before();
@@ -674,7 +689,7 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(const __grid_constant__ G
             }
             kb += sg.k_len;
         }
-        epilogue_chunk<EPI>(args.epi, args.g, row, n0, acc);
+        epilogue_chunk<EPI>(args.epi, args.g, row, row, n0, acc);
     }
 }
 #endif

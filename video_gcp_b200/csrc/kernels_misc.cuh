@@ -140,6 +140,32 @@ __global__ void sample_length_kernel(const float* __restrict__ logits, int ld, i
     end_ind[c] = arg < 2 ? 2 : arg;
 }
 
+// Sampled rollout lengths of one CEM call, reassigned in descending order (counting sort of values in [0, 256); one CTA).
+// With shared start / goal images every candidate's length is an i.i.d. draw from the SAME distribution, independent of its
+// noise, so handing the sorted draws to candidates 0, 1, 2, ... leaves the joint law of the (noise, length) pairs -- and
+// with it costs, elites and refit -- unchanged, while 128-candidate tiles become homogeneous in length: that is what makes
+// the per-level work lists of the pruned tree recursion short (tree_worklists_kernel).
+__global__ void __launch_bounds__(1024) sort_lengths_desc_kernel(long long* __restrict__ end_ind, int n) {
+    __shared__ int hist[256];
+    __shared__ int start[257];          // start[v] = number of values > v  (first position of value v in descending order)
+    const int tid = threadIdx.x;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) atomicAdd(&hist[min(max((int)end_ind[i], 0), 255)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int v = 255; v >= 0; --v) { start[v] = acc; acc += hist[v]; }
+        start[256] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        int v = 255;
+        while (v > 0 && start[v] + hist[v] <= i) --v;      // the value whose run [start, start + count) holds position i
+        end_ind[i] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Balanced pruning (gcp/evaluation/evaluation_matching.py:192-206; gcp/prediction/models/tree/
 // frame_binding.py:42-65): integer interval recursion from (-1, end_ind+1); midpoint with truncating
@@ -344,6 +370,65 @@ __global__ void cost_from_frames_kernel(const float* __restrict__ frame_sq, cons
     }
     s = warp_sum(s);
     if (lane == 0) cost[c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Planner mode, tree side: which (node, 128-candidate tile) pairs of every tree level some candidate keeps.  A node is
+// kept iff its interval in the balanced-pruning recursion still has an interior point (frame_binding.py:42-65) -- the same
+// integer recursion as prune_map_kernel -- and a kept node's ancestors and interval ends are kept, so a level only
+// needs the listed tiles and every operand it reads was computed.  One CTA per level: a thread decides a tile by
+// scanning its 128 candidates, an ordered ballot / prefix compaction writes the list (ascending tile index; padded to
+// an even count with a copy of the last entry, for the CTA-pair GEMMs); rows[l] = listed tiles * 128.
+// tiles: [depth] lists at offsets off(l) = (2^l - 1) * tpn + 2 * l.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool node_kept(int end, int level, int j) {
+    int l = -1, r = end + 1, t = 0;
+    for (int lv = 0; lv <= level; ++lv) {
+        t = (l + r) / 2;
+        if (lv < level) {
+            if ((j >> (level - 1 - lv)) & 1) l = t; else r = t;
+        }
+    }
+    return t != l && t != r;
+}
+__host__ __device__ __forceinline__ int tree_tiles_offset(int level, int tpn) { return ((1 << level) - 1) * tpn + 2 * level; }
+
+__global__ void __launch_bounds__(1024) tree_worklists_kernel(const long long* __restrict__ end_ind, int n_cand, int Bp,
+                                                              int min_last, int* __restrict__ tiles, int* __restrict__ rows) {
+    __shared__ int wsum[32];
+    __shared__ int s_base;
+    const int level = blockIdx.x, tpn = Bp >> 7;
+    const int n_tiles = tpn << level;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* list = tiles + tree_tiles_offset(level, tpn);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const int tile = t0 + tid;
+        bool act = false;
+        if (tile < n_tiles) {
+            const int j = tile / tpn, c0 = (tile - j * tpn) << 7;
+            for (int c = c0; c < min(c0 + 128, n_cand) && !act; ++c) act = node_kept(max((int)end_ind[c], min_last), level, j);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (act) list[off + __popc(b & ((1u << lane) - 1u))] = tile;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += wsum[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int n = s_base;
+        if (n & 1) { list[n] = list[n - 1]; ++n; }
+        rows[level] = n * 128;
+    }
 }
 
 // Pair rows for the learned pairwise networks from two row tables: pairs[r] = cat(a[ia[r]], b[ib[r]]) (a null index

@@ -55,7 +55,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_fused_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmArgs& ia = args.in;
-    const int tiles_m = ia.rows / GEMM_BM;
     const int kb_in = ia.K / GEMM_BK;
 
     // weights only: safe before pdl_wait()
@@ -84,6 +83,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_fused_kernel(const __grid
     const uint32_t tmem_base = *tmem_holder;
     pdl_launch_dependents();
     pdl_wait();
+    int rows = ia.rows;
+    if (ia.rows_dev != nullptr)               // pruned tree level: the live row count is on the device (GemmArgs::rows_dev)
+        rows = min(rows, (max(__ldg(ia.rows_dev) - ia.rows_dev_base, 0) + GEMM_BM - 1) / GEMM_BM * GEMM_BM);
+    const int tiles_m = rows / GEMM_BM;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_fused_kernel(const __grid
                 int kb = 0;
                 for (int s = 0; s < ia.n_seg; ++s) {
                     const ASeg& sg = ia.seg[s];
-                    const int row0 = tile_row0(ia.g, sg.row_mode, tile) + sg.row_base;
+                    const int row0 = tile_row0(ia.g, sg.row_mode, sg.row_mode == ROW_LEVEL ? tile : listed_tile(ia.g, tile)) + sg.row_base;
                     for (int kk = 0; kk < sg.k_len; kk += GEMM_BK, ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* st = smem + stage * MLPF_STAGE_BYTES;

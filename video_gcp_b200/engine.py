@@ -99,7 +99,7 @@ class Engine:
     def rollout(self, I_0, I_g, z, end_ind=None, seed=0, images_shared=False, want_images=True,
                 want_prior=False, want_existence=True, want_aux=True, want_logits=True, fresh=False,
                 prune_threshold=0.5, decode_kept_only=False, l2_goal=None, l2_dense=True, l2_final_step_weight=1.0,
-                l2_out=None):
+                l2_out=None, tree_kept_only=False, sort_sampled_lengths=False):
         """Device tensors in, dict of device tensors out.  z: [B,255,256] fp32, either on the device or a PINNED host
         tensor; a host tensor is uploaded by the library level by level on its own copy stream, overlapped with
         the encoder and the upper tree levels (out["z"] is the device copy, valid in stream order after the call).
@@ -109,7 +109,10 @@ class Engine:
         Planner mode: decode_kept_only=True decodes only the nodes balanced pruning keeps (out["images_df"] then holds
         exactly those nodes' images, the other entries keep whatever the buffer held); l2_goal ([3,32,32] in [-1,1]) adds
         out["l2_cost"] ([B], written to `l2_out` if given), the L2 image cost reduced inside the decoder-tail kernel --
-        with want_images=False no image is written at all."""
+        with want_images=False no image is written at all.  tree_kept_only=True (with decode_kept_only, want_existence=False)
+        also restricts the tree recursion to the (node, candidate tile) pairs some candidate keeps; sort_sampled_lengths=True
+        hands the sampled lengths to the candidates in descending order (same joint distribution; see gcpb200.h), which is
+        what makes that restriction effective."""
         dev = self.device
         B = z.shape[0]
         f32 = dict(device=dev, dtype=torch.float32)
@@ -162,7 +165,8 @@ class Engine:
             _ptr(out.get("existence")), _ptr(out.get("model_enc_seq")), _ptr(out.get("actions")),
             _ptr(out.get("regressed_state")), _ptr(out.get("distances")), _ptr(out.get("pruned_nodes")),
             _ptr(out.get("pruned_len")), float(prune_threshold), int(bool(decode_kept_only)), _ptr(l2_goal),
-            _ptr(out.get("l2_cost")), int(bool(l2_dense)), float(l2_final_step_weight))
+            _ptr(out.get("l2_cost")), int(bool(l2_dense)), float(l2_final_step_weight), int(bool(tree_kept_only)),
+            int(bool(sort_sampled_lengths)))
         with torch.cuda.device(self.index):
             self._check(self.lib.gcpb200_rollout(self.h, C.byref(io), _stream()))
         return out

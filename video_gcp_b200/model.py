@@ -427,7 +427,10 @@ class TreeModel(_GCPModelBase):
         if pm is not None and self.ENGINE_KIND == "tree":
             want_images = want_images and bool(pm.get("images", True))
             want_heads = bool(pm.get("heads", True))     # False: a cost-only rollout (no existence / action / state heads)
-            kw = dict(decode_kept_only=bool(pm.get("kept_only", True)), want_existence=want_heads, want_aux=want_heads)
+            kept = bool(pm.get("kept_only", True))
+            kw = dict(decode_kept_only=kept, want_existence=want_heads, want_aux=want_heads,
+                      tree_kept_only=kept and not want_heads and not self.return_prior,
+                      sort_sampled_lengths=bool(pm.get("sort_lengths", False)))
             if pm.get("l2", None) is not None:
                 kw.update(l2_goal=inputs.I_g[0], l2_dense=bool(pm["l2"][0]), l2_final_step_weight=float(pm["l2"][1]),
                           l2_out=pm.get("l2_out", None))

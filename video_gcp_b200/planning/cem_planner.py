@@ -40,6 +40,10 @@ class CEMPlanner:
             # costs / elites / plans are identical to False, which decodes all 255 nodes of every candidate as the
             # reference does (cem_simulator.py:29-61 then discards them)
             prune_before_decode=True,
+            # True: the sampled rollout lengths of a call are handed to its candidates in descending order (they are i.i.d.
+            # draws from one distribution, independent of the noise, so nothing changes statistically); candidate tiles then
+            # share their length class and the pruned tree recursion skips most of the deep levels.  None = prune_before_decode
+            sort_lengths=None,
         )
 
     def _build_cost(self):
@@ -50,14 +54,15 @@ class CEMPlanner:
         cost is reduced inside the decoder (same bits in both modes); prune_before_decode decides whether the decoder
         visits the kept nodes only (and skips the image writes the caller does not need) or all 255 nodes."""
         spec = self._cost_fcn.fused_spec() if hasattr(self._cost_fcn, "fused_spec") else None
+        sort = bool(self._hp.prune_before_decode if self._hp.sort_lengths is None else self._hp.sort_lengths)
         if not self._hp.prune_before_decode:
-            return dict(planner_mode=dict(kept_only=False, images=True, l2=spec, l2_out=l2_out))
+            return dict(planner_mode=dict(kept_only=False, images=True, l2=spec, l2_out=l2_out, sort_lengths=sort))
         latent_cost = hasattr(self._cost_fcn, "pairs_device")       # learned latent-space cost: reads no image at all
         # CEM iterations of an image-space cost read nothing but the cost: the existence / inverse-model / state heads are
         # left to the final rollout of the elites (which returns actions and states); a latent-space cost needs the pruned
         # latent sequence the heads' path produces
         return dict(planner_mode=dict(kept_only=True, images=images or (spec is None and not latent_cost), l2=spec, l2_out=l2_out,
-                                      heads=images or latent_cost or spec is None))
+                                      heads=images or latent_cost or spec is None, sort_lengths=sort))
 
     def _build_sampler(self):
         return self._hp.sampler(self._hp.sampler_clip_val, self._hp.max_seq_len, self._hp.action_dim, self._hp.initial_std)
