@@ -36,6 +36,9 @@ eng2 = Engine(dev, max_candidates=256, attach_cost_mdl=True)
 eng2.load_weights(synthetic_state_dict(hp, 1))
 o3 = eng2.rollout(big["I_0"][:1].to(dev), big["I_g"][:1].to(dev), big["z"].to(dev), images_shared=True, decode_kept_only=True,
                   want_images=False, l2_goal=goal)
+o4 = eng2.rollout(big["I_0"][:1].to(dev), big["I_g"][:1].to(dev), big["z"].to(dev), images_shared=True, decode_kept_only=True,
+                  want_images=False, want_existence=False, want_aux=False, l2_goal=goal, tree_kept_only=True, sort_sampled_lengths=True)
+assert torch.isfinite(o4["l2_cost"]).all()
 i3, _ = eng2.topk(o3["l2_cost"], 20)
 eng2.refit(o3["z"], i3)
 torch.cuda.synchronize()
