@@ -64,13 +64,51 @@ def workload(cands, config="tree"):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md recipe).  Read in-process through
+    NVML (the library nvidia-smi itself queries), initialised BEFORE the warm-up: spawning `nvidia-smi -lms` next to the
+    timed loop attaches a second client to the GPU, and on a run where its start-up landed inside the K timed steps the
+    launches of one leg stalled (r2y: value 24.5 ms against e2e 14.1 ms for the same step).  The nvidia-smi loop stays as
+    the fall-back when NVML cannot be loaded, and then start() waits for its first row before anything is timed."""
 
-    def __init__(self, index):
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index, period=0.1):
         super().__init__(daemon=True)
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.period = [], None, index, period
+        self._halt = threading.Event()
+        self._first = threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index counts CUDA_VISIBLE_DEVICES entries; NVML counts physical devices: go through the PCI id
+            bus = torch.cuda.get_device_properties(index)
+            bdf = "%08x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            self.nvml = pynvml
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _run_nvml(self):
+        n = self.nvml
+        reasons_fn = n.nvmlDeviceGetCurrentClocksEventReasons
+        while not self._halt.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.handle))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.rows.append([str(sm), str(self.max_mhz), "%.1f" % pw] + ["Active" if mask & b else "Not Active" for b in self.bits])
+            except Exception:  # noqa: BLE001
+                pass
+            self._first.set()
+            self._halt.wait(self.period)
 
     def run(self):
+        if self.nvml is not None:
+            return self._run_nvml()
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -80,19 +118,29 @@ class ClockSampler(threading.Thread):
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
+                self._first.set()
         except Exception:  # noqa: BLE001
             pass
+        self._first.set()
+
+    def start_and_wait(self):
+        """Starts sampling and returns once the first sample is in (at most 5 s), so no client start-up overlaps a timed step."""
+        self.start()
+        self._first.wait(5.0)
 
     def stop(self):
+        self._halt.set()
         if self.proc is not None:
             self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = [n for i, n in enumerate(self.NAMES)
+                   if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
         busy = sorted(sm)[len(sm) // 4:] if sm else []
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -195,6 +243,9 @@ def run_reference(args):
     }))
 
 
+LAST_STEP_MS = []
+
+
 def timed(fn, steps, warmup, world, dev, dist):
     import gc
     for _ in range(warmup):
@@ -211,15 +262,16 @@ def _timed(fn, steps, world, dev, dist):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    LAST_STEP_MS[:] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]    # this rank's steps (diagnostic)
+    ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
@@ -310,12 +362,13 @@ def main():
 
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
+        clocks.start_and_wait()
     l0 = eng.launch_count()
     ms = timed(step_value, args.steps, args.warmup, world, dev, dist)
+    step_ms = list(LAST_STEP_MS)
     launches = (eng.launch_count() - l0) // (args.steps + args.warmup)
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), world, dev, dist)
+    step_ms_e2e = list(LAST_STEP_MS)
     clk = clocks.stop() if rank == 0 else None
 
     extras = {}
@@ -447,7 +500,7 @@ def main():
     phase_ms = {p: round(prof[p] / 2, 3) for p in eng.PHASES}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "step_ms": step_ms, "step_ms_e2e": step_ms_e2e, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload(B), "candidates_total": N, "candidates_per_gpu": B, "rollout_chunk": chunk, "elites": k,
                    "step": "ImageCEMPlanner.cem_iteration (sample -> rollout -> L2 cost -> all-gather -> top-k -> refit)",
@@ -540,12 +593,13 @@ def main_seq(args):
 
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
+        clocks.start_and_wait()
     l0 = eng.launch_count()
     ms = timed(step_value, args.steps, args.warmup, world, dev, dist)
+    step_ms = list(LAST_STEP_MS)
     launches = (eng.launch_count() - l0) // (args.steps + args.warmup)
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3), world, dev, dist)
+    step_ms_e2e = list(LAST_STEP_MS)
     clk = clocks.stop() if rank == 0 else None
     eng.profile_enable(True)
     for _ in range(2):
@@ -562,7 +616,7 @@ def main_seq(args):
     rec_ms = prof["tree_recursion"] / 2
     print(json.dumps({
         "metric": "sequential-GCP CEM rollouts/sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "step_ms": step_ms, "step_ms_e2e": step_ms_e2e, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload(B, "seq"), "candidates_total": N, "elites": k,
                    "l2": "inputs larger than L2 (images written %.1f GB per step)" % (B * 200 * 3072 * 4 / 1e9)},

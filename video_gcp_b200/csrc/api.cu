@@ -88,7 +88,7 @@ struct LevelW {
     Mlp q;                // approximate posterior q(z | e_l, e_r, e_tilde) (training path only; tree/inference.py:16-36)
     Mlp init;             // level 0 only; head rows [0,3072) -> left state, [3072,6144) -> right state
     DevMat init_head_r;   // second half of the init head
-    DevMat proj, embed_main, embed_ctx, lstm[3], out;
+    DevMat proj, embed_main, lstm[3], out;   // the embed layer's context columns: gcpb200_ctx::embed_ctx_all
 };
 
 struct gcpb200_ctx {
@@ -104,6 +104,7 @@ struct gcpb200_ctx {
     std::vector<void*> allocs;
     // weights
     LevelW lvl[8];
+    DevMat embed_ctx_all;   // the context columns of every level's embed layer, stacked: [n_lvl * HID][2 * NZ_ENC]
     SeqW seqw;
     int model = 0, n_slots = 257, lstm_hid = 512;
     // tree shape (gcpb200_config.hierarchy_levels / max_seq_len / tied_layers): 25-room = 8 levels, 255 nodes, 200 frames, one
@@ -737,9 +738,6 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     if (!we || !be) return -1;
     const int EIN = 4 * NZ_ENC + NZ_VAE;   // 768 = [e_l, e_r, z, e_0, e_g]
     CHECK(upload_mat(c, &L.embed_main, HID, 2 * NZ_ENC + NZ_VAE, [&](int n, int k) { return we->data[(size_t)n * EIN + k]; }, nullptr));
-    CHECK(upload_mat(c, &L.embed_ctx, HID, 2 * NZ_ENC,
-                     [&](int n, int k) { return we->data[(size_t)n * EIN + 2 * NZ_ENC + NZ_VAE + k]; },
-                     [&](int n) { return be->data[n]; }));
     for (int i = 0; i < N_LSTM; ++i) CHECK(pack_lstm_cell(c, ws, sp + "lstm." + std::to_string(i) + ".", HID, &L.lstm[i]));
     const gcpb200_tensor* wo = ws.get(sp + "output.weight", 2);
     const gcpb200_tensor* bo = ws.get(sp + "output.bias", 1);
@@ -747,6 +745,23 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     CHECK(upload_mat(c, &L.out, NZ_ENC, HID, [&](int n, int k) { return wo->data[(size_t)n * HID + k]; },
                      [&](int n) { return bo->data[n]; }));
     return 0;
+}
+
+// The context term of every level's embed layer, W_e[:, 512:768] [e_0, e_g] + b_e, depends on the start / goal encodings
+// only: the weights of all levels are stacked so that ONE GEMM per rollout produces the per-candidate row bias of every level.
+static int pack_embed_context(gcpb200_ctx* c, const WStore& ws) {
+    const int n_lvl = c->tied ? 1 : c->depth;
+    const int EIN = 4 * NZ_ENC + NZ_VAE;
+    std::vector<const gcpb200_tensor*> we(n_lvl), be(n_lvl);
+    for (int l = 0; l < n_lvl; ++l) {
+        const std::string sp = (c->tied ? std::string("tree_module.") : "tree_module.tree_modules." + std::to_string(l) + ".") + "subgoal_pred.";
+        we[l] = ws.get(sp + "embed.weight", 2);
+        be[l] = ws.get(sp + "embed.bias", 1);
+        if (!we[l] || !be[l]) return -1;
+    }
+    return upload_mat(c, &c->embed_ctx_all, n_lvl * HID, 2 * NZ_ENC,
+                      [&](int n, int k) { return we[n / HID]->data[(size_t)(n % HID) * EIN + 2 * NZ_ENC + NZ_VAE + k]; },
+                      [&](int n) { return be[n / HID]->data[n % HID]; });
 }
 
 // Training-only tensors: BatchNorm affine terms (batch statistics are computed on the fly), the conv-1d inference
@@ -1084,7 +1099,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? c->n_nodes : c->max_len + 1) * Bp + 256);
     rc |= make_buf(c, &c->pairs, (size_t)c->pair_rows, 256);
     rc |= make_buf(c, &c->seqb, (size_t)(c->max_len + 1) * Bp + 256, NZ_ENC);
-    rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
+    rc |= dalloc(c, &c->ctxb, Bp * (size_t)std::max(c->lstm_hid, (c->tied ? 1 : c->depth) * HID));
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
     rc |= dalloc(c, &c->s2, Bp * 1024);
@@ -1221,6 +1236,7 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
         CHECK(pack_sequential(c, ws));
     } else {
         for (int l = 0; l < (c->tied ? 1 : c->depth); ++l) CHECK(pack_level(c, ws, l));
+        CHECK(pack_embed_context(c, ws));
         if (c->model == GCPB200_MODEL_TREE_ADAPTIVE)
             CHECK(pack_mlp(c, ws, std::string(c->tied ? "tree_module." : "tree_module.tree_modules.0.") + "binding.distance_predictor", true, 2 * NZ_ENC, NZ_MID, 1, 128,
                            nullptr, &c->distance_pred));
@@ -1292,8 +1308,26 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
     const LevelGeom flat = {Bp, 0, c->depth};
     // ---- 1. encoder on start / goal images -> latent slots 0 and 256 (+ decoder skips of I_0)
     const int n_img = io->images_shared ? 1 : B;
-    encoder_kernel<<<dim3(n_img, 2), ENC_THREADS, 0, st>>>(io->I_0, io->I_g, c->enc, c->lat_f32, c->lat.p, 0, goal_row0, c->s0, c->s2,
-                                                            c->s2b.p);
+    if (io->images_shared) {
+        // one start / goal pair: a cluster of 8 CTAs per image instead of one CTA (same work items, same bits)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * ENCC_CTAS);
+        cfg.blockDim = dim3(ENCC_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ENCC_CTAS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GCP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, encoder_cluster_kernel, (const float*)io->I_0, (const float*)io->I_g, c->enc,
+                                          c->lat_f32, c->lat.p, 0, goal_row0, c->s0, c->s2, c->s2b.p));
+    } else {
+        encoder_kernel<<<dim3(n_img, 2), ENC_THREADS, 0, st>>>(io->I_0, io->I_g, c->enc, c->lat_f32, c->lat.p, 0, goal_row0, c->s0,
+                                                                c->s2, c->s2b.p);
+    }
     LAUNCH_CHECK();
     if (io->images_shared) {
         broadcast_rows_kernel<<<(Bp * NZ_ENC + 255) / 256, 256, 0, st>>>(c->lat_f32, c->lat.p, 0, Bp, NZ_ENC);
@@ -1319,7 +1353,7 @@ static int run_encoder_length(gcpb200_ctx* c, cudaStream_t st, const CommonIO& i
     if (io->end_ind) {
         GCP_CUDA_CHECK(cudaMemcpyAsync(c->end_ind, io->end_ind, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     } else {
-        sample_length_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->logits, 256, c->max_len, B, io->seed, c->end_ind);
+        sample_length_kernel<<<(B + 7) / 8, 256, 0, st>>>(c->logits, 256, c->max_len, B, io->seed, c->end_ind);
         LAUNCH_CHECK();
         if (io->sort_lengths && io->images_shared) {
             sort_lengths_desc_kernel<<<1, 1024, 0, st>>>(c->end_ind, B);
@@ -1543,11 +1577,18 @@ struct PosteriorArgs {
 
 // One level of SubgoalTreeLayer.produce_tree (gcp/prediction/utils/tree_utils.py:21-44) = TreeModule.produce_subgoal on all
 // B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
-static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
-                      const PosteriorArgs* post, float* e_df = nullptr, bool pruned = false) {
+// Context term of the embed layer of every level, one row per candidate (see pack_embed_context); once per rollout.
+static int tree_context(gcpb200_ctx* c, cudaStream_t st, int Bp) {
     const LevelGeom flat = {Bp, 0, c->depth};
     const int goal_row0 = (c->n_nodes + 1) * Bp;
-    const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
+    const int n = (c->tied ? 1 : c->depth) * HID;
+    return gemm(c, st, Bp, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)},
+                c->embed_ctx_all, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, n, n));
+}
+
+static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
+                      const PosteriorArgs* post, float* e_df = nullptr, bool pruned = false) {
+    const int goal_row0 = (c->n_nodes + 1) * Bp;
     {
         const LevelW& L = c->lvl[c->tied ? 0 : l];
         // planner mode: only the (node, candidate tile) pairs of this level's work list; the launches are shaped for the whole
@@ -1556,8 +1597,6 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         const GemmDyn dynv = {c->tree_rows + l, 0};
         const GemmDyn* dyn = pruned ? &dynv : nullptr;
         const int rows = Bp << l;
-        // context term of the embed layer: W_e[:, 512:768] [e_0, e_g] + b_e, one row per candidate
-        CHECK(gemm(c, st, Bp, flat, ctx_in, L.embed_ctx, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, HID, HID)));
         // prior p(z | e_l, e_r) and reparametrisation
         const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
         CHECK(mlp_body(c, st, L.prior, rows, g, par, dyn));
@@ -1608,8 +1647,8 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         // embed
         {
             EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
-            e.rowbias = c->ctxb;
-            e.rowbias_ld = HID;
+            e.rowbias = c->ctxb + (c->tied ? 0 : l) * HID;      // this level's columns of tree_context()
+            e.rowbias_ld = (c->tied ? 1 : c->depth) * HID;
             CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e, 0, -1, dyn));
         }
         // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
@@ -1770,6 +1809,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             gcp_set_error("mu_df and log_sigma_df must be given together");
             return -1;
         }
+        if (l == 0) CHECK(tree_context(c, st, Bp));
         if (tree_pruned && l == 0) {
             // the rollout length is known (sampled / injected in run_encoder_length): work lists of every level
             tree_worklists_kernel<<<c->depth, 1024, 0, st>>>(c->end_ind, B, Bp, 1, c->tree_tiles, c->tree_rows);
@@ -2002,6 +2042,7 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
     float* q_ls = io->q_log_sigma ? io->q_log_sigma : w.pq[3];
     {
         PosteriorArgs post = {w.inf_seq, w.tstep, q_mu, q_ls};
+        CHECK(tree_context(c, st, Bp));
         for (int l = 0; l < DEPTH; ++l) CHECK(tree_level(c, st, l, B, Bp, io->eps, p_mu, p_ls, &post));
     }
     float* e_df = io->e_df ? io->e_df : c->e_df;

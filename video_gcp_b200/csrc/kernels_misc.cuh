@@ -33,14 +33,20 @@ struct EncoderWeights {
     const float* b3;   // [128]
 };
 
-template <int CI, int CO, int HIN>
-__device__ __forceinline__ void enc_conv_s2(const float* in, float* out, const float* w, const float* sc,
-                                            const float* sh, const float* bias, int tid, int nthreads) {
-    constexpr int HO = HIN / 2;
-    for (int o = tid; o < CO * HO * HO; o += nthreads) {
+// One strided convolution layer (k4 s2 p1) as work items (output element, part): `P` consecutive lanes share one output, each
+// sums CI / P input channels in (ci, ky, kx) order, an xor-shuffle tree adds the parts, part 0 applies bias / folded BN /
+// LeakyReLU and hands the value to `store(o, v)`.  The arithmetic of an output element depends on nothing but the layer and
+// P, so any distribution of the items over threads / CTAs gives the same bits (the per-image kernel and the cluster kernel
+// below share this function).  [item0, item1) must be a multiple of 32 long and `nthreads` a multiple of 32.
+template <int CI, int CO, int HIN, int P, class Store>
+__device__ __forceinline__ void enc_conv_items(const float* in, const float* w, const float* sc, const float* sh,
+                                               const float* bias, int item0, int item1, int tid, int nthreads, Store store) {
+    constexpr int HO = HIN / 2, CPP = CI / P;
+    for (int it = item0 + tid; it < item1; it += nthreads) {
+        const int o = it / P, part = it % P;
         const int co = o / (HO * HO), oy = (o / HO) % HO, ox = o % HO;
         float s = 0.f;
-        for (int ci = 0; ci < CI; ++ci) {
+        for (int ci = part * CPP; ci < (part + 1) * CPP; ++ci) {
             const float* wp = w + ((size_t)co * CI + ci) * 16;
             const float* ip = in + ci * HIN * HIN;
 #pragma unroll
@@ -55,9 +61,29 @@ __device__ __forceinline__ void enc_conv_s2(const float* in, float* out, const f
                 }
             }
         }
-        if (bias != nullptr) s += __ldg(bias + co);
-        if (sc != nullptr) s = s * __ldg(sc + co) + __ldg(sh + co);
-        out[o] = lrelu_(s);
+#pragma unroll
+        for (int d = P / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (part == 0) {
+            if (bias != nullptr) s += __ldg(bias + co);
+            if (sc != nullptr) s = s * __ldg(sc + co) + __ldg(sh + co);
+            store(o, lrelu_(s));
+        }
+    }
+}
+// head: conv k4 valid on the 4x4 map = 1024 -> 128 linear; 8 lanes per output (128 inputs each), fixed summation order
+template <class Store>
+__device__ __forceinline__ void enc_head_items(const float* a3, const float* w3, const float* b3, int item0, int item1, int tid,
+                                               int nthreads, Store store) {
+    for (int it = item0 + tid; it < item1; it += nthreads) {
+        const int o = it >> 3, part = it & 7;
+        const float* wp = w3 + (size_t)o * 1024 + part * 128;
+        const float* ap = a3 + part * 128;
+        float s = 0.f;
+        for (int k = 0; k < 128; ++k) s = fmaf(ap[k], __ldg(wp + k), s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (part == 0) store(o, s + __ldg(b3 + o));
     }
 }
 
@@ -77,11 +103,11 @@ __global__ void __launch_bounds__(ENC_THREADS) encoder_kernel(const float* __res
     const float* img = goal ? img_b : img_a;
     for (int k = tid; k < 3072; k += ENC_THREADS) a0[k] = img[(size_t)i * 3072 + k];
     __syncthreads();
-    enc_conv_s2<3, 16, 32>(a0, a1, W.w0, nullptr, nullptr, W.b0, tid, ENC_THREADS);
+    enc_conv_items<3, 16, 32, 1>(a0, W.w0, nullptr, nullptr, W.b0, 0, 4096, tid, ENC_THREADS, [&](int o, float v) { a1[o] = v; });
     __syncthreads();
-    enc_conv_s2<16, 32, 16>(a1, a2, W.w1, W.sc1, W.sh1, nullptr, tid, ENC_THREADS);
+    enc_conv_items<16, 32, 16, 4>(a1, W.w1, W.sc1, W.sh1, nullptr, 0, 4 * 2048, tid, ENC_THREADS, [&](int o, float v) { a2[o] = v; });
     __syncthreads();
-    enc_conv_s2<32, 64, 8>(a2, a3, W.w2, W.sc2, W.sh2, nullptr, tid, ENC_THREADS);
+    enc_conv_items<32, 64, 8, 4>(a2, W.w2, W.sc2, W.sh2, nullptr, 0, 4 * 1024, tid, ENC_THREADS, [&](int o, float v) { a3[o] = v; });
     __syncthreads();
     if (!goal && skip0 != nullptr) {
         for (int k = tid; k < 4096; k += ENC_THREADS) skip0[(size_t)i * 4096 + k] = a1[k];
@@ -90,22 +116,60 @@ __global__ void __launch_bounds__(ENC_THREADS) encoder_kernel(const float* __res
             skip2_bf16[(size_t)i * 1024 + k] = __float2bfloat16_rn(a3[k]);
         }
     }
-    {   // head: conv k4 valid on the 4x4 map = 1024 -> 128 linear; 8 threads per output, fixed summation order
-        const int o = tid >> 3, part = tid & 7;
-        const float* wp = W.w3 + (size_t)o * 1024 + part * 128;
-        const float* ap = a3 + part * 128;
-        float s = 0.f;
-        for (int k = 0; k < 128; ++k) s = fmaf(ap[k], __ldg(wp + k), s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (part == 0) {
-            s += __ldg(W.b3 + o);
-            const size_t r = (size_t)(goal ? row0_b : row0_a) + i;
-            lat_f32[r * 128 + o] = s;
-            lat_bf16[r * 128 + o] = __float2bfloat16_rn(s);
+    const size_t r = (size_t)(goal ? row0_b : row0_a) + i;
+    enc_head_items(a3, W.w3, W.b3, 0, 1024, tid, ENC_THREADS, [&](int o, float v) {
+        lat_f32[r * 128 + o] = v;
+        lat_bf16[r * 128 + o] = __float2bfloat16_rn(v);
+    });
+}
+
+// The same encoder for ONE start / goal pair (a CEM call: every candidate shares them), where the per-image kernel above is
+// two CTAs and 170 us of pure latency at the head of every rollout: a cluster of 8 CTAs per image takes an eighth of every
+// layer's work items and broadcasts its outputs into the activation arrays of all 8 CTAs through distributed shared memory
+// (st.shared::cluster), one cluster barrier per layer.  Same work items, same bits.  grid = 16 (2 clusters of 8).
+constexpr int ENCC_CTAS = 8, ENCC_THREADS = 512;
+__device__ __forceinline__ void st_cluster_all(float* local, float v) {
+    const uint32_t a = smem_u32(local);
+#pragma unroll
+    for (uint32_t r = 0; r < ENCC_CTAS; ++r) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_shared(a, r)), "f"(v) : "memory");
+}
+__global__ void __launch_bounds__(ENCC_THREADS) encoder_cluster_kernel(const float* __restrict__ img_a, const float* __restrict__ img_b,
+                                                                       EncoderWeights W, float* lat_f32, bf16* lat_bf16, int row0_a,
+                                                                       int row0_b, float* skip0, float* skip2, bf16* skip2_bf16) {
+    __shared__ float a0[3 * 32 * 32];
+    __shared__ float a1[16 * 16 * 16];
+    __shared__ float a2[32 * 8 * 8];
+    __shared__ float a3[64 * 4 * 4];
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const bool goal = blockIdx.x >= ENCC_CTAS;
+    const float* img = goal ? img_b : img_a;
+    for (int k = tid; k < 3072; k += ENCC_THREADS) a0[k] = img[k];
+    __syncthreads();
+    cluster_sync_all();          // every CTA of the cluster is running before anyone writes into its shared memory
+    const bool keep = !goal && skip0 != nullptr;
+    enc_conv_items<3, 16, 32, 1>(a0, W.w0, nullptr, nullptr, W.b0, rank * 512, (rank + 1) * 512, tid, ENCC_THREADS, [&](int o, float v) {
+        st_cluster_all(&a1[o], v);
+        if (keep) skip0[o] = v;
+    });
+    cluster_sync_all();
+    enc_conv_items<16, 32, 16, 4>(a1, W.w1, W.sc1, W.sh1, nullptr, rank * 1024, (rank + 1) * 1024, tid, ENCC_THREADS,
+                                  [&](int o, float v) { st_cluster_all(&a2[o], v); });
+    cluster_sync_all();
+    enc_conv_items<32, 64, 8, 4>(a2, W.w2, W.sc2, W.sh2, nullptr, rank * 512, (rank + 1) * 512, tid, ENCC_THREADS, [&](int o, float v) {
+        st_cluster_all(&a3[o], v);
+        if (keep) {
+            skip2[o] = v;
+            skip2_bf16[o] = __float2bfloat16_rn(v);
         }
-    }
+    });
+    cluster_sync_all();
+    const size_t r = (size_t)(goal ? row0_b : row0_a);
+    enc_head_items(a3, W.w3, W.b3, rank * 128, (rank + 1) * 128, tid, ENCC_THREADS, [&](int o, float v) {
+        lat_f32[r * 128 + o] = v;
+        lat_bf16[r * 128 + o] = __float2bfloat16_rn(v);
+    });
+    cluster_sync_all();          // no CTA exits while a peer may still store into it
 }
 
 // broadcast row 0 of a slot to all candidates (CEM: every candidate shares the start / goal image)
@@ -127,17 +191,24 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 }
 __global__ void sample_length_kernel(const float* __restrict__ logits, int ld, int n_len, int n_cand,
                                      unsigned long long seed, long long* end_ind) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per candidate: lanes stride over the lengths, then a warp arg-max (first maximum wins, as np.argmax)
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= n_cand) return;
     float best = -INFINITY;
     int arg = 0;
-    for (int k = 0; k < n_len; ++k) {
+    for (int k = lane; k < n_len; k += 32) {
         const uint32_t h = mix32(mix32((uint32_t)seed ^ (uint32_t)(seed >> 32)) + 0x9E3779B9u * (uint32_t)(c * n_len + k + 1));
         const float u = ((h >> 8) + 0.5f) * (1.0f / 16777216.0f);
         const float v = logits[(size_t)c * ld + k] - __logf(-__logf(u));
         if (v > best) { best = v; arg = k; }
     }
-    end_ind[c] = arg < 2 ? 2 : arg;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) end_ind[c] = arg < 2 ? 2 : arg;
 }
 
 // Sampled rollout lengths of one CEM call, reassigned in descending order (counting sort of values in [0, 256); one CTA).
