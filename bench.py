@@ -403,6 +403,15 @@ def main():
         plp = make_planner(pruned=True)
         plp._sampler.init()
         ms_p = timed(lambda: plp.cem_iteration(state_t, goal_t), args.steps, args.warmup, world, dev, dist)
+        pruned_phase = None
+        if B == chunk:
+            eng.profile_enable(True)
+            for _ in range(2):
+                plp.cem_iteration(state_t, goal_t)
+            torch.cuda.synchronize()
+            pp = eng.profile_read()
+            eng.profile_enable(False)
+            pruned_phase = {ph: round(pp[ph] / 2, 3) for ph in eng.PHASES}
         # same candidates, same rollout seeds -> the two modes must agree bit for bit (checked outside the timed region)
         # (the full-decode side also takes the sampled lengths in descending order, so both see the same lengths)
         pa, pb = make_planner(seed=31, sort_lengths=True), make_planner(seed=31, pruned=True)
@@ -421,7 +430,7 @@ def main():
         executed = None if kept is None else NODE_FLOP * kept
         extras["value_pruned"] = {
             "value": N * args.steps / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p / args.steps,
-            "speedup_vs_value": ms / ms_p, "kept_nodes_mean": kept, "executed_flop_per_rollout": executed,
+            "speedup_vs_value": ms / ms_p, "phase_ms_per_step": pruned_phase, "kept_nodes_mean": kept, "executed_flop_per_rollout": executed,
             "same_costs_elites_refit_as_full_decode": same,
             "note": "ImageCEMPlanner(prune_before_decode=True).cem_iteration: only the end_ind+1 nodes balanced pruning keeps "
                     "are decoded AND computed by the tree recursion (sampled lengths handed out in descending order so that "
@@ -440,19 +449,21 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            n_plans = 3
+            n_plans, plan_ms = 3, []
             for _ in range(n_plans):
-                frames, actions, latents, score = plan()
+                t1 = time.perf_counter()
+                frames, actions, latents, score = plan()      # returns host arrays: the call itself synchronises
+                plan_ms.append(round((time.perf_counter() - t1) * 1e3, 3))
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dt = float(dt.item()) / n_plans
             extras["e2e_planner"] = {
-                "ms_per_plan": dt * 1e3, "n_iters": args.planner_iters, "rollouts_per_plan": args.planner_iters * N + k,
+                "ms_per_plan": dt * 1e3, "plan_ms": plan_ms, "n_iters": args.planner_iters, "rollouts_per_plan": args.planner_iters * N + k,
                 "value": (args.planner_iters * N + k) / dt, "unit": UNIT,
                 "note": "ImageCEMPlanner.__call__(state, goal): %d CEM iterations over %d candidates, final rollout of the %d "
-                        "elites, elite rollouts + plan copied to the host (host wall clock, synchronised)" % (args.planner_iters, N, k)}
+                        "elites, the plan (best rollout: frames, actions, latents) and the elite scores copied to the host (host wall clock, synchronised)" % (args.planner_iters, N, k)}
 
     # ---- N > 1: every rank must hold the same elites / distribution, and rank 0 must reproduce any rank's costs
     rank_consistent = None

@@ -45,6 +45,13 @@ def wall(fn, n=6):
     return "host %.2f ms, host+gpu %.2f ms" % (np.median([a for a, _ in ts]), np.median([b for _, b in ts]))
 
 
+if os.environ.get("PROBE_NCU") == "1":       # three planner-mode iterations and out: the launch list for ncu
+    p = planner(True)
+    for _ in range(3):
+        p.cem_iteration(state, goal)
+    torch.cuda.synchronize()
+    sys.exit(0)
+
 for pruned in (False, True):
     p = planner(pruned)
     print("pruned", pruned, "cem_iteration:", wall(lambda: p.cem_iteration(state, goal)))

@@ -77,6 +77,18 @@ def test_frame_nodes_match_golden(golden_dir):
         assert (g["timesteps"][e][nodes] == np.arange(e + 1)).all()
 
 
+def test_kept_nodes_grow_with_rollout_length():
+    """tree_worklists_kernel lists a (node, 128-candidate tile) pair iff the tile's LONGEST candidate keeps the node: valid
+    because balanced pruning keeps, at length L + 1, every node it keeps at length L (every supported depth and length)."""
+    from oracle.gcp_oracle import balanced_keep_mask
+    for depth in range(2, 9):
+        prev = np.zeros(2 ** depth - 1, dtype=bool)
+        for end in range(0, 256):
+            keep, _ = balanced_keep_mask(end, depth)
+            assert not (prev & ~keep).any(), (depth, end)
+            prev = keep
+
+
 # ---- the flat CEM planner's sharded loop (cem_planner.py:55-96 here video_gcp_b200/planning/cem_planner.py) on the CPU: the
 # planner only talks to its engine / simulator / cost function through a handful of calls, so a host stand-in with the
 # same counter-based noise contract exercises the REAL CEMPlanner.cem_iteration -- shard ranges, the cost all-gather

@@ -152,6 +152,10 @@ struct gcpb200_ctx {
     // overlapped upload of host noise (gcpb200_rollout_io.z_host)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_start = nullptr, ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // side stream of the tree rollout: what depends on the encoder / rollout length only (frame map, kept-row offsets, the
+    // decoder's per-call constants) runs beside the tree recursion instead of between it and the decoder
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t ev_prep_fork = nullptr, ev_prep_join = nullptr;
     // ---- training-phase forward + loss (gcpb200_forward_loss)
     bool has_train = false;
     DevMat dec1t, dec2xt, dec2st, dec3t;          // decoder layers 1-3 without BatchNorm folding
@@ -1135,6 +1139,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         cudaError_t ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_copy_start, cudaEventDisableTiming);
         for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_prep_fork, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_prep_join, cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->seq_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_fork, cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_join, cudaEventDisableTiming);
@@ -1176,6 +1183,9 @@ extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
     if (!c) return;
     for (auto& g : c->seq_graphs) cudaGraphExecDestroy(g.exec);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
+    if (c->ev_prep_fork) cudaEventDestroy(c->ev_prep_fork);
+    if (c->ev_prep_join) cudaEventDestroy(c->ev_prep_join);
     if (c->seq_stream) cudaStreamDestroy(c->seq_stream);
     if (c->ev_seq_fork) cudaEventDestroy(c->ev_seq_fork);
     if (c->ev_seq_join) cudaEventDestroy(c->ev_seq_join);
@@ -1474,18 +1484,15 @@ static int run_decoder(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B
 // GCPImageSimulator.rollout hands to the cost, cem_simulator.py:29-61).  The kept (candidate, frame) pairs are compacted
 // into consecutive latent rows (candidate-major); the number of rows is known to the device only, so the GEMMs and the tail
 // kernel are launched for the capacity of a chunk and read the live row count from c->n_rows.  Needs c->frame_node
-// (compute_frame_map) and the finished tree.
+// (compute_frame_map), c->row_off / c->n_rows (kept_offsets_kernel), decoder_prepare and the finished tree.
 static int decoder_kept(gcpb200_ctx* c, cudaStream_t st, int images_shared, int B, int Bp, float* images, const float* l2_goal) {
     const LevelGeom flat = {Bp, 0, c->depth};
-    kept_offsets_kernel<<<1, 1024, 0, st>>>(c->end_ind, B, 1, c->row_off, c->n_rows);
-    LAUNCH_CHECK();
     {
         const size_t n = (size_t)B * c->max_len * 16;
         gather_kept_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->lat.p, c->frame_node, c->end_ind, c->row_off, B, Bp,
                                                                            c->max_len, 1, c->latc.p, c->row_cand, c->row_node);
         LAUNCH_CHECK();
     }
-    CHECK(decoder_prepare(c, st, images_shared, B, Bp));
     const int chunk_rows = c->slot_chunk * Bp;
     const int cap = c->max_len * B;                 // at most 200 kept frames per candidate
     for (int r0 = 0; r0 < cap; r0 += chunk_rows) {
@@ -1715,6 +1722,10 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
         gcp_set_error("tree_kept_only needs decode_kept_only and no existence output (pruned-away nodes are not computed)");
         return -1;
     }
+    if (io->tree_kept_only && ((io->B + 127) >> 7) > TREE_TPN_MAX) {
+        gcp_set_error("tree_kept_only: at most %d candidates per call", TREE_TPN_MAX * 128);
+        return -1;
+    }
     const bool tree_pruned = io->tree_kept_only != 0 && !adaptive && !c->use_ref;
     const bool decode_all = !kept_only && (io->images_df != nullptr || fused_l2);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1780,6 +1791,27 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     const std::vector<Seg> ctx_in = {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)};
 
     delete scope;
+    // ---- 2b. beside the tree recursion: everything that needs only the encoder skips and the rollout length
+    const bool need_map = kept_only || fused_l2 || io->model_enc_seq || io->actions || io->regressed_state;
+    const bool decodes = kept_only || decode_all;
+    bool prep_pending = need_map || decodes;
+    if (prep_pending) {
+        cudaStream_t ps = c->prep_stream;
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_prep_fork, st));
+        GCP_CUDA_CHECK(cudaStreamWaitEvent(ps, c->ev_prep_fork, 0));
+        if (need_map) CHECK(compute_frame_map(c, c->end_ind, B, ps));
+        if (kept_only) {
+            kept_offsets_kernel<<<1, 1024, 0, ps>>>(c->end_ind, B, 1, c->row_off, c->n_rows);
+            LAUNCH_CHECK();
+        }
+        if (decodes) CHECK(decoder_prepare(c, ps, io->images_shared, B, Bp));
+        GCP_CUDA_CHECK(cudaEventRecord(c->ev_prep_join, ps));
+    }
+    auto prep_join = [&]() -> int {
+        if (prep_pending) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_prep_join, 0));
+        prep_pending = false;
+        return 0;
+    };
     scope = new ProfScope(c, st, 1);
     // ---- 3. tree recursion, level by level (SubgoalTreeLayer.produce_tree)
     // Level-ordered decoding: a node can be decoded as soon as its level is done, so the decoder runs in three parts --
@@ -1795,7 +1827,7 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             delete scope;
             scope = nullptr;
             if (l == c->depth - 2) {
-                CHECK(decoder_prepare(c, st, io->images_shared, B, Bp));
+                CHECK(prep_join());
                 CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 4, 4, (1 << (c->depth - 2)) - 1, io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
             } else {
                 CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 2, 4, 1 << (c->depth - 2), io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
@@ -1835,14 +1867,13 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
     delete scope;
     scope = nullptr;
     // ---- 5. decoder over all 255 node latents
-    const bool need_map = kept_only || fused_l2 || io->model_enc_seq || io->actions || io->regressed_state;
-    if (need_map) CHECK(compute_frame_map(c, c->end_ind, B, st));
+    CHECK(prep_join());
     if (level_ordered)      // level 7 = the odd slots
         CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 2, c->n_nodes / 2 + 1, io->images_df, c->n_nodes, io->I_0, io->I_g, l2_goal));
     else if (kept_only)
         CHECK(decoder_kept(c, st, io->images_shared, B, Bp, io->images_df, l2_goal));
-    else if (io->images_df)
-        CHECK(run_decoder(c, st, io->images_shared, B, Bp, c->n_nodes, io->images_df, c->n_nodes, io->I_0, io->I_g));
+    else if (io->images_df)    // (decoder_prepare ran on the side stream)
+        CHECK(decoder_slots(c, st, io->images_shared, B, Bp, 1, 1, c->n_nodes, io->images_df, c->n_nodes, io->I_0, io->I_g));
     if (fused_l2) {
         cost_from_frames_kernel<<<B, 32, 0, st>>>(c->frame_sq, kept_only ? nullptr : c->frame_node, c->row_off, c->end_ind, c->n_nodes,
                                                   c->max_len, io->l2_dense, io->l2_final_step_weight, 1, io->l2_cost);
@@ -2559,8 +2590,7 @@ extern "C" int gcpb200_sample_noise(gcpb200_ctx* c, const float* mean, const flo
         return -1;
     }
     const int per = c->n_nodes * NZ_VAE;
-    const size_t n = (size_t)B * (per / 4);
-    sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    sample_noise_kernel<<<dim3(B, (per / 4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mean, stdv, std_scalar, seed, first_candidate_id, nullptr, B, per, clip, z);
     LAUNCH_CHECK();
     return 0;
@@ -2573,8 +2603,7 @@ extern "C" int gcpb200_sample_noise_ids(gcpb200_ctx* c, const float* mean, const
         return -1;
     }
     const int per = c->n_nodes * NZ_VAE;
-    const size_t n = (size_t)B * (per / 4);
-    sample_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    sample_noise_kernel<<<dim3(B, (per / 4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mean, stdv, std_scalar, seed, 0ULL, ids, B, per, clip, z);
     LAUNCH_CHECK();
     return 0;

@@ -447,9 +447,11 @@ __global__ void cost_from_frames_kernel(const float* __restrict__ frame_sq, cons
 // Planner mode, tree side: which (node, 128-candidate tile) pairs of every tree level some candidate keeps.  A node is
 // kept iff its interval in the balanced-pruning recursion still has an interior point (frame_binding.py:42-65) -- the same
 // integer recursion as prune_map_kernel -- and a kept node's ancestors and interval ends are kept, so a level only
-// needs the listed tiles and every operand it reads was computed.  One CTA per level: a thread decides a tile by
-// scanning its 128 candidates, an ordered ballot / prefix compaction writes the list (ascending tile index; padded to
-// an even count with a copy of the last entry, for the CTA-pair GEMMs); rows[l] = listed tiles * 128.
+// needs the listed tiles and every operand it reads was computed.  "Kept" is monotone in the rollout length (a node kept
+// at length L is kept at every longer one: tests/test_host_logic.py checks it exhaustively for depth <= 8), so a tile
+// needs a node iff its LONGEST candidate keeps it.  One CTA per level: the warps reduce the tiles' maximum lengths into
+// shared memory, a thread decides one (node, tile) pair, an ordered ballot / prefix compaction writes the list (ascending
+// tile index; padded to an even count with a copy of the last entry, for the CTA-pair GEMMs); rows[l] = listed tiles * 128.
 // tiles: [depth] lists at offsets off(l) = (2^l - 1) * tpn + 2 * l.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool node_kept(int end, int level, int j) {
@@ -462,6 +464,7 @@ __device__ __forceinline__ bool node_kept(int end, int level, int j) {
     }
     return t != l && t != r;
 }
+constexpr int TREE_TPN_MAX = 512;      // 128-candidate tiles per call the work lists are built for (65 536 candidates)
 __host__ __device__ __forceinline__ int tree_tiles_offset(int level, int tpn) { return ((1 << level) - 1) * tpn + 2 * level; }
 
 __global__ void __launch_bounds__(1024) tree_worklists_kernel(const long long* __restrict__ end_ind, int n_cand, int Bp,
@@ -472,14 +475,22 @@ __global__ void __launch_bounds__(1024) tree_worklists_kernel(const long long* _
     const int n_tiles = tpn << level;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* list = tiles + tree_tiles_offset(level, tpn);
+    __shared__ int tmax[TREE_TPN_MAX];      // longest rollout of each 128-candidate tile (-1: no candidate)
     if (tid == 0) s_base = 0;
+    for (int t = warp; t < tpn; t += 32) {
+        int m = -1;
+        for (int c = (t << 7) + lane; c < min((t + 1) << 7, n_cand); c += 32) m = max(m, max((int)end_ind[c], min_last));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) tmax[t] = m;
+    }
     __syncthreads();
     for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
         const int tile = t0 + tid;
         bool act = false;
         if (tile < n_tiles) {
-            const int j = tile / tpn, c0 = (tile - j * tpn) << 7;
-            for (int c = c0; c < min(c0 + 128, n_cand) && !act; ++c) act = node_kept(max((int)end_ind[c], min_last), level, j);
+            const int j = tile / tpn, m = tmax[tile - j * tpn];
+            act = m >= 0 && node_kept(m, level, j);
         }
         const unsigned b = __ballot_sync(0xffffffffu, act);
         if (lane == 0) wsum[warp] = __popc(b);
@@ -721,10 +732,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 __global__ void sample_noise_kernel(const float* __restrict__ mean, const float* __restrict__ stdv, float std_scalar,
                                     unsigned long long seed, unsigned long long cand0, const int* __restrict__ ids,
                                     int n_cand, int per_cand, float clip, float* __restrict__ z) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread = 4 outputs
+    // grid = (candidate, blocks of per_cand / 4): one thread = 4 outputs, no division
     const int per4 = per_cand >> 2;
-    if (idx >= (size_t)n_cand * per4) return;
-    const int c = idx / per4, e4 = idx - (size_t)c * per4;
+    const int c = blockIdx.x, e4 = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e4 >= per4) return;
+    const size_t idx = (size_t)c * per4 + e4;
     const unsigned long long gid = ids != nullptr ? (unsigned long long)ids[c] : cand0 + c;
     uint32_t ctr[4] = {(uint32_t)e4, 0u, (uint32_t)gid, (uint32_t)(gid >> 32)};
     philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -739,15 +751,15 @@ __global__ void sample_noise_kernel(const float* __restrict__ mean, const float*
         n[2 * h] = r * cs;
         n[2 * h + 1] = r * sn;
     }
+    const float4 m4 = mean != nullptr ? __ldg(reinterpret_cast<const float4*>(mean) + e4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 s4 = stdv != nullptr ? __ldg(reinterpret_cast<const float4*>(stdv) + e4)
+                                      : make_float4(std_scalar, std_scalar, std_scalar, std_scalar);
+    const float* mp = reinterpret_cast<const float*>(&m4);
+    const float* sp = reinterpret_cast<const float*>(&s4);
     float4 o;
     float* op = reinterpret_cast<float*>(&o);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int e = e4 * 4 + q;
-        const float m = mean != nullptr ? __ldg(mean + e) : 0.f;
-        const float s = stdv != nullptr ? __ldg(stdv + e) : std_scalar;
-        op[q] = fminf(fmaxf(m + s * n[q], -clip), clip);
-    }
+    for (int q = 0; q < 4; ++q) op[q] = fminf(fmaxf(mp[q] + sp[q] * n[q], -clip), clip);
     reinterpret_cast<float4*>(z)[idx] = o;
 }
 
@@ -868,11 +880,6 @@ __global__ void len_to_end_kernel(const int* __restrict__ len, long long* __rest
 __global__ void fill_i64_kernel(long long* p, long long v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
