@@ -156,6 +156,10 @@ struct gcpb200_ctx {
     // decoder's per-call constants) runs beside the tree recursion instead of between it and the decoder
     cudaStream_t prep_stream = nullptr;
     cudaEvent_t ev_prep_fork = nullptr, ev_prep_join = nullptr;
+    // second side stream: the parent-state projection GEMM of a tree level that does not fill the GPU runs beside that
+    // level's prior -> reparametrisation -> embed chain (it needs the previous level's LSTM state only)
+    cudaStream_t proj_stream = nullptr;
+    cudaEvent_t ev_proj_fork = nullptr, ev_proj_join = nullptr;
     // ---- training-phase forward + loss (gcpb200_forward_loss)
     bool has_train = false;
     DevMat dec1t, dec2xt, dec2st, dec3t;          // decoder layers 1-3 without BatchNorm folding
@@ -1142,6 +1146,9 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_prep_fork, cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_prep_join, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->proj_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_proj_fork, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_proj_join, cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->seq_stream, cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_fork, cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_seq_join, cudaEventDisableTiming);
@@ -1186,6 +1193,9 @@ extern "C" void gcpb200_destroy(gcpb200_ctx* c) {
     if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
     if (c->ev_prep_fork) cudaEventDestroy(c->ev_prep_fork);
     if (c->ev_prep_join) cudaEventDestroy(c->ev_prep_join);
+    if (c->proj_stream) cudaStreamDestroy(c->proj_stream);
+    if (c->ev_proj_fork) cudaEventDestroy(c->ev_proj_fork);
+    if (c->ev_proj_join) cudaEventDestroy(c->ev_proj_join);
     if (c->seq_stream) cudaStreamDestroy(c->seq_stream);
     if (c->ev_seq_fork) cudaEventDestroy(c->ev_seq_fork);
     if (c->ev_seq_join) cudaEventDestroy(c->ev_seq_join);
@@ -1604,6 +1614,30 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         const GemmDyn dynv = {c->tree_rows + l, 0};
         const GemmDyn* dyn = pruned ? &dynv : nullptr;
         const int rows = Bp << l;
+        // split-linear projections of the parents' LSTM state
+        auto project = [&](cudaStream_t s) -> int {
+            Seg a = seg(c->hid, 0, HID, ROW_LEFT), b = seg(c->hid, 0, HID, ROW_RIGHT);
+            const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
+            a.group_cols = b.group_cols = HID;
+            for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
+            // Both halves are stored as bf16.  Measured (profiles/r2i_fp32_cell_state.txt): keeping the projected cell state
+            // in fp32 (split_col = 3 * HID -> an fp32 array read by the LSTM epilogue) leaves the latent error where it is
+            // (max-rel 7.5e-3 either way: it is the bf16 rounding of the GEMM OPERANDS, which the SIMT cross-check kernels
+            // with fp32 accumulation reproduce) and costs 1.2 ms per 1024-candidate rollout in extra HBM traffic.
+            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
+            return gemm(c, s, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e, 0, -1, dyn);
+        };
+        // A level whose row tiles do not fill the GPU is a chain of latency-bound launches: its projection GEMM (which needs
+        // only the parents' state, complete since the previous level) runs beside the prior -> reparametrisation -> embed
+        // chain on a side stream.  Not at level 0 (the parents' state comes from the initializer below) and not in the
+        // training phase (one more chain, the posterior, shares the buffers in a different order).
+        const bool proj_aside = l > 0 && post == nullptr && (rows >> 7) <= c->sms && !c->use_ref;
+        if (proj_aside) {
+            GCP_CUDA_CHECK(cudaEventRecord(c->ev_proj_fork, st));
+            GCP_CUDA_CHECK(cudaStreamWaitEvent(c->proj_stream, c->ev_proj_fork, 0));
+            CHECK(project(c->proj_stream));
+            GCP_CUDA_CHECK(cudaEventRecord(c->ev_proj_join, c->proj_stream));
+        }
         // prior p(z | e_l, e_r) and reparametrisation
         const std::vector<Seg> par = {seg(c->lat, 0, NZ_ENC, ROW_LEFT), seg(c->lat, 0, NZ_ENC, ROW_RIGHT)};
         CHECK(mlp_body(c, st, L.prior, rows, g, par, dyn));
@@ -1638,19 +1672,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             CHECK(gemm(c, st, rows, g, {seg(c->tb, 0, L.init.mid_k)}, L.init_head_r, 256, EPI_LINEAR,
                        epi_linear(ACT_NONE, c->hid.p + (size_t)goal_row0 * STATE, STATE, nullptr, 0, STATE), 0, -1, dyn));
         }
-        // split-linear projections of the parents' LSTM state
-        {
-            Seg a = seg(c->hid, 0, HID, ROW_LEFT), b = seg(c->hid, 0, HID, ROW_RIGHT);
-            const int gc[6] = {0, 2 * HID, 4 * HID, HID, 3 * HID, 5 * HID};
-            a.group_cols = b.group_cols = HID;
-            for (int q = 0; q < 6; ++q) a.group_col[q] = b.group_col[q] = gc[q];
-            // Both halves are stored as bf16.  Measured (profiles/r2i_fp32_cell_state.txt): keeping the projected cell state
-            // in fp32 (split_col = 3 * HID -> an fp32 array read by the LSTM epilogue) leaves the latent error where it is
-            // (max-rel 7.5e-3 either way: it is the bf16 rounding of the GEMM OPERANDS, which the SIMT cross-check kernels
-            // with fp32 accumulation reproduce) and costs 1.2 ms per 1024-candidate rollout in extra HBM traffic.
-            EpiParams e = epi_linear(ACT_NONE, c->sh.p, 6 * HID, nullptr, 0, 6 * HID);
-            CHECK(gemm(c, st, rows, g, {a, b}, L.proj, 256, EPI_LINEAR, e, 0, -1, dyn));
-        }
+        if (!proj_aside) CHECK(project(st));
         // embed
         {
             EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
@@ -1658,6 +1680,7 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
             e.rowbias_ld = (c->tied ? 1 : c->depth) * HID;
             CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e, 0, -1, dyn));
         }
+        if (proj_aside) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_proj_join, 0));
         // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
         DevBuf* xin = &c->xa;
         DevBuf* xout = &c->xb;

@@ -55,11 +55,11 @@ class DeviceRollouts:
             lat = eng.prune_gather(take(self.e_df), end_sel)
         if append_latent:
             img = torch.cat([img, lat], -1)
-        # the reference pads these two to the longest sequence of the batch (pad_sequence, base_gcp.py:242): actions
-        # [B, lmax - 1], states [B, lmax]; the device buffers are full length when the length sync was deferred
-        lmax = self.outputs["_lmax"]()
-        act = take(self.outputs.actions)[:, :lmax - 1]
-        sta = take(self.outputs.regressed_state)[:, :lmax]
+        # the reference pads these two to the longest sequence of the batch (pad_sequence, base_gcp.py:242); every list entry
+        # below is cut to its own length anyway, so the full-length device buffers are copied as they are: the pinned
+        # staging shapes then never change between calls (a new shape is a fresh cudaHostAlloc, milliseconds per plan)
+        act = take(self.outputs.actions)
+        sta = take(self.outputs.regressed_state)
 
         def pinned(t):
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -69,10 +69,11 @@ class DeviceRollouts:
         torch.cuda.current_stream(self.end_ind.device).synchronize()
         img, lat, act, sta = img.numpy(), lat.numpy(), act.numpy(), sta.numpy()
         out = AttrDict(predictions=[], actions=[], states=[], latents=[])
+        lmax = max(ends) + 1            # the reference's padded length: its action tensor has lmax - 1 steps
         for n, i in enumerate(sel):
             L = ends[i] + 1
             out.predictions.append(img[n, :L])
-            out.actions.append(act[n, :L])
+            out.actions.append(act[n, :min(L, lmax - 1)])
             out.states.append(sta[n, :L])
             out.latents.append(lat[n, :L])
         return out
