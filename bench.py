@@ -444,18 +444,44 @@ def main():
             def plan():
                 return pl2(state_t, goal_t)
 
-            plan()
+            keep = [plan(), plan()]      # warm-up; results held as a policy holds the current plan
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
+            import gc
+            gc.collect()
+            gc.disable()          # as in timed(): a generation-2 collection of this process's heap is 10-40 ms, one plan is 15
             t0 = time.perf_counter()
             n_plans, plan_ms = 3, []
+            marks = []
+            if trace:       # BENCH_TRACE=1: synchronised host time of every stage of the call (diagnostic, slows the call)
+                def wrap(obj, name, label):
+                    fn = getattr(obj, name)
+
+                    def inner(*a, **k):
+                        torch.cuda.synchronize()
+                        t_in = time.perf_counter()
+                        res = fn(*a, **k)
+                        torch.cuda.synchronize()
+                        marks.append("%s %.2f" % (label, (time.perf_counter() - t_in) * 1e3))
+                        return res
+                    setattr(obj, name, inner)
+                from video_gcp_b200.planning import cem_simulator as _cs
+                wrap(pl2, "cem_iteration", "iter"), wrap(pl2, "_elite_samples", "elite_z"), wrap(pl2, "_rollout_host", "final")
+                wrap(sim, "rollout_device", "rollout_device"), wrap(_cs.DeviceRollouts, "to_host", "to_host")
             for _ in range(n_plans):
+                a0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
                 t1 = time.perf_counter()
                 frames, actions, latents, score = plan()      # returns host arrays: the call itself synchronises
                 plan_ms.append(round((time.perf_counter() - t1) * 1e3, 3))
+                if trace:
+                    print("[plan] %.2f ms | %s | cudaMalloc +%d" % (plan_ms[-1], ", ".join(marks),
+                                                                   torch.cuda.memory_stats().get("num_device_alloc", 0) - a0), file=sys.stderr)
+                    marks.clear()
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            gc.enable()
+            del keep
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dt = float(dt.item()) / n_plans

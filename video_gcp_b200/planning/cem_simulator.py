@@ -35,8 +35,8 @@ class DeviceRollouts:
     def to_host(self, append_latent, idx=None):
         """AttrDict(predictions, actions, states, latents) of numpy lists, for candidates `idx` (default all).
         One device-side gather per field, one D2H copy per field into pinned host memory (a pageable destination costs
-        ~10x the copy time at 250 MB of elite frames); the per-candidate arrays are views of those host blocks, which stay
-        alive as long as any of the arrays does."""
+        ~10x the copy time at 250 MB of elite frames); above 16 MB the per-candidate arrays are views of those host blocks,
+        which stay alive as long as any of the arrays does; a smaller result (the plan) is copied out of them."""
         if not getattr(self, "has_heads", True):
             raise RuntimeError("this rollout was made cost-only (planner_mode heads=False): it carries no frames / actions / states")
         eng = self.model.engine
@@ -68,13 +68,18 @@ class DeviceRollouts:
         img, lat, act, sta = pinned(img), pinned(lat), pinned(act), pinned(sta)
         torch.cuda.current_stream(self.end_ind.device).synchronize()
         img, lat, act, sta = img.numpy(), lat.numpy(), act.numpy(), sta.numpy()
+        if img.nbytes <= (16 << 20):
+            # a plan-sized result leaves the staging blocks at once (0.3 ms of host memcpy): arrays that are views of pinned
+            # blocks keep them out of the host allocator's cache for as long as the caller holds the plan, and every
+            # block that is missing when the next plan arrives is a cudaHostAlloc (2-45 ms measured)
+            img, lat, act, sta = img.copy(), lat.copy(), act.copy(), sta.copy()
         out = AttrDict(predictions=[], actions=[], states=[], latents=[])
-        lmax = max(ends) + 1            # the reference's padded length: its action tensor has lmax - 1 steps
+        lmax = self.outputs["_lmax"]()  # the reference's padded length: its action tensor has lmax - 1 steps
         for n, i in enumerate(sel):
             L = ends[i] + 1
             out.predictions.append(img[n, :L])
             out.actions.append(act[n, :min(L, lmax - 1)])
-            out.states.append(sta[n, :L])
+            out.states.append(sta[n, :min(L, lmax)])
             out.latents.append(lat[n, :L])
         return out
 
