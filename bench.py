@@ -153,6 +153,17 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)", 1650.0
 
 
+def pick_peak(clk, sustained, burst, src):
+    """Roofline denominator for a kernel timed inside the step.  MEASURED_PEAKS.json holds two tensor figures: `burst`
+    (best single matmul, SM clock at its maximum) and `sustained` (matmuls back to back for seconds, by which time the power
+    cap has pulled the SM clock to ~1.25 GHz).  The timed region here is K steps of ~14 ms: when the sampled SM clock stayed
+    within 10 % of its maximum the GPU was in the burst regime and the burst figure is the honest (larger) denominator;
+    otherwise the sustained one.  Both fractions are reported either way."""
+    if clk and clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.9 * clk["sm_max_mhz"]:
+        return burst, src.replace("sustained", "burst: SM clock %.0f of %.0f MHz during the timed region" % (clk["sm_mhz"], clk["sm_max_mhz"]))
+    return sustained, src
+
+
 _ORIG_AFFINITY = None
 
 
@@ -535,6 +546,7 @@ def main():
     value = N * args.steps / (ms * 1e-3)
     e2e_value = N * args.steps / (ms_e2e * 1e-3)
     phase_ms = {p: round(prof[p] / 2, 3) for p in eng.PHASES}
+    peak_used, peak_src_used = pick_peak(clk, peak_tf, peak_burst, peak_src)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "step_ms": step_ms, "step_ms_e2e": step_ms_e2e, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -550,20 +562,23 @@ def main():
                         "reference planner does with np.random); costs + elite ids copied back every step"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "dec_tail3_kernel", "achieved": tail_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": tail_tf / peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "dec_tail3_kernel", "achieved": tail_tf, "peak": peak_used,
+                     "unit": "TFLOP/s", "frac": tail_tf / peak_used,
+                     "frac_of_burst": tail_tf / peak_burst, "frac_of_sustained": tail_tf / peak_tf,
                      "executed": {"achieved": tail_tf * TAIL_EXECUTED_FLOP_PER_IMAGE / TAIL_FLOP_PER_IMAGE,
-                                  "frac": tail_tf * TAIL_EXECUTED_FLOP_PER_IMAGE / TAIL_FLOP_PER_IMAGE / peak_tf,
+                                  "frac": tail_tf * TAIL_EXECUTED_FLOP_PER_IMAGE / TAIL_FLOP_PER_IMAGE / peak_used,
                                   "frac_of_burst": tail_tf * TAIL_EXECUTED_FLOP_PER_IMAGE / TAIL_FLOP_PER_IMAGE / peak_burst,
                                   "note": "tcgen05 FLOPs actually issued (29.36 MFLOP/image vs 32.51 canonical: shared "
                                           "skip half + unused mixture-scale channels are not computed)"},
                      "traffic": TAIL_TRAFFIC_BYTES_B1024 if chunk == 1024 else None,
                      "traffic_note": "bytes per launch, ncu dram read+write (profiles/r2o_dec_tail3_ncu_full.txt)",
-                     "peak_source": peak_src,
+                     "peak_source": peak_src_used,
                      "ms_per_launch": tail_ms, "images_per_launch": tail_imgs},
-        "roofline_step": {"bound": "tensor", "achieved": value / world * FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf,
+        "roofline_step": {"bound": "tensor", "achieved": value / world * FLOP_PER_ROLLOUT / 1e12, "peak": peak_used,
                           "unit": "TFLOP/s per GPU (canonical 16.75 GFLOP/rollout)",
-                          "frac": value / world * FLOP_PER_ROLLOUT / 1e12 / peak_tf},
+                          "frac": value / world * FLOP_PER_ROLLOUT / 1e12 / peak_used,
+                          "frac_of_burst": value / world * FLOP_PER_ROLLOUT / 1e12 / peak_burst,
+                          "frac_of_sustained": value / world * FLOP_PER_ROLLOUT / 1e12 / peak_tf},
         "phase_ms_per_step": phase_ms,
     }
     out.update(extras)
@@ -649,6 +664,7 @@ def main_seq(args):
             dist.destroy_process_group()
         return
     peak_tf, peak_hbm, peak_src, peak_burst = measured_peaks()
+    peak_used, peak_src_used = pick_peak(clk, peak_tf, peak_burst, peak_src)
     value = N * args.steps / (ms * 1e-3)
     rec_ms = prof["tree_recursion"] / 2
     print(json.dumps({
@@ -661,8 +677,11 @@ def main_seq(args):
                 "d2h_bytes_per_step": int(N * 4 + k * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "199-step recurrence (prior MLP + reparametrisation + 3 LSTM cells + output)",
-                     "achieved": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12 / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "achieved": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12, "peak": peak_used, "unit": "TFLOP/s",
+                     "frac": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12 / peak_used,
+                     "frac_of_burst": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12 / peak_burst,
+                     "frac_of_sustained": value / world * SEQ_FLOP_PER_ROLLOUT / 1e12 / peak_tf, "traffic": None,
+                     "peak_source": peak_src_used,
                      "note": "whole-step canonical FLOPs (2 x 9.76 GMAC per rollout) over the step time"},
         "phase_ms_per_step": {p: round(prof[p] / 2, 3) for p in eng.PHASES}, "recurrence_ms": rec_ms,
     }))
