@@ -33,7 +33,10 @@
  * host; the caller owns all I/O buffers, the context owns packed weights and workspace; every call is
  * stream-ordered on `stream` (a cudaStream_t passed as void*) and never synchronises the device; return
  * value 0 = success, non-zero = error with the message available from gcpb200_last_error(); no C++
- * exception crosses this boundary.  One context per (device, host thread).
+ * exception crosses this boundary.  One context per (device, host thread).  gcpb200_rollout forks work onto streams
+ * the context owns (noise upload, per-call decoder constants, projection GEMMs of small tree levels) and joins every
+ * one of them back into `stream` by events before the results that depend on them: to the caller the call is ordered
+ * on `stream` alone.
  */
 #ifndef GCPB200_H
 #define GCPB200_H
