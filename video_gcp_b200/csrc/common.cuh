@@ -52,6 +52,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without release semantics: for barriers that order tcgen05 work only (an accumulator buffer handed back to the MMA
+// issuer after tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The default .release form makes the compiler put a
+// MEMBAR in front of the arrive, which waits for every global store of the epilogue to be acknowledged -- measured as a
+// fifth of the LSTM epilogue's time (profiles/r2aj_lstm_epilogue_ncu.txt) -- although nothing that is ordered through
+// these barriers reads those stores.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -209,6 +217,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
 // arrive (release, cluster scope) on an mbarrier given by its shared::cluster address (own or peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tiled load into THIS CTA's shared memory whose completion is counted on an mbarrier of either CTA of the pair
 // (`bar_cluster_addr`: shared::cluster address, e.g. the leader's full barrier)

@@ -274,6 +274,27 @@ __device__ __forceinline__ void epilogue_math_fast(const EpiParams& p, int col0,
     }
 }
 
+// torch.nn.LSTMCell update of 8 hidden units from their packed gate pre-activations [i(8) | f(8) | g(8) | o(8)].
+// One MUFU op per gate (tanh.approx.f32; sigmoid(x) = 0.5 * tanh(x / 2) + 0.5) instead of ex2 + rcp: the cell update
+// is MUFU-bound (5 instead of 10 ops per hidden unit), and a gate GEMM tile's epilogue is as long as its MMAs.
+// tanh.approx: max relative error 2^-11, below the bf16 rounding (2^-9) of the h / c that leave this epilogue.
+__device__ __forceinline__ void lstm_cell_update(const float (&acc)[32], const float (&cprev)[8], float (&h)[8], float (&c)[8],
+                                                 uint4& hv, uint4& cv) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float ig = fmaf(0.5f, tanh_mufu(0.5f * acc[u]), 0.5f);
+        const float fg = fmaf(0.5f, tanh_mufu(0.5f * acc[8 + u]), 0.5f);
+        const float gg = tanh_mufu(acc[16 + u]);
+        const float og = fmaf(0.5f, tanh_mufu(0.5f * acc[24 + u]), 0.5f);
+        c[u] = fg * cprev[u] + ig * gg;
+        h[u] = og * tanh_mufu(c[u]);
+    }
+    hv.x = pack_bf16x2(h[0], h[1]); hv.y = pack_bf16x2(h[2], h[3]);
+    hv.z = pack_bf16x2(h[4], h[5]); hv.w = pack_bf16x2(h[6], h[7]);
+    cv.x = pack_bf16x2(c[0], c[1]); cv.y = pack_bf16x2(c[2], c[3]);
+    cv.z = pack_bf16x2(c[4], c[5]); cv.w = pack_bf16x2(c[6], c[7]);
+}
+
 // row: row of this launch (compact when the level is pruned); lrow: the row it stands for in the full level
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int lrow, int col0,
@@ -404,24 +425,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGe
                 cprev[2 * i + 1] = t.y;
             }
         }
-        // One MUFU op per gate (tanh.approx.f32; sigmoid(x) = 0.5 * tanh(x / 2) + 0.5) instead of ex2 + rcp: the cell update
-        // is MUFU-bound (5 instead of 10 ops per hidden unit), and a gate GEMM tile's epilogue is as long as its MMAs.
-        // tanh.approx: max relative error 2^-11, below the bf16 rounding (2^-9) of the h / c that leave this epilogue.
         float h[8], c[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float ig = fmaf(0.5f, tanh_mufu(0.5f * acc[u]), 0.5f);
-            const float fg = fmaf(0.5f, tanh_mufu(0.5f * acc[8 + u]), 0.5f);
-            const float gg = tanh_mufu(acc[16 + u]);
-            const float og = fmaf(0.5f, tanh_mufu(0.5f * acc[24 + u]), 0.5f);
-            c[u] = fg * cprev[u] + ig * gg;
-            h[u] = og * tanh_mufu(c[u]);
-        }
         uint4 hv, cv;
-        hv.x = pack_bf16x2(h[0], h[1]); hv.y = pack_bf16x2(h[2], h[3]);
-        hv.z = pack_bf16x2(h[4], h[5]); hv.w = pack_bf16x2(h[6], h[7]);
-        cv.x = pack_bf16x2(c[0], c[1]); cv.y = pack_bf16x2(c[2], c[3]);
-        cv.z = pack_bf16x2(c[4], c[5]); cv.w = pack_bf16x2(c[6], c[7]);
+        lstm_cell_update(acc, cprev, h, c, hv, cv);
         *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.out_bf16_ld + u0) = hv;
         if (cf != nullptr) {
             cf[0] = make_float4(c[0], c[1], c[2], c[3]);
@@ -600,17 +606,82 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const bool pair_fast = kPair && args.epi.rowbias == nullptr && args.epi.split_col == 0 && args.epi.out_f32 == nullptr &&
                                args.epi.out_bf16 != nullptr && args.epi.n_valid >= args.N &&
                                (EPI != EPI_GN || (args.epi.gn_group == 16 && args.N <= 256));
+        // LSTM gate GEMMs with bf16 previous cell state (what the rollouts run): drain with prefetched operands, see below
+        constexpr bool kLstmFast = (EPI == EPI_LSTM) && (CH_PER_WARP * 32 == 128);
+        const bool lstm_fast = kLstmFast && args.epi.c_f32 == nullptr && args.epi.bias != nullptr;
+        float* lstm_bias_sm = reinterpret_cast<float*>(store_stage + (warp - 2) * 128);
         const int row_in_tile = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
         for (int work = work0; work < n_work; work += work_stride) {
             const int grp = work / tiles_n, tile_n = work - grp * tiles_n;
             const int tile_m = grp * (int)C + (int)crank;
-            mbar_wait(&tmem_full[as], aphase);
-            tc_fence_after();
             const int row = tile_m * GEMM_BM + row_in_tile;
             const int lrow = listed_tile(args.g, tile_m) * GEMM_BM + row_in_tile;
+            // LSTM epilogue: everything a tile's cell update needs besides the accumulator -- this warp's 128 gate biases
+            // (staged in its 2 KB of shared memory: every row adds the same ones), the row's previous cell state, its
+            // slot row in the state array (an integer division) -- is fetched BEFORE waiting for the accumulator, so the
+            // global-load latency overlaps the tile's MMAs instead of sitting in the drain (measured: the bias and c_prev
+            // loads were half of the drain's stall samples, profiles/r2aj_lstm_epilogue_ncu.txt)
+            uint4 lstm_cp[kLstmFast ? CH_PER_WARP : 1];
+            bf16 *lstm_out = nullptr, *lstm_hid = nullptr;
+            if (kLstmFast && lstm_fast) {
+                const int colw = tile_n * BN + half * CH_PER_WARP * 32;      // this warp's first packed column
+                const float4 bl = __ldg(reinterpret_cast<const float4*>(args.epi.bias + colw) + lane);
+                const bf16* cpr = args.epi.c_prev + (size_t)row * args.epi.c_prev_ld + args.epi.c_prev_col0 + (colw >> 2);
+#pragma unroll
+                for (int k = 0; k < CH_PER_WARP; ++k) lstm_cp[k] = __ldg(reinterpret_cast<const uint4*>(cpr + k * 8));
+                lstm_out = args.epi.out_bf16 + (size_t)row * args.epi.out_bf16_ld + (colw >> 2);
+                if (args.epi.write_hid)
+                    lstm_hid = args.epi.hid + (size_t)map_row(args.g, ROW_SELF, lrow) * args.epi.hid_ld + args.epi.hid_col0 + (colw >> 2);
+                __syncwarp();                                   // the previous tile's reads of the staged biases are done
+                reinterpret_cast<float4*>(lstm_bias_sm)[lane] = bl;
+                __syncwarp();
+            }
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+            if (kLstmFast && lstm_fast) {
+                // (operands fetched above, before the wait) drain: bias from shared memory, cell update, stores
+#pragma unroll
+                for (int k = 0; k < CH_PER_WARP; ++k) {
+                    float acc[32];
+                    __syncwarp();
+                    tmem_ld32(t0 + (half * CH_PER_WARP + k) * 32, acc);
+                    if (k == CH_PER_WARP - 1) {      // the accumulator buffer goes back as soon as it is in registers
+                        tc_fence_before();
+                        if (PAIR) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                        } else {
+                            mbar_arrive_relaxed(&tmem_empty[as]);
+                        }
+                    }
+                    const float4* b4 = reinterpret_cast<const float4*>(lstm_bias_sm) + k * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b4[i];
+                        acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+                    }
+                    float cprev[8], h[8], c[8];
+                    const __nv_bfloat162* cp2 = reinterpret_cast<const __nv_bfloat162*>(&lstm_cp[k]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 t = __bfloat1622float2(cp2[i]);
+                        cprev[2 * i] = t.x;
+                        cprev[2 * i + 1] = t.y;
+                    }
+                    uint4 hv, cv;
+                    lstm_cell_update(acc, cprev, h, c, hv, cv);
+                    *reinterpret_cast<uint4*>(lstm_out + k * 8) = hv;
+                    if (args.epi.write_hid) {
+                        *reinterpret_cast<uint4*>(lstm_hid + k * 8) = hv;
+                        *reinterpret_cast<uint4*>(lstm_hid + k * 8 + args.epi.hidden) = cv;
+                    }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                continue;
+            }
             if (kPair && pair_fast) {
                 // both chunks of this thread at once; the accumulator buffer is released as soon as they are in registers
                 float a0[32], a1[32];
@@ -620,9 +691,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 tc_fence_before();
                 if (PAIR) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                    if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[as]), 0));
                 } else {
-                    mbar_arrive(&tmem_empty[as]);
+                    mbar_arrive_relaxed(&tmem_empty[as]);
                 }
                 const int c0 = tile_n * BN + ch0 * 32;
                 epilogue_math_fast<EPI>(args.epi, c0, a0, gn_sm);
@@ -646,9 +717,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tc_fence_before();
             if (PAIR) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[as]), 0));
             } else {
-                mbar_arrive(&tmem_empty[as]);
+                mbar_arrive_relaxed(&tmem_empty[as]);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
