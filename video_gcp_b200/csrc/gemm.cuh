@@ -296,28 +296,48 @@ __device__ __forceinline__ void lstm_cell_update(const float (&acc)[32], const f
 }
 
 // row: row of this launch (compact when the level is pruned); lrow: the row it stands for in the full level
+// bias_sm: the chunk's 32 biases staged in shared memory, rb: the row's 32 row-bias values already in registers (both
+// fetched by the caller before it waited for the accumulator); null: read them from global memory here.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const LevelGeom& g, int row, int lrow, int col0,
-                                               float (&acc)[32], uint4* stage = nullptr, const float* gn_sm = nullptr) {
+                                               float (&acc)[32], uint4* stage = nullptr, const float* gn_sm = nullptr,
+                                               const float* bias_sm = nullptr, const float4* rb = nullptr) {
     const int cand = lrow % g.Bp;
     if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        if (bias_sm != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_sm);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(b4 + i);
-            acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = b4[i];
+                acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+            }
+        } else {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(b4 + i);
+                acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+            }
         }
     }
     if (EPI == EPI_LINEAR || EPI == EPI_GN) {
         if (col0 >= p.n_valid) return;
         const int nvalid = min(32, p.n_valid - col0);
         if (p.rowbias != nullptr) {
-            const int rc = p.rowbias_idx != nullptr ? __ldg(p.rowbias_idx + row) : cand;
-            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)rc * p.rowbias_ld + col0);
+            if (rb != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(rb + i);
-                acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = rb[i];
+                    acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+                }
+            } else {
+                const int rc = p.rowbias_idx != nullptr ? __ldg(p.rowbias_idx + row) : cand;
+                const float4* rg = reinterpret_cast<const float4*>(p.rowbias + (size_t)rc * p.rowbias_ld + col0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = __ldg(rg + i);
+                    acc[4 * i] += b.x; acc[4 * i + 1] += b.y; acc[4 * i + 2] += b.z; acc[4 * i + 3] += b.w;
+                }
             }
         }
         if (EPI == EPI_GN) {
@@ -470,6 +490,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     uint4* store_stage = reinterpret_cast<uint4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
+    // per epilogue warp: the biases of the columns it drains (up to 128), staged before the accumulator wait
+    __shared__ __align__(16) float bias_stage[GEMM_EPI_WARPS * 128];
     // EPI_GN: GroupNorm scale / shift of all N <= 256 columns (weights, so reading them before pdl_wait() is safe)
     __shared__ __align__(16) float gn_sm[EPI == EPI_GN ? 512 : 4];
     if (EPI == EPI_GN && args.N <= 256) {
@@ -609,7 +631,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // LSTM gate GEMMs with bf16 previous cell state (what the rollouts run): drain with prefetched operands, see below
         constexpr bool kLstmFast = (EPI == EPI_LSTM) && (CH_PER_WARP * 32 == 128);
         const bool lstm_fast = kLstmFast && args.epi.c_f32 == nullptr && args.epi.bias != nullptr;
-        float* lstm_bias_sm = reinterpret_cast<float*>(store_stage + (warp - 2) * 128);
+        float* lstm_bias_sm = bias_stage + (warp - 2) * 128;
+        float* const bias_sm_w = lstm_bias_sm;
         const int row_in_tile = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
@@ -637,6 +660,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 __syncwarp();                                   // the previous tile's reads of the staged biases are done
                 reinterpret_cast<float4*>(lstm_bias_sm)[lane] = bl;
                 __syncwarp();
+            }
+            // generic drain: the same idea -- this warp's biases staged in shared memory and the row bias of its first
+            // chunk in registers before the wait; the row bias of chunk k + 1 is requested before chunk k is processed
+            const bool gen_pref = !(kLstmFast && lstm_fast) && !(kPair && pair_fast) && EPI != EPI_LSTM;
+            const bool rb_pref = gen_pref && BN == 256 && (EPI == EPI_LINEAR || EPI == EPI_GN) && args.epi.rowbias != nullptr;
+            float4 rbn[8];
+            const float* rb_row = nullptr;
+            if (gen_pref) {
+                constexpr int WCOLS = CH_PER_WARP * 32;
+                const int colw = tile_n * BN + half * WCOLS;
+                if (args.epi.bias != nullptr) {
+                    float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane < WCOLS / 4) bl = __ldg(reinterpret_cast<const float4*>(args.epi.bias + colw) + lane);
+                    __syncwarp();
+                    if (lane < WCOLS / 4) reinterpret_cast<float4*>(bias_sm_w)[lane] = bl;
+                    __syncwarp();
+                }
+                if (rb_pref) {
+                    const int rc = args.epi.rowbias_idx != nullptr ? __ldg(args.epi.rowbias_idx + row) : lrow % args.g.Bp;
+                    rb_row = args.epi.rowbias + (size_t)rc * args.epi.rowbias_ld;
+                    if (colw < args.epi.n_valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rbn[i] = __ldg(reinterpret_cast<const float4*>(rb_row + colw) + i);
+                    }
+                }
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
@@ -709,10 +757,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll 1
             for (int ch = half * CH_PER_WARP; ch < (half + 1) * CH_PER_WARP; ++ch) {
                 float acc[32];
+                float4 rbc[8];
+                const int col0 = tile_n * BN + ch * 32;
+                if (rb_pref) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rbc[i] = rbn[i];
+                    if (ch + 1 < (half + 1) * CH_PER_WARP && col0 + 32 < args.epi.n_valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rbn[i] = __ldg(reinterpret_cast<const float4*>(rb_row + col0 + 32) + i);
+                    }
+                }
                 __syncwarp();
                 tmem_ld32(t0 + ch * 32, acc);
-                epilogue_chunk<EPI>(args.epi, args.g, row, lrow, tile_n * BN + ch * 32, acc, store_stage + (warp - 2) * 128,
-                                    (EPI == EPI_GN && args.N <= 256) ? gn_sm : nullptr);
+                epilogue_chunk<EPI>(args.epi, args.g, row, lrow, col0, acc, store_stage + (warp - 2) * 128,
+                                    (EPI == EPI_GN && args.N <= 256) ? gn_sm : nullptr,
+                                    (gen_pref && args.epi.bias != nullptr) ? bias_sm_w + (ch - half * CH_PER_WARP) * 32 : nullptr,
+                                    rb_pref ? rbc : nullptr);
             }
             tc_fence_before();
             if (PAIR) {
