@@ -88,7 +88,7 @@ struct LevelW {
     Mlp q;                // approximate posterior q(z | e_l, e_r, e_tilde) (training path only; tree/inference.py:16-36)
     Mlp init;             // level 0 only; head rows [0,3072) -> left state, [3072,6144) -> right state
     DevMat init_head_r;   // second half of the init head
-    DevMat proj, embed_main, lstm[3], out;   // the embed layer's context columns: gcpb200_ctx::embed_ctx_all
+    DevMat proj, embed_main, lstm[3], out;
 };
 
 struct gcpb200_ctx {
@@ -104,7 +104,6 @@ struct gcpb200_ctx {
     std::vector<void*> allocs;
     // weights
     LevelW lvl[8];
-    DevMat embed_ctx_all;   // the context columns of every level's embed layer, stacked: [n_lvl * HID][2 * NZ_ENC]
     SeqW seqw;
     int model = 0, n_slots = 257, lstm_hid = 512;
     // tree shape (gcpb200_config.hierarchy_levels / max_seq_len / tied_layers): 25-room = 8 levels, 255 nodes, 200 frames, one
@@ -745,7 +744,12 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     const gcpb200_tensor* be = ws.get(sp + "embed.bias", 1);
     if (!we || !be) return -1;
     const int EIN = 4 * NZ_ENC + NZ_VAE;   // 768 = [e_l, e_r, z, e_0, e_g]
-    CHECK(upload_mat(c, &L.embed_main, HID, 2 * NZ_ENC + NZ_VAE, [&](int n, int k) { return we->data[(size_t)n * EIN + k]; }, nullptr));
+    // all 768 input columns in the reference's order [e_l, e_r, z, e_0, e_g]: the context columns are two more K segments
+    // of the embed GEMM (ROW_CAND rows of the latent array).  Hoisting them into a per-candidate row bias saved a third of
+    // this GEMM's MMAs and cost more than that in its epilogue: a row-bias read is 32 scattered 16-byte loads per warp
+    // instruction, and the embed GEMM (K = 512) was epilogue-bound at 3x its memory time (profiles/r2aq_embed.txt)
+    CHECK(upload_mat(c, &L.embed_main, HID, EIN, [&](int n, int k) { return we->data[(size_t)n * EIN + k]; },
+                     [&](int n) { return be->data[n]; }));
     for (int i = 0; i < N_LSTM; ++i) CHECK(pack_lstm_cell(c, ws, sp + "lstm." + std::to_string(i) + ".", HID, &L.lstm[i]));
     const gcpb200_tensor* wo = ws.get(sp + "output.weight", 2);
     const gcpb200_tensor* bo = ws.get(sp + "output.bias", 1);
@@ -755,22 +759,6 @@ static int pack_level(gcpb200_ctx* c, const WStore& ws, int l) {
     return 0;
 }
 
-// The context term of every level's embed layer, W_e[:, 512:768] [e_0, e_g] + b_e, depends on the start / goal encodings
-// only: the weights of all levels are stacked so that ONE GEMM per rollout produces the per-candidate row bias of every level.
-static int pack_embed_context(gcpb200_ctx* c, const WStore& ws) {
-    const int n_lvl = c->tied ? 1 : c->depth;
-    const int EIN = 4 * NZ_ENC + NZ_VAE;
-    std::vector<const gcpb200_tensor*> we(n_lvl), be(n_lvl);
-    for (int l = 0; l < n_lvl; ++l) {
-        const std::string sp = (c->tied ? std::string("tree_module.") : "tree_module.tree_modules." + std::to_string(l) + ".") + "subgoal_pred.";
-        we[l] = ws.get(sp + "embed.weight", 2);
-        be[l] = ws.get(sp + "embed.bias", 1);
-        if (!we[l] || !be[l]) return -1;
-    }
-    return upload_mat(c, &c->embed_ctx_all, n_lvl * HID, 2 * NZ_ENC,
-                      [&](int n, int k) { return we[n / HID]->data[(size_t)(n % HID) * EIN + 2 * NZ_ENC + NZ_VAE + k]; },
-                      [&](int n) { return be[n / HID]->data[n % HID]; });
-}
 
 // Training-only tensors: BatchNorm affine terms (batch statistics are computed on the fly), the conv-1d inference
 // encoder (blox/torch/subnetworks.py:135-147), decoder layers 1-3 without BN folding.  The posterior MLPs are packed
@@ -1107,7 +1095,7 @@ extern "C" int gcpb200_create(gcpb200_ctx** out, const gcpb200_config* cfg) {
     c->pair_rows = (int)((c->model == GCPB200_MODEL_TREE_ADAPTIVE ? c->n_nodes : c->max_len + 1) * Bp + 256);
     rc |= make_buf(c, &c->pairs, (size_t)c->pair_rows, 256);
     rc |= make_buf(c, &c->seqb, (size_t)(c->max_len + 1) * Bp + 256, NZ_ENC);
-    rc |= dalloc(c, &c->ctxb, Bp * (size_t)std::max(c->lstm_hid, (c->tied ? 1 : c->depth) * HID));
+    rc |= dalloc(c, &c->ctxb, Bp * c->lstm_hid);
     rc |= dalloc(c, &c->logits, Bp * 256);
     rc |= dalloc(c, &c->s0, Bp * 4096);
     rc |= dalloc(c, &c->s2, Bp * 1024);
@@ -1256,7 +1244,6 @@ extern "C" int gcpb200_load_weights(gcpb200_ctx* c, const gcpb200_tensor* tensor
         CHECK(pack_sequential(c, ws));
     } else {
         for (int l = 0; l < (c->tied ? 1 : c->depth); ++l) CHECK(pack_level(c, ws, l));
-        CHECK(pack_embed_context(c, ws));
         if (c->model == GCPB200_MODEL_TREE_ADAPTIVE)
             CHECK(pack_mlp(c, ws, std::string(c->tied ? "tree_module." : "tree_module.tree_modules.0.") + "binding.distance_predictor", true, 2 * NZ_ENC, NZ_MID, 1, 128,
                            nullptr, &c->distance_pred));
@@ -1594,15 +1581,6 @@ struct PosteriorArgs {
 
 // One level of SubgoalTreeLayer.produce_tree (gcp/prediction/utils/tree_utils.py:21-44) = TreeModule.produce_subgoal on all
 // B * 2^l nodes of level l (tree_module.py:67-114): prior (+ posterior), reparametrisation, TreeLSTM, output latent.
-// Context term of the embed layer of every level, one row per candidate (see pack_embed_context); once per rollout.
-static int tree_context(gcpb200_ctx* c, cudaStream_t st, int Bp) {
-    const LevelGeom flat = {Bp, 0, c->depth};
-    const int goal_row0 = (c->n_nodes + 1) * Bp;
-    const int n = (c->tied ? 1 : c->depth) * HID;
-    return gemm(c, st, Bp, flat, {seg(c->lat, 0, NZ_ENC, ROW_LEVEL, 0), seg(c->lat, 0, NZ_ENC, ROW_LEVEL, goal_row0)},
-                c->embed_ctx_all, 256, EPI_LINEAR, epi_linear(ACT_NONE, nullptr, 0, c->ctxb, n, n));
-}
-
 static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, const float* z, float* mu_df, float* ls_df,
                       const PosteriorArgs* post, float* e_df = nullptr, bool pruned = false) {
     const int goal_row0 = (c->n_nodes + 1) * Bp;
@@ -1676,9 +1654,9 @@ static int tree_level(gcpb200_ctx* c, cudaStream_t st, int l, int B, int Bp, con
         // embed
         {
             EpiParams e = epi_linear(ACT_NONE, c->xa.p, HID, nullptr, 0, HID);
-            e.rowbias = c->ctxb + (c->tied ? 0 : l) * HID;      // this level's columns of tree_context()
-            e.rowbias_ld = (c->tied ? 1 : c->depth) * HID;
-            CHECK(gemm(c, st, rows, g, par_z, L.embed_main, 256, EPI_LINEAR, e, 0, -1, dyn));
+            const std::vector<Seg> in = {par[0], par[1], seg(c->zeta, 0, NZ_VAE), seg(c->lat, 0, NZ_ENC, ROW_CAND, 0),
+                                         seg(c->lat, 0, NZ_ENC, ROW_CAND, goal_row0)};
+            CHECK(gemm(c, st, rows, g, in, L.embed_main, 256, EPI_LINEAR, e, 0, -1, dyn));
         }
         if (proj_aside) GCP_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_proj_join, 0));
         // three LSTM cells; the new (h, c) of every non-leaf node goes to the slot-major state array
@@ -1864,7 +1842,6 @@ extern "C" int gcpb200_rollout(gcpb200_ctx* c, const gcpb200_rollout_io* io, voi
             gcp_set_error("mu_df and log_sigma_df must be given together");
             return -1;
         }
-        if (l == 0) CHECK(tree_context(c, st, Bp));
         if (tree_pruned && l == 0) {
             // the rollout length is known (sampled / injected in run_encoder_length): work lists of every level
             tree_worklists_kernel<<<c->depth, 1024, 0, st>>>(c->end_ind, B, Bp, 1, c->tree_tiles, c->tree_rows);
@@ -2096,7 +2073,6 @@ extern "C" int gcpb200_forward_loss(gcpb200_ctx* c, const gcpb200_train_io* io, 
     float* q_ls = io->q_log_sigma ? io->q_log_sigma : w.pq[3];
     {
         PosteriorArgs post = {w.inf_seq, w.tstep, q_mu, q_ls};
-        CHECK(tree_context(c, st, Bp));
         for (int l = 0; l < DEPTH; ++l) CHECK(tree_level(c, st, l, B, Bp, io->eps, p_mu, p_ls, &post));
     }
     float* e_df = io->e_df ? io->e_df : c->e_df;

@@ -21,11 +21,13 @@ namespace gcp {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_MAX_SEGS = 4;
+constexpr int GEMM_MAX_SEGS = 5;
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each takes half the columns
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
-enum RowMode { ROW_LEVEL = 0, ROW_SELF = 1, ROW_LEFT = 2, ROW_RIGHT = 3 };
+// ROW_CAND: row (node j, candidate c) of a level reads array row row_base + c -- a per-candidate array shared by all nodes
+// (the start / goal encodings in slots 0 and n_nodes + 1 of the latent array)
+enum RowMode { ROW_LEVEL = 0, ROW_SELF = 1, ROW_LEFT = 2, ROW_RIGHT = 3, ROW_CAND = 4 };
 enum EpiKind { EPI_LINEAR = 0, EPI_GN = 1, EPI_REPARAM = 2, EPI_LSTM = 3 };
 enum ActKind { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
 
@@ -120,12 +122,14 @@ __device__ __forceinline__ int tile_row0(const LevelGeom& g, int mode, int tile_
     const int tpn = g.Bp >> 7;
     const int j = tile_m / tpn;
     const int c0 = (tile_m - j * tpn) << 7;
+    if (mode == ROW_CAND) return c0;                   // caller adds row_base
     return slot_of(g, j, mode) * g.Bp + c0;
 }
 __device__ __forceinline__ int map_row(const LevelGeom& g, int mode, int row) {
     if (mode == ROW_LEVEL) return row;
     const int j = row / g.Bp;
     const int c = row - j * g.Bp;
+    if (mode == ROW_CAND) return c;
     return slot_of(g, j, mode) * g.Bp + c;
 }
 __device__ __forceinline__ int listed_tile(const LevelGeom& g, int tile_m) {
