@@ -86,3 +86,27 @@ def test_single_matches(g):
     np.testing.assert_array_equal(inds, g["match_inds"])
     np.testing.assert_array_equal(p, g["match_p"])
     np.testing.assert_array_equal(q, g["match_q"])
+
+
+def test_min_cumsum_matches_the_reference_compiled_extension():
+    """The oracle's accumulated-cost table against the reference's own native code: gcp/evaluation/cutils.pyx compiled by
+    oracle/build_ref_cutils.py (c_dtw's inner loop, dtw_utils.py:99-116).  Bit-exact on float64, incl. ragged shapes, ties,
+    a single row / column and infinities in the cost."""
+    from oracle import build_ref_cutils
+    cutils = build_ref_cutils.load()
+    if cutils is None:
+        pytest.skip("oracle/_ref/cutils*.so not built (python -m oracle.build_ref_cutils needs /root/reference)")
+    r = np.random.default_rng(3)
+    cases = [r.uniform(0, 5, size=s) for s in ((1, 1), (1, 9), (9, 1), (7, 13), (40, 31), (200, 200))]
+    cases.append(r.integers(0, 3, size=(25, 25)).astype(np.float64))        # ties
+    inf_case = r.uniform(0, 5, size=(12, 12))
+    inf_case[3, :5] = np.inf
+    cases.append(inf_case)
+    for C in cases:
+        rr, cc = C.shape
+        T = np.zeros((rr + 1, cc + 1))
+        T[0, 1:] = np.inf
+        T[1:, 0] = np.inf
+        T[1:, 1:] = C
+        cutils.min_cumsum(T)                       # in place, as c_dtw calls it
+        assert np.array_equal(T, D.min_cumsum(C)), C.shape
